@@ -1,0 +1,214 @@
+/* vlct.h -- C ABI of the B200-native VL+CT hydro/MHD block update.
+ *
+ * This is the drop-in boundary for ONE hot path of Enzo-E: the Method plugin
+ * EnzoMethodMHDVlct (van Leer predictor-corrector + constrained transport).
+ * Every entry point below replaces one piece of the reference's plugin
+ * surface; the reference file:line it stands in for is cited next to it.
+ * (All citations are relative to the reference checkout's root.)
+ *
+ * Conventions
+ *  - plain C types only: no C++/torch/CUDA types in any signature;
+ *  - every function returns an int status (VLCT_OK == 0) -- the reference
+ *    reports failures through ASSERT/ERROR macros that abort
+ *    (src/Cello/error_Error.hpp:52-59,264-273); a host adapter turns a
+ *    non-zero status + vlct_last_error() into the same ERROR(...) call;
+ *  - all field data are fp64 (enzo_float == double under
+ *    CONFIG_PRECISION_DOUBLE, src/Enzo/enzo_typedefs.hpp:14-18), stored as
+ *    C-order (z,y,x) arrays with x contiguous and ghost zones included,
+ *    exactly what Field::view<enzo_float>(name) wraps
+ *    (src/Cello/data_FieldData.cpp:1318-1383);
+ *  - a handle is NOT thread-safe: one handle per host thread / GPU, like one
+ *    Method instance per Charm++ PE.
+ *  - there is no CPU fallback: if no CUDA device is usable, vlct_create fails.
+ */
+#ifndef VLCT_H
+#define VLCT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLCT_ABI_VERSION 1
+#define VLCT_MAX_PASSIVE 16
+
+/* ---- status codes ---------------------------------------------------- */
+enum {
+  VLCT_OK = 0,
+  VLCT_ERR_INVALID_CONFIG = 1,  /* a reference ASSERT/ERROR on parameters   */
+  VLCT_ERR_INVALID_BLOCK  = 2,  /* missing field pointer / bad shape        */
+  VLCT_ERR_CUDA           = 3,  /* CUDA runtime failure (sticky)            */
+  VLCT_ERR_NO_DEVICE      = 4,  /* no usable sm_100 device: no CPU fallback */
+  VLCT_ERR_UNKNOWN_KEY    = 5,  /* vlct_config_set: unknown parameter key   */
+  VLCT_ERR_INTERNAL       = 6
+};
+
+/* ---- parameter values ------------------------------------------------ */
+/* Method:mhd_vlct:riemann_solver  (src/Enzo/hydro-mhd/riemann/EnzoRiemann.cpp:26-68) */
+enum { VLCT_RIEMANN_HLL = 0, VLCT_RIEMANN_HLLE = 1,
+       VLCT_RIEMANN_HLLC = 2, VLCT_RIEMANN_HLLD = 3 };
+/* Method:mhd_vlct:reconstruct_method
+ * (src/Enzo/hydro-mhd/toolkit/EnzoReconstructor.cpp:14-44) */
+enum { VLCT_RECON_NN = 0, VLCT_RECON_PLM_ENZO = 1, VLCT_RECON_PLM_ATHENA = 2 };
+/* Method:mhd_vlct:mhd_choice
+ * (src/Enzo/hydro-mhd/EnzoMHDIntegratorStageCommands.cpp:76-98) */
+enum { VLCT_MHD_UNSET = -1, VLCT_MHD_NO_BFIELD = 0,
+       VLCT_MHD_CONSTRAINED_TRANSPORT = 1 };
+/* Method:mhd_vlct:time_scheme (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:46-60) */
+enum { VLCT_TIME_VL = 0, VLCT_TIME_EULER = 1 };
+/* Physics:fluid_props:dual_energy:type
+ * (src/Enzo/fluid-props/EnzoDualEnergyConfig.hpp; only "disabled" and
+ *  "modern" are accepted by VL+CT, EnzoMHDIntegratorStageCommands.cpp:31-34) */
+enum { VLCT_DE_DISABLED = 0, VLCT_DE_MODERN = 1, VLCT_DE_BRYAN95 = 2 };
+enum { VLCT_MEM_HOST = 0, VLCT_MEM_DEVICE = 1 };
+
+/* The configuration the reference reads in the EnzoMethodMHDVlct constructor
+ * (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:38-152) and from
+ * Physics:fluid_props (src/Enzo/enzo-core/EnzoConfig.cpp:952-1262).
+ * Trivially copyable: this is also what a pup() routine serialises
+ * (EnzoMethodMHDVlct.cpp:170-197). */
+typedef struct vlct_config {
+  int    riemann_solver;      /* default VLCT_RIEMANN_HLLD                      */
+  int    reconstruct_method;  /* full-step reconstructor; default PLM_ENZO.
+                                 The half step ALWAYS uses NN (cpp:54-55)       */
+  double theta_limiter;       /* default 1.5, must lie in [1,2]                 */
+  int    mhd_choice;          /* REQUIRED (cpp:74-77); default VLCT_MHD_UNSET   */
+  int    time_scheme;         /* default VLCT_TIME_VL                           */
+  double courant;             /* < 0 => default (0.3 for vl, 1.0 for euler)     */
+  double gamma;               /* Physics:fluid_props:eos:gamma, default 5/3     */
+  int    dual_energy;         /* default VLCT_DE_DISABLED                       */
+  double dual_energy_eta;     /* default 0.001                                  */
+  double density_floor;       /* must be > 0 (StageCommands.cpp:37-40)          */
+  double pressure_floor;      /* must be > 0                                    */
+  int    n_passive;           /* number of fields in group "color"              */
+  int    has_acceleration;    /* 1 if acceleration_{x,y,z} fields exist
+                                 (EnzoMethodMHDVlct.cpp:219-232)                */
+} vlct_config;
+
+/* One Cello Block as seen by Method::compute / Method::timestep:
+ * the field pointers Field::view would return, the active size, the ghost
+ * depth, EnzoBlock::CellWidth (src/Enzo/enzo-core/EnzoBlock.cpp:236-245).
+ *
+ * Array shapes, with m? = n? + 2 g?:
+ *   cell-centred fields              (mz,   my,   mx)
+ *   bfieldi_x                        (mz,   my,   mx+1)
+ *   bfieldi_y                        (mz,   my+1, mx)
+ *   bfieldi_z                        (mz+1, my,   mx)
+ * Unused pointers (e.g. bfield_* in hydro mode) may be NULL. */
+typedef struct vlct_block {
+  int nx, ny, nz;
+  int gx, gy, gz;
+  double dx, dy, dz;
+  double *density;
+  double *velocity_x, *velocity_y, *velocity_z;
+  double *total_energy;          /* specific total energy                   */
+  double *internal_energy;       /* specific; only with dual energy         */
+  double *bfield_x, *bfield_y, *bfield_z;     /* cell-centred, MHD only     */
+  double *bfieldi_x, *bfieldi_y, *bfieldi_z;  /* face-centred, MHD only     */
+  double *pressure;              /* permanent scratch field, written by
+                                    timestep (EnzoMethodMHDVlct.cpp:571-573)*/
+  double *acceleration_x, *acceleration_y, *acceleration_z; /* optional      */
+  double *passive[VLCT_MAX_PASSIVE]; /* "color" group scalars, as densities  */
+  int   mem_space;               /* VLCT_MEM_HOST: pointers are host memory,
+                                    staged H2D/D2H inside the call;
+                                    VLCT_MEM_DEVICE: device pointers         */
+  void *stream;                  /* cudaStream_t (DEVICE only); NULL = the
+                                    library's own stream                     */
+} vlct_block;
+
+typedef struct vlct_handle vlct_handle;
+
+/* ---- configuration ---------------------------------------------------- */
+
+/* Fill *cfg with the reference's defaults (see field comments above). */
+int vlct_config_init(vlct_config *cfg);
+
+/* Set one parameter from its parameter-file key and textual value, e.g.
+ *   vlct_config_set(&cfg, "Method:mhd_vlct:riemann_solver", "hlld");
+ *   vlct_config_set(&cfg, "Physics:fluid_props:eos:gamma", "1.4");
+ * Keys: the Method:mhd_vlct:* keys parsed at
+ * src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:38-101 and the
+ * Physics:fluid_props:{eos:gamma, dual_energy:{type,eta}, floors:{density,
+ * pressure}} keys of src/Enzo/enzo-core/EnzoConfig.cpp:952-1262. The removed
+ * keys half_dt_reconstruct_method / full_dt_reconstruct_method are rejected
+ * like the reference does (EnzoMethodMHDVlct.cpp:62-70). errbuf (may be
+ * NULL) receives a message on failure. */
+int vlct_config_set(vlct_config *cfg, const char *key, const char *value,
+                    char *errbuf, int errbuf_len);
+
+/* Validate a configuration the way the reference's constructors do, without
+ * touching a GPU (EnzoMethodMHDVlct.cpp:90-152,
+ * EnzoMHDIntegratorStageCommands.cpp:18-64, EnzoRiemann.cpp:26-68,
+ * EnzoReconstructor.cpp:14-44, EnzoBfieldMethod.cpp:14-27). */
+int vlct_config_validate(const vlct_config *cfg, char *errbuf, int errbuf_len);
+
+/* ---- the Method plugin surface ----------------------------------------- */
+
+/* EnzoMethodMHDVlct::EnzoMethodMHDVlct(ParameterGroup, bool)
+ * (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:90-152). Binds to the current
+ * CUDA device. Scratch space is allocated lazily from the first block and
+ * reused for every later block (cpp:236-246), so all blocks given to one
+ * handle must share one shape. */
+int vlct_create(const vlct_config *cfg, vlct_handle **out);
+
+/* ~EnzoMethodMHDVlct (cpp:156-166) */
+void vlct_destroy(vlct_handle *h);
+
+/* Method::name() (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.hpp:123-124): "mhd_vlct" */
+const char *vlct_name(void);
+
+/* EnzoMethodMHDVlct::compute(Block*) (cpp:356-500) with dt = block->dt().
+ * Advances the block's fields in place by one full VL+CT step. On return the
+ * arrays hold exactly what the reference leaves behind, ghost zones included:
+ * hydro fields change only in the active zone, centred B on [2,m-2)^3, face
+ * B on the active-zone faces. The caller still calls block->compute_done(). */
+int vlct_compute(vlct_handle *h, const vlct_block *block, double dt);
+
+/* EnzoMethodMHDVlct::timestep(Block*) (cpp:551-588): dual-energy sync, writes
+ * the "pressure" field, returns courant * min over ALL cells (ghosts included,
+ * EnzoMHDIntegratorStageCommands.cpp:299-366) of dx_i/(|v_i| + c_signal). */
+int vlct_timestep(vlct_handle *h, const vlct_block *block, double *dt_out);
+
+/* Message of the last failure on this handle (never NULL). */
+const char *vlct_last_error(const vlct_handle *h);
+const char *vlct_status_string(int status);
+
+/* ---- instrumentation ---------------------------------------------------- */
+
+/* Number of CUDA kernels this handle has launched since creation / last reset
+ * (bench.py reports the difference over the timed region as gpu_launches). */
+long long vlct_kernel_launches(const vlct_handle *h);
+
+/* Bytes of device scratch currently owned by the handle. */
+long long vlct_scratch_bytes(const vlct_handle *h);
+
+/* Block until all work submitted through this handle has finished. */
+int vlct_synchronize(vlct_handle *h);
+
+/* ---- ghost-zone refresh on the device --------------
+ * Stand-ins for the refresh phase that precedes compute() on a unigrid
+ * (src/Cello/control_refresh.cpp:243-359, src/Cello/data_FieldFace.cpp).
+ * All pointers are DEVICE pointers. */
+
+/* Fill every ghost zone of every field of the block from the block's own
+ * active zone (a single periodic block: root_blocks = [1,1,1] with
+ * Boundary:type = "periodic"). Face-centred fields follow FieldFace's rule
+ * that the shared face belongs to both sides. axes: bit 0/1/2 = x/y/z. */
+int vlct_refresh_periodic(vlct_handle *h, const vlct_block *block, int axes);
+
+/* Pack / unpack the ghost-exchange slab of all fields along one axis
+ * (axis 0,1,2 = x,y,z; side 0 = lower, 1 = upper) into / from a contiguous
+ * device buffer: the payload of one MsgRefresh FieldFace
+ * (src/Cello/control_refresh.cpp:331-359). vlct_halo_bytes gives its size.
+ * "send" slabs are the g outermost ACTIVE layers; "recv" slabs are the ghost
+ * layers. Slabs span the full (ghost-including) extent of the other axes so
+ * that exchanging x, then y, then z also fills edges and corners. */
+long long vlct_halo_bytes(const vlct_handle *h, const vlct_block *block, int axis);
+int vlct_halo_pack(vlct_handle *h, const vlct_block *block, int axis, int side,
+                   double *buffer);
+int vlct_halo_unpack(vlct_handle *h, const vlct_block *block, int axis,
+                     int side, const double *buffer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLCT_H */

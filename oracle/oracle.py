@@ -1,0 +1,128 @@
+"""TEST INFRASTRUCTURE ONLY -- Python access to the two CPU checkers.
+
+  kind="oracle": oracle/libvlct_oracle.so, this repo's plain-C restatement of
+                 the reference's VL+CT algorithm (oracle/vlct_oracle.c)
+  kind="ref":    oracle/_ref/libvlct_ref.so, the reference's own sources
+                 compiled against oracle/ref_shim (built by `make -C oracle ref`
+                 in the container that has /root/reference)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this module. The product (enzo-e_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from enzo_e_b200 import abi  # noqa: E402  (struct layouts only)
+
+ORACLE_LIB = os.path.join(_HERE, "libvlct_oracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libvlct_ref.so")
+
+
+def build(target="all"):
+    """Run the oracle Makefile (building the checker is not using it)."""
+    subprocess.run(["make", "-C", _HERE, "-j8", target], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def have_ref():
+    return os.path.exists(REF_LIB)
+
+
+def have_oracle():
+    return os.path.exists(ORACLE_LIB)
+
+
+_libs = {}
+
+
+def _load(kind):
+    if kind in _libs:
+        return _libs[kind]
+    path = {"oracle": ORACLE_LIB, "ref": REF_LIB}[kind]
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing: run `make -C oracle` (kind={kind})")
+    lib = C.CDLL(path)
+    pfx = "vlct_oracle" if kind == "oracle" else "vlct_ref"
+    create = getattr(lib, pfx + "_create")
+    create.restype = C.c_void_p
+    create.argtypes = [C.POINTER(abi.VlctConfig), C.c_int, C.c_int, C.c_int]
+    destroy = getattr(lib, pfx + "_destroy")
+    destroy.restype = None
+    destroy.argtypes = [C.c_void_p]
+    compute = getattr(lib, pfx + "_compute")
+    compute.restype = C.c_int
+    compute.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_double]
+    timestep = getattr(lib, pfx + "_timestep")
+    timestep.restype = C.c_int
+    timestep.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock),
+                         C.POINTER(C.c_double)]
+    _libs[kind] = (lib, create, destroy, compute, timestep)
+    return _libs[kind]
+
+
+def numpy_block(fields, n, g, d, passive=()):
+    """Build a vlct_block (host memory) over a dict of numpy arrays."""
+    nx, ny, nz = n
+    gx, gy, gz = g
+    blk = abi.VlctBlock(nx=nx, ny=ny, nz=nz, gx=gx, gy=gy, gz=gz,
+                        dx=d[0], dy=d[1], dz=d[2], mem_space=abi.MEM_HOST,
+                        stream=None)
+    for name in abi.CELL_FIELDS + abi.FACE_FIELDS + abi.OTHER_FIELDS:
+        arr = fields.get(name)
+        if arr is None:
+            continue
+        shape = abi.field_shape(name, nx, ny, nz, gx, gy, gz)
+        assert arr.dtype == np.float64 and arr.flags.c_contiguous, name
+        assert arr.shape == shape, (name, arr.shape, shape)
+        setattr(blk, name, arr.ctypes.data_as(C.POINTER(C.c_double)))
+    for i, name in enumerate(passive):
+        arr = fields[name]
+        assert arr.dtype == np.float64 and arr.flags.c_contiguous, name
+        blk.passive[i] = arr.ctypes.data_as(C.POINTER(C.c_double))
+    return blk
+
+
+class CpuMethod:
+    """A CPU `EnzoMethodMHDVlct` (oracle restatement or compiled reference)."""
+
+    def __init__(self, cfg, ghost=(3, 3, 3), kind="oracle"):
+        self.kind = kind
+        self.cfg = cfg
+        (self._lib, create, self._destroy, self._compute,
+         self._timestep) = _load(kind)
+        self._h = create(C.byref(cfg), *ghost)
+        if not self._h:
+            raise RuntimeError(f"{kind}: create failed")
+
+    def close(self):
+        if self._h:
+            self._destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, blk, dt):
+        rc = self._compute(self._h, C.byref(blk), float(dt))
+        if rc != 0:
+            raise RuntimeError(f"{self.kind}: compute failed ({rc})")
+
+    def timestep(self, blk):
+        out = C.c_double(0.0)
+        rc = self._timestep(self._h, C.byref(blk), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"{self.kind}: timestep failed ({rc})")
+        return out.value

@@ -1,0 +1,374 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product.
+//
+// Stand-in for Cello's umbrella header, written for this repository so that
+// the reference's *unmodified* VL+CT hot-path sources (read in place from
+// /root/reference/src, never copied) compile into oracle/_ref/libvlct_ref.so
+// without Charm++, HDF5, the parameter-file parser or the rest of Cello.
+//
+// It supplies light fakes for the small surface of Cello that those sources
+// touch: Block / Data / Field / FieldDescr / Grouping (field lookup by name over
+// caller-provided memory), Method / Physics / Compute / Refresh (empty PUP::able
+// bases), ParameterGroup (a string->string dictionary) and the cello:: accessors.
+// The real CelloView / ViewMap / error-macro headers are used as they are.
+#ifndef VLCT_SHIM_CELLO_HPP
+#define VLCT_SHIM_CELLO_HPP
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <limits>
+#include <map>
+#include <memory>
+#include <random>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include <charm++.h>
+#include "pup_stl.h"
+
+// --- real reference headers (macros + views), found via -I .../src/Cello ----
+#include "cello_defines.hpp"   // FORCE_INLINE
+#include "error_Error.hpp"     // ASSERT*/ERROR*/WARNING* macros
+#include "view_CelloView.hpp"
+#include "view_ViewCollec.hpp"
+#include "view_StringIndRdOnlyMap.hpp"
+#include "view_ViewMap.hpp"
+
+#ifndef MIN
+#define MIN(a,b) (((a)<(b))?(a):(b))
+#endif
+#ifndef MAX
+#define MAX(a,b) (((a)>(b))?(a):(b))
+#endif
+#define UNUSED(x) (void)(x)
+
+enum precision_enum {
+  precision_unknown, precision_default, precision_single, precision_double,
+  precision_extended80, precision_extended96, precision_quadruple
+};
+typedef int precision_type;
+
+enum struct ghost_choice { exclude, include, permit };
+enum class InitCycleKind { fresh, charmrestart, fresh_or_noncharm_restart };
+
+enum { ir_post_unset = -1 };
+
+//----------------------------------------------------------------------
+
+class Grouping {
+public:
+  void add(const std::string& item, const std::string& group)
+  { groups_[group].push_back(item); }
+  int size(const std::string& group) const {
+    auto it = groups_.find(group);
+    return (it == groups_.end()) ? 0 : (int) it->second.size();
+  }
+  std::string item(const std::string& group, int index) const
+  { return groups_.at(group).at(index); }
+  std::vector<std::string> group_list(const std::string& group) const {
+    auto it = groups_.find(group);
+    return (it == groups_.end()) ? std::vector<std::string>() : it->second;
+  }
+  bool is_in(const std::string& item, const std::string& group) const {
+    auto it = groups_.find(group);
+    if (it == groups_.end()) return false;
+    return std::find(it->second.begin(), it->second.end(), item)
+      != it->second.end();
+  }
+private:
+  std::map<std::string, std::vector<std::string>> groups_;
+};
+
+//----------------------------------------------------------------------
+
+/// One entry per permanent field: a name, a centering and caller-owned memory
+struct ShimFieldEntry {
+  std::string name;
+  int cx, cy, cz;      // 1 if face-centred along that axis
+  double* ptr;         // caller-owned storage, (mz+cz, my+cy, mx+cx) C-order
+};
+
+class FieldDescr {
+public:
+  FieldDescr() : gx_(0), gy_(0), gz_(0) {}
+  int insert(const std::string& name, int cx, int cy, int cz) {
+    entries_.push_back({name, cx, cy, cz, nullptr});
+    return (int) entries_.size() - 1;
+  }
+  void clear() { entries_.clear(); groups_ = Grouping(); }
+  void set_ghost_depth(int gx, int gy, int gz) { gx_=gx; gy_=gy; gz_=gz; }
+
+  bool is_field(const std::string& name) const { return field_id(name) >= 0; }
+  int field_id(const std::string& name) const {
+    for (std::size_t i = 0; i < entries_.size(); i++)
+      if (entries_[i].name == name) return (int) i;
+    return -1;
+  }
+  std::string field_name(int id) const { return entries_.at(id).name; }
+  int field_count() const { return (int) entries_.size(); }
+  void ghost_depth(int /*id*/, int* gx, int* gy, int* gz) const
+  { if (gx) *gx = gx_; if (gy) *gy = gy_; if (gz) *gz = gz_; }
+  void centering(int id, int* cx, int* cy, int* cz) const {
+    const ShimFieldEntry& e = entries_.at(id);
+    if (cx) *cx = e.cx; if (cy) *cy = e.cy; if (cz) *cz = e.cz;
+  }
+  int precision(int /*id*/) const { return precision_default; }
+  Grouping* groups() { return &groups_; }
+  const Grouping* groups() const { return &groups_; }
+  const std::vector<ShimFieldEntry>& entries() const { return entries_; }
+private:
+  std::vector<ShimFieldEntry> entries_;
+  Grouping groups_;
+  int gx_, gy_, gz_;
+};
+
+//----------------------------------------------------------------------
+
+class FieldData {
+public:
+  FieldData() : nx(0), ny(0), nz(0) {}
+  int nx, ny, nz;                 // active-zone size
+  std::vector<double*> ptrs;      // one per FieldDescr entry
+};
+
+class Field {
+public:
+  Field() : descr_(nullptr), data_(nullptr) {}
+  Field(FieldDescr* d, FieldData* f) : descr_(d), data_(f) {}
+
+  int field_id(const std::string& name) const { return descr_->field_id(name); }
+  bool is_field(const std::string& name) const { return descr_->is_field(name);}
+  std::string field_name(int id) const { return descr_->field_name(id); }
+  void ghost_depth(int id, int* gx, int* gy, int* gz) const
+  { descr_->ghost_depth(id, gx, gy, gz); }
+  void centering(int id, int* cx, int* cy, int* cz) const
+  { descr_->centering(id, cx, cy, cz); }
+  int precision(int id) const { return descr_->precision(id); }
+  void size(int* nx, int* ny, int* nz) const
+  { if (nx) *nx = data_->nx; if (ny) *ny = data_->ny; if (nz) *nz = data_->nz; }
+  void dimensions(int id, int* mx, int* my, int* mz) const {
+    int gx, gy, gz, cx, cy, cz;
+    descr_->ghost_depth(id, &gx, &gy, &gz);
+    descr_->centering(id, &cx, &cy, &cz);
+    if (mx) *mx = data_->nx + 2*gx + cx;
+    if (my) *my = data_->ny + 2*gy + cy;
+    if (mz) *mz = data_->nz + 2*gz + cz;
+  }
+  Grouping* groups() { return descr_->groups(); }
+  bool ghosts_allocated() const { return true; }
+  double history_time(int /*history*/) const { return 0.0; }
+  const char* values(int id, int /*history*/ = 0) const
+  { return (id < 0) ? nullptr : (const char*) data_->ptrs.at(id); }
+  const char* values(const std::string& name, int history = 0) const
+  { return values(field_id(name), history); }
+
+  template<class T>
+  CelloView<T,3> view(int id, ghost_choice choice = ghost_choice::include,
+                      int history = 0) {
+    static_assert(std::is_same<T,double>::value, "oracle shim is fp64 only");
+    if (id < 0 || choice == ghost_choice::exclude || history != 0) {
+      ERROR("Field::view (shim)", "unsupported view request");
+    }
+    int mx, my, mz;
+    dimensions(id, &mx, &my, &mz);
+    return CelloView<T,3>(data_->ptrs.at(id), mz, my, mx);
+  }
+  template<class T>
+  CelloView<T,3> view(const std::string& name,
+                      ghost_choice choice = ghost_choice::include,
+                      int history = 0) {
+    int id = field_id(name);
+    if (id < 0) { ERROR1("Field::view (shim)", "no field named %s", name.c_str()); }
+    return view<T>(id, choice, history);
+  }
+  template<class T>
+  CelloView<const T,3> view(int id, ghost_choice choice = ghost_choice::include,
+                            int history = 0) const
+  { return const_cast<Field*>(this)->view<T>(id, choice, history); }
+  template<class T>
+  CelloView<const T,3> view(const std::string& name,
+                            ghost_choice choice = ghost_choice::include,
+                            int history = 0) const
+  { return const_cast<Field*>(this)->view<T>(name, choice, history); }
+private:
+  FieldDescr* descr_;
+  FieldData* data_;
+};
+
+//----------------------------------------------------------------------
+
+class FaceFluxes {
+public:
+  void get_size(int*, int*, int*) const {}
+  double* flux_array(int*, int*, int*) { return nullptr; }
+};
+class FluxData {
+public:
+  int num_fields() const { return 0; }
+  int index_field(int) const { return 0; }
+  FaceFluxes* block_fluxes(int, int, int) { return nullptr; }
+  void allocate(int, int, int, std::vector<int>, bool) {}
+};
+
+class Data {
+public:
+  Data(FieldDescr* d) : descr_(d) {}
+  Field field() { return Field(descr_, &field_data); }
+  FluxData* flux_data() { return &flux_data_; }
+  void lower(double* x, double* y, double* z) const
+  { if (x) *x = xm[0]; if (y) *y = xm[1]; if (z) *z = xm[2]; }
+  void field_cell_width(double* hx, double* hy, double* hz) const
+  { if (hx) *hx = h[0]; if (hy) *hy = h[1]; if (hz) *hz = h[2]; }
+  FieldData field_data;
+  double xm[3] = {0,0,0};
+  double h[3] = {1,1,1};
+private:
+  FieldDescr* descr_;
+  FluxData flux_data_;
+};
+
+class Index {
+public:
+  bool is_root() const { return true; }
+};
+
+/// In the shim every block is an EnzoBlock (see Enzo/enzo.hpp)
+class Block {
+public:
+  Block(FieldDescr* d) : data_(d), dt_(0), time_(0), cycle_(0),
+                         compute_done_count(0) {}
+  virtual ~Block() {}
+  Data* data() { return &data_; }
+  bool is_leaf() const { return true; }
+  double dt() const { return dt_; }
+  double time() const { return time_; }
+  int cycle() const { return cycle_; }
+  Index index() const { return Index(); }
+  void cell_width(double* hx, double* hy, double* hz) const
+  { const_cast<Data&>(data_).field_cell_width(hx, hy, hz); }
+  void compute_done() { compute_done_count++; }
+  void initial_done() {}
+  void set_dt(double dt) { dt_ = dt; }
+  Data data_;
+  double dt_, time_;
+  int cycle_;
+  int compute_done_count;
+};
+
+//----------------------------------------------------------------------
+
+class Refresh {
+public:
+  void add_all_fields() {}
+  void add_field(const std::string&) {}
+  void add_field(int) {}
+};
+
+class Simulation {
+public:
+  void refresh_set_name(int, const std::string&) {}
+};
+
+class Monitor {
+public:
+  void print(const char*, const char*, ...) {}
+};
+
+class Problem {
+public:
+  bool method_exists(const std::string&) const { return false; }
+  bool method_precedes(const std::string&, const std::string&) const
+  { return false; }
+};
+
+/// A dictionary standing in for the parameter-file group "Method:mhd_vlct"
+class ParameterGroup {
+public:
+  ParameterGroup() : path_("Method:mhd_vlct") {}
+  void set(const std::string& key, const std::string& value)
+  { values_[key] = value; }
+  const std::string* param(const std::string& key) const {
+    auto it = values_.find(key);
+    return (it == values_.end()) ? nullptr : &it->second;
+  }
+  std::string value_string(const std::string& key,
+                           const std::string& deflt) const
+  { const std::string* p = param(key); return p ? *p : deflt; }
+  double value_float(const std::string& key, double deflt) const
+  { const std::string* p = param(key); return p ? atof(p->c_str()) : deflt; }
+  bool value_logical(const std::string& key, bool deflt) const {
+    const std::string* p = param(key);
+    return p ? (*p == "true" || *p == "1") : deflt;
+  }
+  int value_integer(const std::string& key, int deflt) const
+  { const std::string* p = param(key); return p ? atoi(p->c_str()) : deflt; }
+  std::string full_name(const std::string& key) const
+  { return path_ + ":" + key; }
+  std::string get_group_path() const { return path_; }
+private:
+  std::string path_;
+  std::map<std::string, std::string> values_;
+};
+
+//----------------------------------------------------------------------
+
+namespace cello {
+  const double pi = 3.14159265358979324;
+
+  int rank();
+  FieldDescr* field_descr();
+  Simulation* simulation();
+  Refresh* refresh(int ir);
+  Monitor* monitor();
+  bool is_initial_cycle(InitCycleKind kind) noexcept;
+}
+
+//----------------------------------------------------------------------
+
+class Method : public PUP::able {
+public:
+  Method(double courant = 1.0) : ir_post_(0), courant_(courant) {}
+  Method(CkMigrateMessage* m) : PUP::able(m), ir_post_(0), courant_(1.0) {}
+  virtual ~Method() {}
+  virtual void pup(PUP::er& p) { PUP::able::pup(p); }
+  virtual void compute(Block* block) throw() = 0;
+  virtual std::string name() throw() = 0;
+  virtual double timestep(Block*) throw()
+  { return std::numeric_limits<double>::max(); }
+  double courant() const throw() { return courant_; }
+  void set_courant(double courant) throw() { courant_ = courant; }
+protected:
+  int ir_post_;
+  double courant_;
+};
+
+class Physics : public PUP::able {
+public:
+  Physics() {}
+  Physics(CkMigrateMessage* m) : PUP::able(m) {}
+  virtual ~Physics() {}
+  virtual std::string type() const = 0;
+};
+
+class Compute : public PUP::able {
+public:
+  Compute() : i_hist_(0) {}
+  Compute(CkMigrateMessage* m) : PUP::able(m), i_hist_(0) {}
+  virtual ~Compute() {}
+  virtual void compute(Block* block) throw() = 0;
+  virtual int  get_history(int) { return i_hist_; }
+  virtual void set_history(int i_hist) { i_hist_ = i_hist; }
+protected:
+  int i_hist_;
+};
+
+#endif /* VLCT_SHIM_CELLO_HPP */

@@ -1,0 +1,5 @@
+// Test infrastructure only: forwards to the shim's single Cello header.
+#ifndef VLCT_SHIM_CELLO_data_HPP
+#define VLCT_SHIM_CELLO_data_HPP
+#include "Cello/cello.hpp"
+#endif

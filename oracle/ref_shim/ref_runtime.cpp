@@ -1,0 +1,254 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product.
+//
+// Runtime half of the shim (written for this repository): definitions of the
+// cello:: / enzo:: accessors declared in the shim headers, and a small C ABI
+// (vlct_ref_*) that drives the reference's *own* EnzoMethodMHDVlct object --
+// compiled unmodified from /root/reference/src -- on caller-provided arrays.
+//
+// The result, oracle/_ref/libvlct_ref.so, is the ground truth the C
+// restatement in oracle/vlct_oracle.c is validated against, and the
+// "reference" CPU baseline that bench.py times. The product never links it.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "Cello/cello.hpp"
+#include "Enzo/enzo.hpp"
+#include "Enzo/hydro-mhd/hydro-mhd.hpp"
+
+#include "../../include/vlct.h"
+
+//----------------------------------------------------------------------
+// global state the reference reaches through cello:: / enzo:: accessors
+//----------------------------------------------------------------------
+
+namespace {
+  FieldDescr* g_field_descr = nullptr;
+  EnzoPhysicsFluidProps* g_fluid_props = nullptr;
+  Simulation g_simulation;
+  Refresh g_refresh;
+  Monitor g_monitor;
+  Problem g_problem;
+}
+
+namespace cello {
+  void message(FILE* fp, const char* type, const char* file, int line,
+               const char* function, const char* message, ...)
+  {
+    va_list args;
+    va_start(args, message);
+    fprintf(fp, "[vlct_ref] %s %s:%d %s: ", type, file, line, function);
+    vfprintf(fp, message, args);
+    fprintf(fp, "\n");
+    va_end(args);
+    fflush(fp);
+  }
+  [[noreturn]] void error() { fflush(stdout); fflush(stderr); abort(); }
+
+  int rank() { return 3; }
+  FieldDescr* field_descr() { return g_field_descr; }
+  Simulation* simulation() { return &g_simulation; }
+  Refresh* refresh(int) { return &g_refresh; }
+  Monitor* monitor() { return &g_monitor; }
+  // returning false skips EnzoMethodMHDVlct::post_init_checks_, which only
+  // inspects other Methods of a full simulation (gravity, flux_correct, ...)
+  bool is_initial_cycle(InitCycleKind) noexcept { return false; }
+}
+
+namespace enzo {
+  EnzoBlock* block(Block* block) { return static_cast<EnzoBlock*>(block); }
+  Problem* problem() { return &g_problem; }
+  EnzoPhysicsCosmology* cosmology() { return nullptr; }
+  EnzoPhysicsFluidProps* fluid_props() { return g_fluid_props; }
+  const EnzoMethodGrackle* grackle_method() { return nullptr; }
+  const GrackleChemistryData* grackle_chemistry() { return nullptr; }
+  double grav_constant_codeU() noexcept { return 1.0; }
+}
+
+//----------------------------------------------------------------------
+
+namespace {
+
+struct RefHandle {
+  vlct_config cfg;
+  FieldDescr descr;
+  EnzoPhysicsFluidProps* fluid_props;
+  EnzoMethodMHDVlct* method;
+  std::vector<std::string> passive_names;
+};
+
+void activate(RefHandle* h) {
+  if (g_field_descr != &h->descr) g_field_descr = &h->descr;
+  if (g_fluid_props != h->fluid_props) g_fluid_props = h->fluid_props;
+}
+
+std::string fmt_double(double v) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.17g", v);
+  return buf;
+}
+
+const char* riemann_name(int v) {
+  switch (v) {
+  case VLCT_RIEMANN_HLL:  return "hll";
+  case VLCT_RIEMANN_HLLE: return "hlle";
+  case VLCT_RIEMANN_HLLC: return "hllc";
+  default:                return "hlld";
+  }
+}
+const char* recon_name(int v) {
+  switch (v) {
+  case VLCT_RECON_NN:         return "nn";
+  case VLCT_RECON_PLM_ATHENA: return "plm_athena";
+  default:                    return "plm";
+  }
+}
+
+// attach the caller's arrays to a shim block
+void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
+  FieldData& fd = blk.data()->field_data;
+  fd.nx = b->nx; fd.ny = b->ny; fd.nz = b->nz;
+  fd.ptrs.assign(h->descr.field_count(), nullptr);
+  auto set = [&](const char* name, double* p) {
+    int id = h->descr.field_id(name);
+    if (id >= 0) {
+      if (p == nullptr) {
+        fprintf(stderr, "[vlct_ref] missing pointer for field %s\n", name);
+        abort();
+      }
+      fd.ptrs[id] = p;
+    }
+  };
+  set("density", b->density);
+  set("velocity_x", b->velocity_x);
+  set("velocity_y", b->velocity_y);
+  set("velocity_z", b->velocity_z);
+  set("total_energy", b->total_energy);
+  set("internal_energy", b->internal_energy);
+  set("bfield_x", b->bfield_x);
+  set("bfield_y", b->bfield_y);
+  set("bfield_z", b->bfield_z);
+  set("bfieldi_x", b->bfieldi_x);
+  set("bfieldi_y", b->bfieldi_y);
+  set("bfieldi_z", b->bfieldi_z);
+  set("pressure", b->pressure);
+  set("acceleration_x", b->acceleration_x);
+  set("acceleration_y", b->acceleration_y);
+  set("acceleration_z", b->acceleration_z);
+  for (std::size_t i = 0; i < h->passive_names.size(); i++)
+    set(h->passive_names[i].c_str(), b->passive[i]);
+  blk.CellWidth[0] = b->dx; blk.CellWidth[1] = b->dy; blk.CellWidth[2] = b->dz;
+  blk.data()->h[0] = b->dx; blk.data()->h[1] = b->dy; blk.data()->h[2] = b->dz;
+}
+
+} // namespace
+
+//----------------------------------------------------------------------
+
+extern "C" {
+
+void* vlct_ref_create(const vlct_config* cfg, int gx, int gy, int gz)
+{
+  RefHandle* h = new RefHandle;
+  h->cfg = *cfg;
+  const bool mhd = (cfg->mhd_choice == VLCT_MHD_CONSTRAINED_TRANSPORT);
+  const bool de = (cfg->dual_energy != VLCT_DE_DISABLED);
+
+  h->descr.set_ghost_depth(gx, gy, gz);
+  h->descr.insert("density", 0,0,0);
+  h->descr.insert("velocity_x", 0,0,0);
+  h->descr.insert("velocity_y", 0,0,0);
+  h->descr.insert("velocity_z", 0,0,0);
+  h->descr.insert("total_energy", 0,0,0);
+  if (de) h->descr.insert("internal_energy", 0,0,0);
+  if (mhd) {
+    h->descr.insert("bfield_x", 0,0,0);
+    h->descr.insert("bfield_y", 0,0,0);
+    h->descr.insert("bfield_z", 0,0,0);
+    h->descr.insert("bfieldi_x", 1,0,0);
+    h->descr.insert("bfieldi_y", 0,1,0);
+    h->descr.insert("bfieldi_z", 0,0,1);
+  }
+  h->descr.insert("pressure", 0,0,0);
+  if (cfg->has_acceleration) {
+    h->descr.insert("acceleration_x", 0,0,0);
+    h->descr.insert("acceleration_y", 0,0,0);
+    h->descr.insert("acceleration_z", 0,0,0);
+  }
+  for (int i = 0; i < cfg->n_passive; i++) {
+    char name[32];
+    snprintf(name, sizeof(name), "passive_%d", i);
+    h->passive_names.push_back(name);
+    h->descr.insert(name, 0,0,0);
+    h->descr.groups()->add(name, "color");
+  }
+
+  EnzoDualEnergyConfig de_config = EnzoDualEnergyConfig::build_disabled();
+  if (cfg->dual_energy == VLCT_DE_MODERN) {
+    de_config = EnzoDualEnergyConfig::build_modern_formulation
+      (cfg->dual_energy_eta);
+  } else if (cfg->dual_energy == VLCT_DE_BRYAN95) {
+    de_config = EnzoDualEnergyConfig::build_bryan95_formulation
+      (cfg->dual_energy_eta, cfg->dual_energy_eta);
+  }
+  EnzoFluidFloorConfig floors(cfg->density_floor, cfg->pressure_floor, 0., 0.);
+  EnzoEOSVariant eos(EnzoEOSIdeal::construct(cfg->gamma));
+  h->fluid_props = new EnzoPhysicsFluidProps(de_config, floors, eos, 0.6);
+
+  activate(h);
+
+  ParameterGroup p;
+  p.set("riemann_solver", riemann_name(cfg->riemann_solver));
+  p.set("reconstruct_method", recon_name(cfg->reconstruct_method));
+  p.set("theta_limiter", fmt_double(cfg->theta_limiter));
+  p.set("time_scheme", cfg->time_scheme == VLCT_TIME_EULER ? "euler" : "vl");
+  if (cfg->mhd_choice != VLCT_MHD_UNSET)
+    p.set("mhd_choice", mhd ? "constrained_transport" : "no_bfield");
+  if (cfg->courant >= 0) p.set("courant", fmt_double(cfg->courant));
+
+  h->method = new EnzoMethodMHDVlct(p, false);
+  return h;
+}
+
+void vlct_ref_destroy(void* handle)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  if (h == nullptr) return;
+  activate(h);
+  delete h->method;
+  delete h->fluid_props;
+  if (g_field_descr == &h->descr) g_field_descr = nullptr;
+  if (g_fluid_props == h->fluid_props) g_fluid_props = nullptr;
+  delete h;
+}
+
+int vlct_ref_compute(void* handle, const vlct_block* b, double dt)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->descr);
+  bind_block(h, blk, b);
+  blk.set_dt(dt);
+  h->method->compute(&blk);
+  return (blk.compute_done_count == 1) ? 0 : 1;
+}
+
+int vlct_ref_timestep(void* handle, const vlct_block* b, double* dt_out)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->descr);
+  bind_block(h, blk, b);
+  *dt_out = h->method->timestep(&blk);
+  return 0;
+}
+
+const char* vlct_ref_name(void* handle)
+{
+  static std::string name;
+  name = static_cast<RefHandle*>(handle)->method->name();
+  return name.c_str();
+}
+
+} // extern "C"
