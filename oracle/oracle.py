@@ -126,3 +126,61 @@ class CpuMethod:
         if rc != 0:
             raise RuntimeError(f"{self.kind}: timestep failed ({rc})")
         return out.value
+
+
+# ---------------------------------------------------------------------------
+# problem initialisers + periodic refresh (oracle/vlct_oracle_ic.c)
+# ---------------------------------------------------------------------------
+_DBL_MIN = 2.2250738585072014e-308
+
+
+def _ic_lib():
+    lib = _load("oracle")[0]
+    if not getattr(lib, "_ic_ready", False):
+        dp = C.POINTER(C.c_double)
+        lib.vlct_ic_inclined_wave.restype = C.c_int
+        lib.vlct_ic_inclined_wave.argtypes = [
+            C.POINTER(abi.VlctBlock), dp, C.c_double, C.c_char_p, C.c_double,
+            C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+        lib.vlct_ic_shock_tube.restype = C.c_int
+        lib.vlct_ic_shock_tube.argtypes = [
+            C.POINTER(abi.VlctBlock), dp, C.c_double, C.c_char_p, C.c_int,
+            C.c_double, C.c_double, C.c_int]
+        lib.vlct_ic_center_bfield.restype = C.c_int
+        lib.vlct_ic_center_bfield.argtypes = [C.POINTER(abi.VlctBlock)]
+        lib.vlct_oracle_refresh_periodic.restype = C.c_int
+        lib.vlct_oracle_refresh_periodic.argtypes = [
+            C.POINTER(abi.VlctBlock), C.c_int, C.c_int]
+        lib._ic_ready = True
+    return lib
+
+
+def ic_inclined_wave(blk, lower, gamma, wave_type, alpha, beta, amplitude=1e-6,
+                     lam=1.0, positive_vel=True, parallel_vel=None):
+    """EnzoInitialInclinedWave on a host block (fills ghost zones too)."""
+    lo = (C.c_double * 3)(*lower)
+    pv = _DBL_MIN if parallel_vel is None else float(parallel_vel)
+    rc = _ic_lib().vlct_ic_inclined_wave(
+        C.byref(blk), lo, gamma, wave_type.encode(), alpha, beta, amplitude,
+        lam, 1 if positive_vel else 0, pv)
+    if rc != 0:
+        raise RuntimeError(f"vlct_ic_inclined_wave failed ({rc})")
+
+
+def ic_shock_tube(blk, lower, gamma, setup, aligned_ax=0, axis_velocity=0.0,
+                  trans_velocity=0.0, flipped=False):
+    lo = (C.c_double * 3)(*lower)
+    rc = _ic_lib().vlct_ic_shock_tube(
+        C.byref(blk), lo, gamma, setup.encode(), aligned_ax, axis_velocity,
+        trans_velocity, 1 if flipped else 0)
+    if rc != 0:
+        raise RuntimeError(f"vlct_ic_shock_tube failed ({rc})")
+
+
+def center_bfield(blk):
+    _ic_lib().vlct_ic_center_bfield(C.byref(blk))
+
+
+def refresh_periodic(blk, n_passive=0, axes=7):
+    """Ghost refresh of a single periodic block (host memory)."""
+    _ic_lib().vlct_oracle_refresh_periodic(C.byref(blk), n_passive, axes)

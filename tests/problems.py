@@ -1,0 +1,158 @@
+"""The reference's vlct answer-test problems restated on raw arrays.
+
+Mirrors input/vlct/*.in + input/vlct/run_*_test.py + tools/l1_error_norm.py of
+the reference: same parameter values, same cycle order (stopping/timestep ->
+refresh -> compute, src/Cello/control_stopping.cpp:44-142,
+control_compute.cpp:42-157), same L1 error norm.
+"""
+import numpy as np
+
+from helpers import abi, make_config, oracle
+
+# input/vlct/MHD_linear_wave/initial_*.in, HD_linear_wave/initial_*.in
+ALPHA = 0.7297276562269663   # sin(alpha) = 2/3
+BETA = 1.1071487177940904    # sin(beta)  = 2/sqrt(5)
+
+# name -> (wave_type parameter, final time)
+MHD_WAVES = {"fast": ("fast", 0.5), "alfven": ("alfven", 1.0),
+             "slow": ("slow", 2.0), "entropy": ("mhd_entropy", 1.0)}
+HD_WAVES = {"sound": ("sound", 1.0), "hd_entropy": ("hd_entropy", 1.0),
+            "hd_transv_entropy_v1": ("hd_transv_entropy_v1", 1.0),
+            "hd_transv_entropy_v2": ("hd_transv_entropy_v2", 1.0)}
+
+# golden L1 norms: input/vlct/run_MHD_linear_wave_test.py:178-188,
+#                  input/vlct/run_HD_linear_wave_test.py:70-80
+GOLDEN_MHD = {("fast", 16): 1.6388526155394664e-07,
+              ("fast", 32): 3.302538226654406e-08,
+              ("alfven", 16): 1.927245356389947e-07,
+              ("alfven", 32): 3.005870212811956e-08,
+              ("slow", 16): 2.2373810027584788e-07,
+              ("slow", 32): 4.43702e-08,
+              ("entropy", 16): 1.0021263485338544e-07,
+              ("entropy", 32): 2.9194839706868883e-08}
+GOLDEN_HD = {("sound", 16): 1.3704437791196907e-07,
+             ("sound", 32): 2.3484946798755385e-08,
+             ("hd_entropy", 16): 8.736217559091042e-08,
+             ("hd_entropy", 32): 2.2383944940640457e-08,
+             ("hd_transv_entropy_v1", 16): 7.671004076321944e-08,
+             ("hd_transv_entropy_v1", 32): 1.6725791096617187e-08,
+             ("hd_transv_entropy_v2", 16): 8.640730176761958e-08,
+             ("hd_transv_entropy_v2", 32): 1.6960029746447077e-08}
+
+
+def golden_isclose(a, b):
+    """input/vlct/testing_utils.py:275-292 with abs_tol=True"""
+    return bool(np.isclose(a, b, rtol=1e-13, atol=7e-14))
+
+
+def linear_wave_config(mhd):
+    """input/vlct/vl.incl (+ vlct.incl for MHD)"""
+    return make_config(riemann="hlld" if mhd else "hllc", recon="plm",
+                       theta=2.0, mhd=mhd, courant=0.4,
+                       gamma=1.6666666666666667, dfloor=1e-200, pfloor=1e-200)
+
+
+def alloc_fields(cfg, n, g, passive=()):
+    names = ["density", "velocity_x", "velocity_y", "velocity_z",
+             "total_energy", "pressure"]
+    if cfg.dual_energy:
+        names.append("internal_energy")
+    if cfg.mhd_choice == 1:
+        names += ["bfield_x", "bfield_y", "bfield_z",
+                  "bfieldi_x", "bfieldi_y", "bfieldi_z"]
+    f = {k: np.zeros(abi.field_shape(k, *n, *g)) for k in names}
+    for k in passive:
+        f[k] = np.zeros(abi.field_shape("density", *n, *g))
+    return f
+
+
+def linear_wave_setup(name, N, mhd=True, positive_vel=True):
+    """Domain [0,3]x[0,1.5]^2 with (2N,N,N) cells, one periodic block."""
+    cfg = linear_wave_config(mhd)
+    n, g = (2 * N, N, N), (3, 3, 3)
+    d = (3.0 / n[0], 1.5 / n[1], 1.5 / n[2])
+    f = alloc_fields(cfg, n, g)
+    blk = oracle.numpy_block(f, n, g, d)
+    wave_type, t_final = (MHD_WAVES if mhd else HD_WAVES)[name]
+    oracle.ic_inclined_wave(blk, (0.0, 0.0, 0.0), cfg.gamma, wave_type, ALPHA,
+                            BETA, 1e-6, 1.0, positive_vel)
+    return cfg, f, blk, n, g, d, t_final
+
+
+def pressure_of(cfg, f):
+    """EnzoComputePressure formula (what an Output of "pressure" holds)."""
+    gm1 = cfg.gamma - 1.0
+    if cfg.dual_energy:
+        return gm1 * f["density"] * f["internal_energy"]
+    ke = 0.5 * (f["velocity_x"] * f["velocity_x"] +
+                f["velocity_y"] * f["velocity_y"] +
+                f["velocity_z"] * f["velocity_z"])
+    me = 0.0
+    if cfg.mhd_choice == 1:
+        me = 0.5 * (f["bfield_x"] * f["bfield_x"] + f["bfield_y"] * f["bfield_y"]
+                    + f["bfield_z"] * f["bfield_z"])
+    return gm1 * (f["density"] * (f["total_energy"] - ke) - me)
+
+
+def snapshot(cfg, f, g):
+    """The active-zone fields an Output would dump."""
+    gx, gy, gz = g
+    out = {}
+    names = ["density", "velocity_x", "velocity_y", "velocity_z",
+             "total_energy"]
+    if cfg.mhd_choice == 1:
+        names += ["bfield_x", "bfield_y", "bfield_z"]
+    p = pressure_of(cfg, f)
+    for k in names:
+        out[k] = f[k][gz:-gz, gy:-gy, gx:-gx].copy()
+    out["pressure"] = p[gz:-gz, gy:-gy, gx:-gx].copy()
+    return out
+
+
+def l1_error_norm(a, b, fields, res):
+    """tools/l1_error_norm.py:195-234 in "sim" mode with -n res"""
+    resid = [np.sum(np.abs(a[k] - b[k])) / float(res ** 3) for k in fields]
+    return float(np.sqrt(np.sum(np.square(np.array(resid)))))
+
+
+def evolve(method, blk, t_stop, refresh, dump_times=(), max_cycles=100000):
+    """Cycle loop: timestep -> (clip) -> refresh -> compute -> advance."""
+    t, cycle, dts = 0.0, 0, []
+    while t < t_stop and cycle < max_cycles:
+        dt = method.timestep(blk)
+        for td in dump_times:                  # io_ScheduleList.cpp:133-159
+            if t < td < t + dt:
+                dt = td - t
+                break
+        dt = min(dt, t_stop - t)               # control_stopping.cpp:86
+        refresh(blk)
+        method.compute(blk, dt)
+        t += dt
+        cycle += 1
+        dts.append(dt)
+    return dts
+
+
+LINWAVE_FIELDS_MHD = ["density", "velocity_x", "velocity_y", "velocity_z",
+                      "pressure", "bfield_x", "bfield_y", "bfield_z"]
+LINWAVE_FIELDS_HD = ["density", "velocity_x", "velocity_y", "velocity_z",
+                     "pressure"]
+
+
+def run_linear_wave(name, N, mhd=True, kind="oracle", positive_vel=True,
+                    method=None, refresh=None):
+    cfg, f, blk, n, g, d, t_final = linear_wave_setup(name, N, mhd,
+                                                      positive_vel)
+    own = method is None
+    if own:
+        method = oracle.CpuMethod(cfg, g, kind=kind)
+    if refresh is None:
+        def refresh(b):
+            oracle.refresh_periodic(b, 0)
+    s0 = snapshot(cfg, f, g)
+    dts = evolve(method, blk, t_final, refresh, dump_times=(0.0, t_final))
+    s1 = snapshot(cfg, f, g)
+    if own:
+        method.close()
+    fields = LINWAVE_FIELDS_MHD if mhd else LINWAVE_FIELDS_HD
+    return l1_error_norm(s0, s1, fields, N), dts, f
