@@ -1,0 +1,574 @@
+// vlct_api.cu -- the C ABI (include/vlct.h) over the CUDA kernels.
+//
+// Host-side mirror of EnzoMethodMHDVlct (hydro-mhd/EnzoMethodMHDVlct.cpp): the
+// handle plays the role of the Method object (configuration + lazily
+// allocated scratch that is reused for every block, cpp:236-246), vlct_compute
+// is the two-stage loop of EnzoMethodMHDVlct::compute (cpp:459-496) and
+// vlct_timestep is EnzoMethodMHDVlct::timestep (cpp:551-588).
+//
+// There is deliberately no CPU path in this file: without a CUDA device
+// vlct_create fails with VLCT_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "vlct_kernels.cuh"
+
+using namespace vlct;
+
+struct vlct_handle {
+  vlct_config cfg;
+  Params P;
+  int device = -1;
+  cudaStream_t own_stream = nullptr;
+  Geom G{0, 0, 0};
+  Scratch S;
+  std::vector<void*> allocations;
+  long long scratch_bytes = 0;
+  unsigned long long* d_dt_bits = nullptr;
+  unsigned long long* h_dt_bits = nullptr;   // pinned
+  // device mirror of a HOST block (mem_space == VLCT_MEM_HOST)
+  bool have_mirror = false;
+  vlct_block mirror;
+  std::vector<void*> mirror_allocs;
+  long long launches = 0;
+  std::string last_error;
+};
+
+namespace {
+
+int fail(vlct_handle* h, int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list args;
+  va_start(args, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, args);
+  va_end(args);
+  if (h) h->last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, call)                                                    \
+  do {                                                                       \
+    cudaError_t err__ = (call);                                              \
+    if (err__ != cudaSuccess)                                                \
+      return fail((h), VLCT_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                  cudaGetErrorString(err__), __FILE__, __LINE__);            \
+  } while (0)
+
+int dev_alloc(vlct_handle* h, double** out, size_t count, bool scratch = true)
+{
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, count * sizeof(double)));
+  CUDA_TRY(h, cudaMemset(p, 0, count * sizeof(double)));
+  (scratch ? h->allocations : h->mirror_allocs).push_back(p);
+  if (scratch) h->scratch_bytes += (long long) (count * sizeof(double));
+  *out = (double*) p;
+  return VLCT_OK;
+}
+
+size_t face_count(const Geom& G, int d)
+{
+  return (size_t) (G.mx + (d == 0)) * (size_t) (G.my + (d == 1)) *
+         (size_t) (G.mz + (d == 2));
+}
+
+/// EnzoVlctScratchSpace (hydro-mhd/EnzoMethodMHDVlct.hpp:217-312) +
+/// EnzoBfieldMethodCT scratch (toolkit/EnzoBfieldMethodCT.cpp:41-76), minus
+/// everything the fused kernels never materialise.
+int alloc_scratch(vlct_handle* h, const Geom& G)
+{
+  h->G = G;
+  const size_t n = G.cells();
+  const Params& P = h->P;
+  Scratch& S = h->S;
+  memset(&S, 0, sizeof(S));
+  int rc;
+#define ALLOC(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != VLCT_OK) return rc
+  const bool two_stage = (h->cfg.time_scheme == VLCT_TIME_VL);
+  if (two_stage) {
+    ALLOC(S.temp.rho, n); ALLOC(S.temp.vx, n); ALLOC(S.temp.vy, n);
+    ALLOC(S.temp.vz, n); ALLOC(S.temp.etot, n);
+    if (P.de) ALLOC(S.temp.eint, n);
+    if (P.mhd) {
+      ALLOC(S.temp.bx, n); ALLOC(S.temp.by, n); ALLOC(S.temp.bz, n);
+      for (int d = 0; d < 3; d++) ALLOC(S.tbi.bi[d], face_count(G, d));
+    }
+    for (int s = 0; s < P.nsc; s++) ALLOC(S.temp.sc[s], n);
+  }
+  for (int d = 0; d < 3; d++) {
+    FluxSet& F = S.flux[d];
+    ALLOC(F.rho, n); ALLOC(F.mx_, n); ALLOC(F.my_, n); ALLOC(F.mz_, n);
+    ALLOC(F.e, n);
+    if (P.mhd) {
+      if (d != 0) ALLOC(F.bx, n);
+      if (d != 1) ALLOC(F.by, n);
+      if (d != 2) ALLOC(F.bz, n);
+    }
+    if (P.de) { ALLOC(F.eint, n); ALLOC(F.vbar, n); }
+    for (int s = 0; s < P.nsc; s++) ALLOC(F.sc[s], n);
+  }
+  ALLOC(S.prim_p, n);
+  for (int s = 0; s < P.nsc; s++) ALLOC(S.prim_sc[s], n);
+  if (P.mhd) for (int d = 0; d < 3; d++) ALLOC(S.edge[d], n);
+#undef ALLOC
+  return VLCT_OK;
+}
+
+int check_block(vlct_handle* h, const vlct_block* b, bool for_timestep)
+{
+  if (b == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "NULL block");
+  if (b->nx <= 0 || b->ny <= 0 || b->nz <= 0)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "block must be three-dimensional (nx,ny,nz > 0); this "
+                "implementation supports rank 3 only");
+  if (!(b->dx > 0 && b->dy > 0 && b->dz > 0))
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "cell widths must be positive");
+  const Params& P = h->P;
+#define NEED(field)                                                          \
+  if (b->field == nullptr)                                                   \
+    return fail(h, VLCT_ERR_INVALID_BLOCK,                                   \
+                "\"%s\" must be a permanent field", #field)
+  NEED(density); NEED(velocity_x); NEED(velocity_y); NEED(velocity_z);
+  NEED(total_energy);
+  if (P.de) NEED(internal_energy);
+  if (P.mhd) {
+    NEED(bfield_x); NEED(bfield_y); NEED(bfield_z);
+    if (!for_timestep) { NEED(bfieldi_x); NEED(bfieldi_y); NEED(bfieldi_z); }
+  }
+  if (for_timestep) NEED(pressure);
+#undef NEED
+  for (int s = 0; s < P.nsc; s++)
+    if (b->passive[s] == nullptr)
+      return fail(h, VLCT_ERR_INVALID_BLOCK, "passive scalar %d is NULL", s);
+  if (!for_timestep) {
+    // EnzoMethodMHDVlct.cpp:124-133: ghost depth >= sum of the stages' staling
+    const int full = (h->cfg.reconstruct_method == VLCT_RECON_NN) ? 1 : 2;
+    const int need = (h->cfg.time_scheme == VLCT_TIME_VL) ? 1 + full : full;
+    const int gmin = b->gx < b->gy ? (b->gx < b->gz ? b->gx : b->gz)
+                                   : (b->gy < b->gz ? b->gy : b->gz);
+    if (gmin < need)
+      return fail(h, VLCT_ERR_INVALID_BLOCK, "ghost depth must be at least %d.",
+                  need);
+    if (h->cfg.has_acceleration &&
+        (b->acceleration_x == nullptr || b->acceleration_y == nullptr ||
+         b->acceleration_z == nullptr))
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "acceleration fields are configured but missing");
+  }
+  if (b->mem_space != VLCT_MEM_HOST && b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "unknown mem_space %d", b->mem_space);
+  return VLCT_OK;
+}
+
+Geom geom_of(const vlct_block* b)
+{
+  Geom G;
+  G.mx = b->nx + 2 * b->gx; G.my = b->ny + 2 * b->gy; G.mz = b->nz + 2 * b->gz;
+  return G;
+}
+
+State state_of(const vlct_handle* h, const vlct_block* b)
+{
+  State u;
+  memset(&u, 0, sizeof(u));
+  u.rho = b->density; u.vx = b->velocity_x; u.vy = b->velocity_y;
+  u.vz = b->velocity_z; u.etot = b->total_energy; u.eint = b->internal_energy;
+  u.bx = b->bfield_x; u.by = b->bfield_y; u.bz = b->bfield_z;
+  for (int s = 0; s < h->P.nsc; s++) u.sc[s] = b->passive[s];
+  return u;
+}
+
+// ---- HOST mem_space: a device mirror of the block ---------------------------
+struct FieldRef { double* vlct_block::*member; int face; };
+
+const FieldRef kFields[] = {
+  { &vlct_block::density, -1 }, { &vlct_block::velocity_x, -1 },
+  { &vlct_block::velocity_y, -1 }, { &vlct_block::velocity_z, -1 },
+  { &vlct_block::total_energy, -1 }, { &vlct_block::internal_energy, -1 },
+  { &vlct_block::bfield_x, -1 }, { &vlct_block::bfield_y, -1 },
+  { &vlct_block::bfield_z, -1 }, { &vlct_block::bfieldi_x, 0 },
+  { &vlct_block::bfieldi_y, 1 }, { &vlct_block::bfieldi_z, 2 },
+  { &vlct_block::pressure, -1 }, { &vlct_block::acceleration_x, -1 },
+  { &vlct_block::acceleration_y, -1 }, { &vlct_block::acceleration_z, -1 },
+};
+constexpr int kNumFields = (int) (sizeof(kFields) / sizeof(kFields[0]));
+
+size_t field_count(const Geom& G, int face)
+{ return face < 0 ? G.cells() : face_count(G, face); }
+
+int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
+{
+  if (h->have_mirror) return VLCT_OK;
+  h->mirror = *b;
+  h->mirror.mem_space = VLCT_MEM_DEVICE;
+  int rc;
+  for (int f = 0; f < kNumFields; f++) {
+    h->mirror.*(kFields[f].member) = nullptr;
+    if (b->*(kFields[f].member) == nullptr) continue;
+    double* p;
+    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), false)) != VLCT_OK)
+      return rc;
+    h->mirror.*(kFields[f].member) = p;
+  }
+  for (int s = 0; s < VLCT_MAX_PASSIVE; s++) {
+    h->mirror.passive[s] = nullptr;
+    if (s < h->P.nsc) {
+      double* p;
+      if ((rc = dev_alloc(h, &p, G.cells(), false)) != VLCT_OK) return rc;
+      h->mirror.passive[s] = p;
+    }
+  }
+  h->have_mirror = true;
+  return VLCT_OK;
+}
+
+/// copy the listed members between the host block and its device mirror
+int mirror_copy(vlct_handle* h, const vlct_block* host, const Geom& G,
+                cudaStream_t st, bool to_device, bool inputs_only_changed)
+{
+  for (int f = 0; f < kNumFields; f++) {
+    double* hp = host->*(kFields[f].member);
+    double* dp = h->mirror.*(kFields[f].member);
+    if (hp == nullptr || dp == nullptr) continue;
+    if (!to_device && inputs_only_changed) {
+      // compute() never modifies pressure or the acceleration fields
+      if (kFields[f].member == &vlct_block::pressure ||
+          kFields[f].member == &vlct_block::acceleration_x ||
+          kFields[f].member == &vlct_block::acceleration_y ||
+          kFields[f].member == &vlct_block::acceleration_z) continue;
+    }
+    const size_t bytes = field_count(G, kFields[f].face) * sizeof(double);
+    CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) dp : (void*) hp,
+                                to_device ? (void*) hp : (void*) dp, bytes,
+                                to_device ? cudaMemcpyHostToDevice
+                                          : cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < h->P.nsc; s++) {
+    const size_t bytes = G.cells() * sizeof(double);
+    double* hp = host->passive[s];
+    double* dp = h->mirror.passive[s];
+    CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) dp : (void*) hp,
+                                to_device ? (void*) hp : (void*) dp, bytes,
+                                to_device ? cudaMemcpyHostToDevice
+                                          : cudaMemcpyDeviceToHost, st));
+  }
+  return VLCT_OK;
+}
+
+int total_staling(int recon) { return recon == VLCT_RECON_NN ? 1 : 2; }
+int immediate_staling(int recon) { return recon == VLCT_RECON_NN ? 0 : 1; }
+
+/// the stage loop of EnzoMethodMHDVlct::compute on device pointers
+int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
+                      double dt, cudaStream_t st)
+{
+  const Params& P = h->P;
+  const State ext = state_of(h, b);
+  FaceB bi;
+  bi.bi[0] = b->bfieldi_x; bi.bi[1] = b->bfieldi_y; bi.bi[2] = b->bfieldi_z;
+  const double width[3] = { b->dx, b->dy, b->dz };
+  const double* accel[3] = { b->acceleration_x, b->acceleration_y,
+                             b->acceleration_z };
+  const int nstages = (h->cfg.time_scheme == VLCT_TIME_EULER) ? 1 : 2;
+  int stale = 0;
+  for (int stage = 0; stage < nstages; stage++) {
+    const bool final_stage = (stage + 1) == nstages;
+    const double cur_dt = (!final_stage) ? dt / 2. : dt;
+    const int recon = (nstages == 2 && stage == 0) ? VLCT_RECON_NN
+                                                   : h->cfg.reconstruct_method;
+    const State& cur = (stage == 0) ? ext : h->S.temp;
+    const State& out = final_stage ? ext : h->S.temp;
+    const FaceB& bi_cur = (stage == 0) ? bi : h->S.tbi;
+    const FaceB& bi_out = (stage == 1 || nstages == 1) ? bi : h->S.tbi;
+
+    launch_primitives(st, P, G, cur, h->S, stale, &h->launches);
+    const int cs = stale + immediate_staling(recon);
+    for (int dim = 0; dim < 3; dim++)
+      launch_flux(st, P, G, dim, recon, cur, h->S, bi_cur, cs, &h->launches);
+    if (P.mhd)
+      launch_ct(st, P, G, cur, h->S, bi, bi_out, cur_dt, width, cs, &h->launches);
+    // gravity: full step only, i.e. stage index 1
+    // (EnzoMHDIntegratorStageCommands.cpp:181,279)
+    const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
+                         accel[0] != nullptr;
+    launch_update(st, P, G, ext, out, h->S, bi_out, accel, gravity, cur_dt,
+                  width, cs, &h->launches);
+    stale += total_staling(recon);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vlct_create(const vlct_config* cfg, vlct_handle** out)
+{
+  if (out == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  *out = nullptr;
+  vlct_handle* h = new vlct_handle;
+  *out = h;   // returned even on failure so that vlct_last_error() works
+  char err[512] = "";
+  int rc = vlct_config_validate(cfg, err, (int) sizeof(err));
+  if (rc != VLCT_OK) { h->last_error = err; return rc; }
+  h->cfg = *cfg;
+  if (h->cfg.courant < 0)   // EnzoMethodMHDVlct.cpp:100-101
+    h->cfg.courant = (cfg->time_scheme == VLCT_TIME_VL) ? 0.3 : 1.0;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, VLCT_ERR_NO_DEVICE,
+                "no CUDA device is visible; this library has no CPU fallback");
+  }
+  CUDA_TRY(h, cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major < 10)
+    return fail(h, VLCT_ERR_NO_DEVICE,
+                "device %d (%s, sm_%d%d) is not a Blackwell-class GPU; the "
+                "kernels are built for sm_100a only", h->device, prop.name,
+                prop.major, prop.minor);
+
+  Params& P = h->P;
+  P.gamma = cfg->gamma;
+  P.theta = cfg->theta_limiter;
+  P.density_floor = cfg->density_floor;
+  P.pressure_floor = cfg->pressure_floor;
+  P.mhd = (cfg->mhd_choice == VLCT_MHD_CONSTRAINED_TRANSPORT);
+  P.de = (cfg->dual_energy == VLCT_DE_MODERN);
+  P.de_eta = P.de ? cfg->dual_energy_eta : 0.0;
+  // `float ggm1 = gamma*(gamma-1.)` -- a float in the fp64 path
+  // (fluid-props/EnzoPhysicsFluidProps.cpp:234)
+  const float ggm1 = (float) (cfg->gamma * (cfg->gamma - 1.));
+  P.ggm1 = (double) ggm1;
+  P.nsc = cfg->n_passive;
+  P.riemann = cfg->riemann_solver;
+  P.recon = cfg->reconstruct_method;
+
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaMalloc((void**) &h->d_dt_bits, sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMallocHost((void**) &h->h_dt_bits, sizeof(unsigned long long)));
+  return VLCT_OK;
+}
+
+void vlct_destroy(vlct_handle* h)
+{
+  if (h == nullptr) return;
+  if (h->device >= 0) {
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (void* p : h->allocations) cudaFree(p);
+    for (void* p : h->mirror_allocs) cudaFree(p);
+    if (h->d_dt_bits) cudaFree(h->d_dt_bits);
+    if (h->h_dt_bits) cudaFreeHost(h->h_dt_bits);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  }
+  delete h;
+}
+
+int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  int rc = check_block(h, b, false);
+  if (rc != VLCT_OK) return rc;
+  const Geom G = geom_of(b);
+  if (h->G.mx == 0) {
+    if ((rc = alloc_scratch(h, G)) != VLCT_OK) return rc;
+  } else if (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz) {
+    // the reference sizes its scratch from the first block and reuses it
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "all blocks handled by one handle must share one shape "
+                "(first block was %dx%dx%d incl. ghosts, got %dx%dx%d)",
+                h->G.mx, h->G.my, h->G.mz, G.mx, G.my, G.mz);
+  }
+  if (b->mem_space == VLCT_MEM_DEVICE) {
+    cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+    return compute_on_device(h, b, G, dt, st);
+  }
+  // HOST: stage through the device mirror; synchronous
+  cudaStream_t st = h->own_stream;
+  if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
+  if ((rc = mirror_copy(h, b, G, st, true, false)) != VLCT_OK) return rc;
+  if ((rc = compute_on_device(h, &h->mirror, G, dt, st)) != VLCT_OK) return rc;
+  if ((rc = mirror_copy(h, b, G, st, false, true)) != VLCT_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return VLCT_OK;
+}
+
+int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  if (dt_out == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_out is NULL");
+  int rc = check_block(h, b, true);
+  if (rc != VLCT_OK) return rc;
+  const Geom G = geom_of(b);
+  const double width[3] = { b->dx, b->dy, b->dz };
+  cudaStream_t st;
+  const vlct_block* db = b;
+  if (b->mem_space == VLCT_MEM_DEVICE) {
+    st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  } else {
+    st = h->own_stream;
+    if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
+    if ((rc = mirror_copy(h, b, G, st, true, false)) != VLCT_OK) return rc;
+    db = &h->mirror;
+  }
+  const State u = state_of(h, db);
+  launch_timestep(st, h->P, G, u, db->pressure, width, h->d_dt_bits, &h->launches);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+  if (b->mem_space == VLCT_MEM_HOST) {
+    // timestep writes "pressure" and (dual energy) total/internal energy
+    const size_t bytes = G.cells() * sizeof(double);
+    CUDA_TRY(h, cudaMemcpyAsync(b->pressure, db->pressure, bytes, cudaMemcpyDeviceToHost, st));
+    if (h->P.de) {
+      CUDA_TRY(h, cudaMemcpyAsync(b->total_energy, db->total_energy, bytes, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(h, cudaMemcpyAsync(b->internal_energy, db->internal_energy, bytes, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  double dt_baryons;
+  memcpy(&dt_baryons, h->h_dt_bits, sizeof(double));
+  // "Multiply resulting dt by CourantSafetyNumber" (cpp:585-587)
+  *dt_out = dt_baryons * h->cfg.courant;
+  return VLCT_OK;
+}
+
+const char* vlct_last_error(const vlct_handle* h)
+{ return h ? h->last_error.c_str() : "NULL handle"; }
+
+long long vlct_kernel_launches(const vlct_handle* h)
+{ return h ? h->launches : 0; }
+
+long long vlct_scratch_bytes(const vlct_handle* h)
+{ return h ? h->scratch_bytes : 0; }
+
+int vlct_synchronize(vlct_handle* h)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  return VLCT_OK;
+}
+
+// ---- ghost-zone refresh ------------------------------------------------------
+
+namespace {
+struct RefreshField { double* p; int n0, n1, n2; int face; };
+
+int collect_fields(vlct_handle* h, const vlct_block* b, const Geom& G,
+                   std::vector<RefreshField>& out)
+{
+  for (int f = 0; f < kNumFields; f++) {
+    double* p = b->*(kFields[f].member);
+    if (p == nullptr) continue;
+    const int face = kFields[f].face;
+    out.push_back({ p, G.mz + (face == 2), G.my + (face == 1),
+                    G.mx + (face == 0), face });
+  }
+  for (int s = 0; s < h->P.nsc; s++)
+    if (b->passive[s]) out.push_back({ b->passive[s], G.mz, G.my, G.mx, -1 });
+  return VLCT_OK;
+}
+}  // namespace
+
+int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_refresh_periodic needs a DEVICE block");
+  const Geom G = geom_of(b);
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  std::vector<RefreshField> fields;
+  collect_fields(h, b, G, fields);
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  for (int axis = 0; axis < 3; axis++) {
+    if (!(axes & (1 << axis))) continue;
+    if (n[axis] < g[axis])
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "periodic refresh needs n >= ghost depth along every axis");
+    for (const RefreshField& f : fields)
+      launch_wrap_axis(st, f.p, f.n0, f.n1, f.n2, axis, n[axis], g[axis],
+                       f.face == axis ? 1 : 0, &h->launches);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
+long long vlct_halo_bytes(const vlct_handle* h, const vlct_block* b, int axis)
+{
+  if (h == nullptr || b == nullptr || axis < 0 || axis > 2) return -1;
+  const Geom G = geom_of(b);
+  std::vector<RefreshField> fields;
+  collect_fields(const_cast<vlct_handle*>(h), b, G, fields);
+  const int g[3] = { b->gx, b->gy, b->gz };
+  long long total = 0;
+  for (const RefreshField& f : fields) {
+    const int ext[3] = { f.n2, f.n1, f.n0 };
+    long long cnt = g[axis];
+    for (int a = 0; a < 3; a++) if (a != axis) cnt *= ext[a];
+    total += cnt;
+  }
+  return total * (long long) sizeof(double);
+}
+
+namespace {
+int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
+              double* buffer, bool pack)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE || axis < 0 || axis > 2 ||
+      (side != 0 && side != 1) || buffer == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "bad arguments to halo pack/unpack");
+  const Geom G = geom_of(b);
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  std::vector<RefreshField> fields;
+  collect_fields(h, b, G, fields);
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  size_t off = 0;
+  for (const RefreshField& f : fields) {
+    // Along `axis` a cell-centred field has ghosts [0,g) and [g+n, 2g+n); a
+    // field that is face-centred along `axis` (cen = 1) has n+1 active faces
+    // [g, g+n] and ghosts [0,g), [g+n+1, 2g+n+1). The shared boundary face is
+    // computed identically on both sides and is not exchanged.
+    //   pack   side 0 (goes to the lower neighbour's upper ghosts): [g+cen, 2g+cen)
+    //   pack   side 1 (goes to the upper neighbour's lower ghosts): [n, n+g)
+    //   unpack side 0 (my lower ghosts): [0, g)
+    //   unpack side 1 (my upper ghosts): [g+n+cen, 2g+n+cen)
+    const int cen = (f.face == axis) ? 1 : 0;
+    const int width = g[axis];
+    int lo;
+    if (pack) lo = (side == 0) ? g[axis] + cen : n[axis];
+    else      lo = (side == 0) ? 0 : g[axis] + n[axis] + cen;
+    launch_slab_copy(st, f.p, f.n0, f.n1, f.n2, axis, lo, width, buffer + off,
+                     pack, &h->launches);
+    const int ext[3] = { f.n2, f.n1, f.n0 };
+    size_t cnt = (size_t) width;
+    for (int a = 0; a < 3; a++) if (a != axis) cnt *= (size_t) ext[a];
+    off += cnt;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+}  // namespace
+
+int vlct_halo_pack(vlct_handle* h, const vlct_block* b, int axis, int side,
+                   double* buffer)
+{ return halo_copy(h, b, axis, side, buffer, true); }
+
+int vlct_halo_unpack(vlct_handle* h, const vlct_block* b, int axis, int side,
+                     const double* buffer)
+{ return halo_copy(h, b, axis, side, const_cast<double*>(buffer), false); }
+
+}  // extern "C"

@@ -1,0 +1,785 @@
+// vlct_kernels.cu -- sm_100a kernels of the VL+CT block update.
+//
+// One stage of the integrator (EnzoMHDIntegratorStageCommands::
+// compute_update_stage, hydro-mhd/EnzoMHDIntegratorStageCommands.cpp:102-203)
+// is executed as
+//
+//   k_primitives   pressure (+ specific scalars) of the stage's input state
+//   k_flux<x|y|z>  fused  reconstruct -> longitudinal-B fix -> Riemann ->
+//                  passive-scalar fluxes; nothing but the fluxes reaches HBM
+//   k_edge_efield  fused  cell-centred E -> upwind weights -> edge E
+//   k_face_bfield  CT update of the three face-centred components
+//   k_update       fused  centred B -> flux divergence (+ dual-energy source,
+//                  gravity) -> conserved update -> floors / dual-energy sync
+//
+// where the reference makes ~25 separate full-array passes. The arrays
+// priml/primr/dUcons/weights/centre-E of the reference never exist here.
+//
+// Regions: every kernel works on the reference's stale-depth-trimmed index
+// boxes so that even the ghost-zone content left behind is identical.
+// All arithmetic is fp64; compile with -fmad=false for bit parity.
+#include "vlct_kernels.cuh"
+#include "vlct_physics.cuh"
+
+#include <cfloat>
+
+namespace vlct {
+
+namespace {
+
+struct Box { int lo[3], hi[3]; };  // [lo,hi) along x,y,z
+
+constexpr int kBlockX = 64;
+constexpr int kBlockY = 4;
+
+inline dim3 grid_for(const Box& b)
+{
+  const int nx = b.hi[0] - b.lo[0], ny = b.hi[1] - b.lo[1], nz = b.hi[2] - b.lo[2];
+  return dim3((unsigned) ((nx + kBlockX - 1) / kBlockX),
+              (unsigned) ((ny + kBlockY - 1) / kBlockY), (unsigned) nz);
+}
+inline bool empty(const Box& b)
+{ return b.hi[0] <= b.lo[0] || b.hi[1] <= b.lo[1] || b.hi[2] <= b.lo[2]; }
+
+#define VLCT_THREAD_IN_BOX(box, i, j, k)                                     \
+  const int i = (box).lo[0] + (int) (blockIdx.x * blockDim.x + threadIdx.x); \
+  const int j = (box).lo[1] + (int) (blockIdx.y * blockDim.y + threadIdx.y); \
+  const int k = (box).lo[2] + (int) blockIdx.z;                              \
+  if (i >= (box).hi[0] || j >= (box).hi[1] || k >= (box).hi[2]) return;
+
+__device__ __forceinline__ size_t cidx(const Geom& G, int k, int j, int i)
+{ return ((size_t) k * (size_t) G.my + (size_t) j) * (size_t) G.mx + (size_t) i; }
+
+/// index into the face-centred array of component d
+__device__ __forceinline__ size_t fidx(const Geom& G, int d, int k, int j, int i)
+{
+  const size_t n2 = (size_t) G.mx + (d == 0), n1 = (size_t) G.my + (d == 1);
+  return ((size_t) k * n1 + (size_t) j) * n2 + (size_t) i;
+}
+
+struct ScalarPtrs { double* p[kMaxPassive]; };
+
+// ---------------------------------------------------------------------------
+// primitives: EnzoPhysicsFluidProps::primitive_from_integration
+// (fluid-props/EnzoPhysicsFluidProps.cpp:64-138) and
+// EnzoComputePressure::compute_pressure (fluid-props/EnzoComputePressure.cpp:82-198)
+// ---------------------------------------------------------------------------
+template <bool MHD, bool DE>
+__device__ __forceinline__ double pressure_of(const Params& P, const State& u,
+                                              size_t c)
+{
+  const double gm1 = P.gamma - 1.0;
+  if (DE) {
+    return gm1 * __ldg(u.rho + c) * __ldg(u.eint + c);
+  } else {
+    const double vx = __ldg(u.vx + c), vy = __ldg(u.vy + c), vz = __ldg(u.vz + c);
+    const double ke = 0.5 * (vx * vx + vy * vy + vz * vz);
+    double me_den = 0.;
+    if (MHD) {
+      const double bx = __ldg(u.bx + c), by = __ldg(u.by + c), bz = __ldg(u.bz + c);
+      me_den = 0.5 * (bx * bx + by * by + bz * bz);
+    }
+    return gm1 * (__ldg(u.rho + c) * (__ldg(u.etot + c) - ke) - me_den);
+  }
+}
+
+template <bool MHD, bool DE>
+__global__ void __launch_bounds__(kBlockX * kBlockY)
+k_primitives(const Params P, const Geom G, const State u, double* prim_p,
+             const ScalarPtrs spec, const Box box)
+{
+  VLCT_THREAD_IN_BOX(box, i, j, k);
+  const size_t c = cidx(G, k, j, i);
+  prim_p[c] = pressure_of<MHD, DE>(P, u, c);
+  for (int s = 0; s < P.nsc; s++)
+    spec.p[s][c] = __ldg(u.sc[s] + c) / __ldg(u.rho + c);
+}
+
+// ---------------------------------------------------------------------------
+// fluxes along one dimension
+//   reconstruction  toolkit/EnzoReconstructorNN.cpp:14-48,
+//                   toolkit/EnzoReconstructorPLM.hpp:166-248
+//   B fix           toolkit/EnzoBfieldMethodCT.cpp:122-166
+//   Riemann         riemann/EnzoRiemannImpl.hpp:266-338
+//   passive flux    riemann/EnzoRiemannUtils.hpp:267-314
+// ---------------------------------------------------------------------------
+template <int RECON>
+__device__ __forceinline__ void
+recon_pair(const double* __restrict__ a, size_t c, ptrdiff_t sd, double theta,
+           bool use_floor, double floor_, double& wl, double& wr)
+{
+  if (RECON == RECON_NN) {
+    wl = __ldg(a + c);
+    wr = __ldg(a + c + sd);
+  } else {
+    const double w0 = __ldg(a + c - sd), w1 = __ldg(a + c);
+    const double w2 = __ldg(a + c + sd), w3 = __ldg(a + c + 2 * sd);
+    const double dvl = limited_slope<RECON>(w0, w1, w2, theta);
+    const double dvr = limited_slope<RECON>(w1, w2, w3, theta);
+    const double hl = dvl * 0.5, hr = dvr * 0.5;
+    wl = w1 + hl;   // left state of face c  <- cell c   (val + half_dv)
+    wr = w2 - hr;   // right state of face c <- cell c+1 (val - half_dv)
+    if (use_floor) {
+      wl = apply_floor(wl, floor_);
+      wr = apply_floor(wr, floor_);
+    }
+  }
+}
+
+template <int DIM, int RECON, int SOLVER, bool DE>
+__global__ void __launch_bounds__(kBlockX * kBlockY)
+k_flux(const Params P, const Geom G, const State u,
+       const double* __restrict__ prim_p, const ScalarPtrs spec,
+       const double* __restrict__ bi, const FluxSet F, const Box box)
+{
+  constexpr bool MHD = (SOLVER != SOLVER_HLLC);
+  constexpr int JD = (DIM + 1) % 3, KD = (DIM + 2) % 3;
+  VLCT_THREAD_IN_BOX(box, i, j, k);
+  const size_t c = cidx(G, k, j, i);
+  const ptrdiff_t sd = (DIM == 0) ? 1
+                     : (DIM == 1) ? (ptrdiff_t) G.mx
+                                  : (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
+  const double* v[3] = { u.vx, u.vy, u.vz };
+  const double* b[3] = { u.bx, u.by, u.bz };
+  const double theta = P.theta;
+
+  Prim wl, wr;
+  recon_pair<RECON>(u.rho, c, sd, theta, true, P.density_floor, wl.rho, wr.rho);
+  recon_pair<RECON>(v[DIM], c, sd, theta, false, 0., wl.vi, wr.vi);
+  recon_pair<RECON>(v[JD], c, sd, theta, false, 0., wl.vj, wr.vj);
+  recon_pair<RECON>(v[KD], c, sd, theta, false, 0., wl.vk, wr.vk);
+  recon_pair<RECON>(prim_p, c, sd, theta, true, P.pressure_floor, wl.p, wr.p);
+  if (MHD) {
+    recon_pair<RECON>(b[JD], c, sd, theta, false, 0., wl.bj, wr.bj);
+    recon_pair<RECON>(b[KD], c, sd, theta, false, 0., wl.bk, wr.bk);
+    // face f of the sweep <-> index f+1 of the face-centred array
+    const int di = (DIM == 0), dj = (DIM == 1), dk = (DIM == 2);
+    const double blong = __ldg(bi + fidx(G, DIM, k + dk, j + dj, i + di));
+    wl.bi = blong;
+    wr.bi = blong;
+  } else {
+    wl.bi = wl.bj = wl.bk = 0.;
+    wr.bi = wr.bj = wr.bk = 0.;
+  }
+
+  Flux f;
+  riemann_solve<SOLVER, DE>(P.gamma, wl, wr, f);
+
+  double* fm[3] = { F.mx_, F.my_, F.mz_ };
+  F.rho[c] = f.rho;
+  fm[DIM][c] = f.mi;
+  fm[JD][c] = f.mj;
+  fm[KD][c] = f.mk;
+  F.e[c] = f.e;
+  if (MHD) {
+    double* fb[3] = { F.bx, F.by, F.bz };
+    fb[JD][c] = f.bj;
+    fb[KD][c] = f.bk;
+  }
+  if (DE) {
+    F.eint[c] = f.eint;
+    F.vbar[c] = f.vbar;
+  }
+  for (int s = 0; s < P.nsc; s++) {
+    double sl, sr;
+    recon_pair<RECON>(spec.p[s], c, sd, theta, false, 0., sl, sr);
+    F.sc[s][c] = passive_flux(sl, sr, f.rho);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// constrained transport (toolkit/EnzoBfieldMethodCT.cpp)
+//   identify_upwind :170-216, compute_center_efield :267-292,
+//   compute_edge_ :384-457 (negate_Ej = true), update_bfield :617-687
+// ---------------------------------------------------------------------------
+struct EdgeArgs {
+  const double* v[3];
+  const double* b[3];
+  const double* frho[3];      // density flux of each sweep (upwind weights)
+  const double* fb[3][3];     // fb[sweep][component]
+  double* edge[3];
+  Box box[3];
+};
+
+__device__ __forceinline__ double upwind_weight(double dflux)
+{
+  if (dflux > 0) return 1.0;
+  if (dflux < 0) return 0.0;
+  return 0.5;
+}
+
+template <int D>
+__device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
+                                               int k, int j, int i)
+{
+  constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
+  const Box& bx = A.box[D];
+  if (i < bx.lo[0] || i >= bx.hi[0] || j < bx.lo[1] || j >= bx.hi[1] ||
+      k < bx.lo[2] || k >= bx.hi[2]) return;
+  const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
+  const ptrdiff_t sj = st[JD], sk = st[KD];
+  const size_t c = cidx(G, k, j, i);
+
+  // cell-centred E_d = -v_j B_k + v_k B_j
+  auto ecen = [&](size_t n) {
+    return (-__ldg(A.v[JD] + n) * __ldg(A.b[KD] + n) +
+            __ldg(A.v[KD] + n) * __ldg(A.b[JD] + n));
+  };
+  const double Ec = ecen(c), Ec_jp1 = ecen(c + sj), Ec_kp1 = ecen(c + sk),
+               Ec_jkp1 = ecen(c + sj + sk);
+  // E_d on j-faces is -F_j(B_k) (negation applied below), on k-faces +F_k(B_j)
+  const double* Fj = A.fb[JD][KD];
+  const double* Fk = A.fb[KD][JD];
+  const double Ej = __ldg(Fj + c), Ej_kp1 = __ldg(Fj + c + sk);
+  const double Ek = __ldg(Fk + c), Ek_jp1 = __ldg(Fk + c + sj);
+  const double Wj = upwind_weight(__ldg(A.frho[JD] + c));
+  const double Wj_kp1 = upwind_weight(__ldg(A.frho[JD] + c + sk));
+  const double Wk = upwind_weight(__ldg(A.frho[KD] + c));
+  const double Wk_jp1 = upwind_weight(__ldg(A.frho[KD] + c + sj));
+
+  const double dEdj_r = Wk_jp1 * (Ec_jp1 + Ej) + (1 - Wk_jp1) * (Ec_jkp1 + Ej_kp1);
+  const double dEdj_l = Wk * (-Ej - Ec) + (1 - Wk) * (-Ej_kp1 - Ec_kp1);
+  const double dEdk_r = Wj_kp1 * (Ec_kp1 - Ek) + (1 - Wj_kp1) * (Ec_jkp1 - Ek_jp1);
+  const double dEdk_l = Wj * (Ek - Ec) + (1 - Wj) * (Ek_jp1 - Ec_jp1);
+
+  double Ej_sum = Ej + Ej_kp1;
+  Ej_sum *= -1;
+  const double Ek_sum = Ek + Ek_jp1;
+  A.edge[D][c] = 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
+}
+
+__global__ void __launch_bounds__(kBlockX * kBlockY)
+k_edge_efield(const Geom G, const EdgeArgs A, const Box box)
+{
+  VLCT_THREAD_IN_BOX(box, i, j, k);
+  edge_component<0>(G, A, k, j, i);
+  edge_component<1>(G, A, k, j, i);
+  edge_component<2>(G, A, k, j, i);
+}
+
+struct FaceArgs {
+  const double* edge[3];
+  const double* bi0[3];
+  double* bi_out[3];
+  double dtd[3];            // dt / width along x,y,z
+  Box box[3];
+};
+
+template <int D>
+__device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
+                                               int k, int j, int i)
+{
+  constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
+  const Box& bx = A.box[D];
+  if (i < bx.lo[0] || i >= bx.hi[0] || j < bx.lo[1] || j >= bx.hi[1] ||
+      k < bx.lo[2] || k >= bx.hi[2]) return;
+  const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
+  // face f along D is edge index f-1 along D
+  const size_t e = cidx(G, k - (D == 2), j - (D == 1), i - (D == 0));
+  const double ek_Rj = __ldg(A.edge[KD] + e), ek_Lj = __ldg(A.edge[KD] + e - st[JD]);
+  const double ej_Rk = __ldg(A.edge[JD] + e), ej_Lk = __ldg(A.edge[JD] + e - st[KD]);
+  const double E_k_term = A.dtd[JD] * (ek_Rj - ek_Lj);
+  const double E_j_term = A.dtd[KD] * (ej_Rk - ej_Lk);
+  const size_t f = fidx(G, D, k, j, i);
+  A.bi_out[D][f] = __ldg(A.bi0[D] + f) - E_k_term + E_j_term;
+}
+
+__global__ void __launch_bounds__(kBlockX * kBlockY)
+k_face_bfield(const Geom G, const FaceArgs A, const Box box)
+{
+  VLCT_THREAD_IN_BOX(box, i, j, k);
+  face_component<0>(G, A, k, j, i);
+  face_component<1>(G, A, k, j, i);
+  face_component<2>(G, A, k, j, i);
+}
+
+// ---------------------------------------------------------------------------
+// update: toolkit/EnzoBfieldMethodCT.cpp:702-728 (centred B),
+// toolkit/EnzoIntegrationQuanUpdate.cpp:105-147,183-268,
+// toolkit/EnzoSourceInternalEnergy.cpp:16-92, toolkit/EnzoSourceGravity.cpp:17-69,
+// fluid-props/EnzoPhysicsFluidProps.cpp:162-290
+// ---------------------------------------------------------------------------
+struct UpdateArgs {
+  State u0, out;
+  FluxSet flux[3];
+  const double* bi_out[3];
+  const double* prim_p;
+  const double* accel[3];
+  double dtd[3];
+  double dt;
+  int gravity;
+  Box inner;                 // [s+1, m-s-1)^3: conserved update + floors
+};
+
+template <bool DE, bool MHD>
+__device__ __forceinline__ void
+floor_energy_and_sync(const Params& P, double rho, double vx, double vy,
+                      double vz, double bx, double by, double bz, double& etot,
+                      double& eint)
+{
+  const double inv_gm1 = 1. / (P.gamma - 1.);
+  const double inv_rho = 1. / rho;
+  const double eint_floor = P.pressure_floor * inv_gm1 * inv_rho;
+  const double v2 = (vx * vx + vy * vy + vz * vz);
+  double non_thermal_e = 0.5 * v2;
+  double b2 = 0;
+  if (MHD) {
+    b2 = (bx * bx + by * by + bz * bz);
+    non_thermal_e += (0.5 * b2 * inv_rho);
+  }
+  if (DE) {
+    const double eta = P.de_eta;
+    const double half_factor = (eta != 0.) ? 0.5 : 0.;
+    const double eint_1 = etot - non_thermal_e;
+    double cur_eint = eint;
+    const double cs2_1 = fmax(0., P.ggm1 * eint_1);
+    if ((cs2_1 > fmax(eta * v2, eta * b2 * inv_rho)) &&
+        (eint_1 > half_factor * cur_eint)) {
+      cur_eint = eint_1;
+    }
+    cur_eint = apply_floor(cur_eint, eint_floor);
+    eint = cur_eint;
+    etot = cur_eint + non_thermal_e;
+  } else {
+    const double etot_floor = eint_floor + non_thermal_e;
+    etot = apply_floor(etot, etot_floor);
+  }
+}
+
+template <bool MHD, bool DE>
+__global__ void __launch_bounds__(kBlockX * kBlockY)
+k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
+{
+  VLCT_THREAD_IN_BOX(box, i, j, k);
+  const size_t c = cidx(G, k, j, i);
+  const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
+
+  double bx = 0., by = 0., bz = 0.;
+  if (MHD) {
+    bx = 0.5 * (__ldg(A.bi_out[0] + fidx(G, 0, k, j, i)) +
+                __ldg(A.bi_out[0] + fidx(G, 0, k, j, i + 1)));
+    by = 0.5 * (__ldg(A.bi_out[1] + fidx(G, 1, k, j, i)) +
+                __ldg(A.bi_out[1] + fidx(G, 1, k, j + 1, i)));
+    bz = 0.5 * (__ldg(A.bi_out[2] + fidx(G, 2, k, j, i)) +
+                __ldg(A.bi_out[2] + fidx(G, 2, k + 1, j, i)));
+    A.out.bx[c] = bx;
+    A.out.by[c] = by;
+    A.out.bz[c] = bz;
+  }
+
+  const Box& in = A.inner;
+  if (i < in.lo[0] || i >= in.hi[0] || j < in.lo[1] || j >= in.hi[1] ||
+      k < in.lo[2] || k >= in.hi[2]) return;
+
+  // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
+  double d_rho = 0., d_mx = 0., d_my = 0., d_mz = 0., d_e = 0., d_eint = 0.;
+  double p_floored = 0.;
+  if (DE) p_floored = apply_floor(__ldg(A.prim_p + c), P.pressure_floor);
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const FluxSet& F = A.flux[d];
+    const size_t l = c - st[d];
+    const double dtdx = A.dtd[d];
+    d_rho -= dtdx * (__ldg(F.rho + c) - __ldg(F.rho + l));
+    d_mx -= dtdx * (__ldg(F.mx_ + c) - __ldg(F.mx_ + l));
+    d_my -= dtdx * (__ldg(F.my_ + c) - __ldg(F.my_ + l));
+    d_mz -= dtdx * (__ldg(F.mz_ + c) - __ldg(F.mz_ + l));
+    d_e -= dtdx * (__ldg(F.e + c) - __ldg(F.e + l));
+    if (DE) {
+      d_eint -= dtdx * (__ldg(F.eint + c) - __ldg(F.eint + l));
+      d_eint -= dtdx * p_floored * (__ldg(F.vbar + c) - __ldg(F.vbar + l));
+    }
+  }
+
+  const double old_rho = __ldg(A.u0.rho + c);
+  const double vx0 = __ldg(A.u0.vx + c), vy0 = __ldg(A.u0.vy + c),
+               vz0 = __ldg(A.u0.vz + c);
+  if (A.gravity) {
+    const double ax = __ldg(A.accel[0] + c), ay = __ldg(A.accel[1] + c),
+                 az = __ldg(A.accel[2] + c);
+    const double dt = A.dt;
+    d_mx += dt * old_rho * ax;
+    d_my += dt * old_rho * ay;
+    d_mz += dt * old_rho * az;
+    d_e += dt * old_rho * ((vx0 * ax) + (vy0 * ay) + (vz0 * az));
+  }
+
+  // passive scalars (conserved form)
+  for (int s = 0; s < P.nsc; s++) {
+    double d_s = 0.;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const double* Fs = A.flux[d].sc[s];
+      d_s -= A.dtd[d] * (__ldg(Fs + c) - __ldg(Fs + c - st[d]));
+    }
+    A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
+  }
+
+  double new_rho = old_rho + d_rho;
+  new_rho = apply_floor(new_rho, P.density_floor);
+  const double inv_new_rho = 1. / new_rho;
+  const double vx = (vx0 * old_rho + d_mx) * inv_new_rho;
+  const double vy = (vy0 * old_rho + d_my) * inv_new_rho;
+  const double vz = (vz0 * old_rho + d_mz) * inv_new_rho;
+  double etot = (__ldg(A.u0.etot + c) * old_rho + d_e) * inv_new_rho;
+  double eint = 0.;
+  if (DE) eint = (__ldg(A.u0.eint + c) * old_rho + d_eint) * inv_new_rho;
+
+  floor_energy_and_sync<DE, MHD>(P, new_rho, vx, vy, vz, bx, by, bz, etot, eint);
+
+  A.out.rho[c] = new_rho;
+  A.out.vx[c] = vx;
+  A.out.vy[c] = vy;
+  A.out.vz[c] = vz;
+  A.out.etot[c] = etot;
+  if (DE) A.out.eint[c] = eint;
+}
+
+// ---------------------------------------------------------------------------
+// timestep: hydro-mhd/EnzoMethodMHDVlct.cpp:551-588,
+//           hydro-mhd/EnzoMHDIntegratorStageCommands.cpp:299-366
+// ---------------------------------------------------------------------------
+template <bool MHD, bool DE>
+__global__ void __launch_bounds__(256)
+k_timestep(const Params P, const Geom G, const State u, double* pressure,
+           double dx, double dy, double dz, unsigned long long* dt_bits)
+{
+  const size_t n = G.cells();
+  double local_min = DBL_MAX;
+  for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < n;
+       c += (size_t) gridDim.x * blockDim.x) {
+    const double rho = u.rho[c];
+    const double vx = u.vx[c], vy = u.vy[c], vz = u.vz[c];
+    double bx = 0., by = 0., bz = 0.;
+    if (MHD) { bx = u.bx[c]; by = u.by[c]; bz = u.bz[c]; }
+    double p;
+    if (DE) {
+      double etot = u.etot[c], eint = u.eint[c];
+      floor_energy_and_sync<true, MHD>(P, rho, vx, vy, vz, bx, by, bz, etot, eint);
+      u.etot[c] = etot;
+      u.eint[c] = eint;
+      p = (P.gamma - 1.0) * rho * eint;
+    } else {
+      const double ke = 0.5 * (vx * vx + vy * vy + vz * vz);
+      double me_den = 0.;
+      if (MHD) me_den = 0.5 * (bx * bx + by * by + bz * bz);
+      p = (P.gamma - 1.0) * (rho * (u.etot[c] - ke) - me_den);
+    }
+    pressure[c] = p;
+    double cs;
+    if (MHD) cs = eos_cfast_max(P.gamma, rho, p, bx, by, bz);
+    else     cs = sqrt(eos_cs2(P.gamma, rho, p));
+    const double local_dt = min3(dx / (fabs(vx) + cs), dy / (fabs(vy) + cs),
+                                 dz / (fabs(vz) + cs));
+    local_min = std_min(local_min, local_dt);
+  }
+  // warp-shuffle min, then one atomic per block. Non-negative doubles order
+  // like their bit patterns; NaNs compare above +inf and so never win, which
+  // matches std::min(dtBaryons, local_dt) keeping the old value.
+  unsigned long long bits = (unsigned long long) __double_as_longlong(local_min);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
+    bits = (other < bits) ? other : bits;
+  }
+  __shared__ unsigned long long warp_min[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_min[warp] = bits;
+  __syncthreads();
+  if (warp == 0) {
+    bits = (lane < (int) (blockDim.x >> 5)) ? warp_min[lane]
+                                            : 0x7fefffffffffffffULL;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
+      bits = (other < bits) ? other : bits;
+    }
+    if (lane == 0) atomicMin(dt_bits, bits);
+  }
+}
+
+__global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+
+// ---------------------------------------------------------------------------
+// ghost-zone helpers (stand-ins for the refresh phase on a unigrid)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_wrap_axis(double* p, int n0, int n1, int n2, int axis, int n, int g, int cen)
+{
+  // threads enumerate the ghost layers only: 2g layers along `axis`
+  const int ext[3] = { n2, n1, n0 };
+  int sh[3] = { ext[0], ext[1], ext[2] };
+  sh[axis] = 2 * g;
+  const size_t total = (size_t) sh[0] * sh[1] * sh[2];
+  for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t) gridDim.x * blockDim.x) {
+    int idx[3];
+    idx[0] = (int) (t % sh[0]);
+    idx[1] = (int) ((t / sh[0]) % sh[1]);
+    idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
+    int a = idx[axis];
+    int dst, src;
+    if (a < g) { dst = a; src = a + n; }
+    else       { dst = g + n + cen + (a - g); src = dst - n; }
+    idx[axis] = dst;
+    const size_t d = ((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0];
+    idx[axis] = src;
+    const size_t s = ((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0];
+    p[d] = p[s];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
+            double* buffer, int pack)
+{
+  const int ext[3] = { n2, n1, n0 };
+  int sh[3] = { ext[0], ext[1], ext[2] };
+  sh[axis] = width;
+  const size_t total = (size_t) sh[0] * sh[1] * sh[2];
+  for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t) gridDim.x * blockDim.x) {
+    int idx[3];
+    idx[0] = (int) (t % sh[0]);
+    idx[1] = (int) ((t / sh[0]) % sh[1]);
+    idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
+    idx[axis] += lo;
+    const size_t f = ((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0];
+    if (pack) buffer[t] = field[f];
+    else      field[f] = buffer[t];
+  }
+}
+
+inline Box full_box(const Geom& G, int s)
+{
+  Box b;
+  b.lo[0] = b.lo[1] = b.lo[2] = s;
+  b.hi[0] = G.mx - s; b.hi[1] = G.my - s; b.hi[2] = G.mz - s;
+  return b;
+}
+
+inline ScalarPtrs scalar_ptrs(double* const* p, int n)
+{
+  ScalarPtrs s;
+  for (int i = 0; i < kMaxPassive; i++) s.p[i] = (i < n) ? p[i] : nullptr;
+  return s;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+void launch_primitives(cudaStream_t st, const Params& P, const Geom& G,
+                       const State& cur, const Scratch& S, int stale,
+                       long long* launches)
+{
+  const Box box = full_box(G, stale);
+  if (empty(box)) return;
+  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
+  const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
+  if (P.mhd) {
+    if (P.de) k_primitives<true, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
+    else      k_primitives<true, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
+  } else {
+    if (P.de) k_primitives<false, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
+    else      k_primitives<false, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
+  }
+  ++*launches;
+}
+
+namespace {
+
+template <int DIM, int RECON, int SOLVER>
+void flux_de(cudaStream_t st, bool de, dim3 grid, dim3 block, const Params& P,
+             const Geom& G, const State& cur, const double* prim_p,
+             const ScalarPtrs& spec, const double* bi, const FluxSet& F,
+             const Box& box)
+{
+  if (de) k_flux<DIM, RECON, SOLVER, true><<<grid, block, 0, st>>>(P, G, cur, prim_p, spec, bi, F, box);
+  else    k_flux<DIM, RECON, SOLVER, false><<<grid, block, 0, st>>>(P, G, cur, prim_p, spec, bi, F, box);
+}
+
+template <int DIM, int RECON>
+void flux_solver(cudaStream_t st, int solver, bool de, dim3 grid, dim3 block,
+                 const Params& P, const Geom& G, const State& cur,
+                 const double* prim_p, const ScalarPtrs& spec, const double* bi,
+                 const FluxSet& F, const Box& box)
+{
+  switch (solver) {
+  case VLCT_RIEMANN_HLLD:
+    flux_de<DIM, RECON, SOLVER_HLLD>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  case VLCT_RIEMANN_HLLE:
+    flux_de<DIM, RECON, SOLVER_HLLE>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  default:
+    flux_de<DIM, RECON, SOLVER_HLLC>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  }
+}
+
+template <int DIM>
+void flux_recon(cudaStream_t st, int recon, int solver, bool de, dim3 grid,
+                dim3 block, const Params& P, const Geom& G, const State& cur,
+                const double* prim_p, const ScalarPtrs& spec, const double* bi,
+                const FluxSet& F, const Box& box)
+{
+  switch (recon) {
+  case VLCT_RECON_NN:
+    flux_solver<DIM, RECON_NN>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  case VLCT_RECON_PLM_ATHENA:
+    flux_solver<DIM, RECON_PLM_ATHENA>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  default:
+    flux_solver<DIM, RECON_PLM_ENZO>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
+  }
+}
+
+}  // namespace
+
+void launch_flux(cudaStream_t st, const Params& P, const Geom& G, int dim,
+                 int recon, const State& cur, const Scratch& S,
+                 const FaceB& bi_cur, int cs, long long* launches)
+{
+  // non-stale faces: [cs, f-cs) on every axis of the face-shaped array
+  Box box = full_box(G, cs);
+  box.hi[dim] -= 1;
+  if (empty(box)) return;
+  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
+  const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
+  const double* bi = P.mhd ? bi_cur.bi[dim] : nullptr;
+  const bool de = P.de != 0;
+  switch (dim) {
+  case 0: flux_recon<0>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[0], box); break;
+  case 1: flux_recon<1>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[1], box); break;
+  default: flux_recon<2>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[2], box); break;
+  }
+  ++*launches;
+}
+
+void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
+               const State& cur, const Scratch& S, const FaceB& bi0,
+               const FaceB& bi_out, double dt, const double* width, int s,
+               long long* launches)
+{
+  const int m[3] = { G.mx, G.my, G.mz };
+  const dim3 block(kBlockX, kBlockY);
+  {
+    EdgeArgs A;
+    A.v[0] = cur.vx; A.v[1] = cur.vy; A.v[2] = cur.vz;
+    A.b[0] = cur.bx; A.b[1] = cur.by; A.b[2] = cur.bz;
+    for (int d = 0; d < 3; d++) {
+      A.frho[d] = S.flux[d].rho;
+      A.fb[d][0] = S.flux[d].bx; A.fb[d][1] = S.flux[d].by; A.fb[d][2] = S.flux[d].bz;
+      A.edge[d] = S.edge[d];
+      // CT.cpp:548-556: start 1 along d, 0 along j,k; stop (extent-1)
+      for (int a = 0; a < 3; a++) {
+        A.box[d].lo[a] = s + ((a == d) ? 1 : 0);
+        A.box[d].hi[a] = m[a] - s - 1;
+      }
+    }
+    Box box;   // union of the three component boxes
+    for (int a = 0; a < 3; a++) { box.lo[a] = s; box.hi[a] = m[a] - s - 1; }
+    if (!empty(box)) {
+      k_edge_efield<<<grid_for(box), block, 0, st>>>(G, A, box);
+      ++*launches;
+    }
+  }
+  {
+    FaceArgs A;
+    for (int d = 0; d < 3; d++) {
+      A.edge[d] = S.edge[d];
+      A.bi0[d] = bi0.bi[d];
+      A.bi_out[d] = bi_out.bi[d];
+      A.dtd[d] = dt / width[d];
+      // CT.cpp:646-667: interior faces along d, inner cells along j,k
+      for (int a = 0; a < 3; a++) {
+        A.box[d].lo[a] = s + 1;
+        A.box[d].hi[a] = (a == d) ? (m[a] - s) : (m[a] - s - 1);
+      }
+    }
+    Box box;
+    for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
+    if (!empty(box)) {
+      k_face_bfield<<<grid_for(box), block, 0, st>>>(G, A, box);
+      ++*launches;
+    }
+  }
+}
+
+void launch_update(cudaStream_t st, const Params& P, const Geom& G,
+                   const State& u0, const State& out, const Scratch& S,
+                   const FaceB& bi_out, const double* accel[3], bool gravity,
+                   double dt, const double* width, int s, long long* launches)
+{
+  UpdateArgs A;
+  A.u0 = u0; A.out = out;
+  for (int d = 0; d < 3; d++) {
+    A.flux[d] = S.flux[d];
+    A.bi_out[d] = bi_out.bi[d];
+    A.accel[d] = gravity ? accel[d] : nullptr;
+    A.dtd[d] = dt / width[d];
+  }
+  A.prim_p = S.prim_p;
+  A.dt = dt;
+  A.gravity = gravity ? 1 : 0;
+  A.inner = full_box(G, s + 1);
+  // with CT the centred B is rewritten on the whole [s, m-s)^3 region
+  const Box box = P.mhd ? full_box(G, s) : A.inner;
+  if (empty(box)) return;
+  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
+  if (P.mhd) {
+    if (P.de) k_update<true, true><<<grid, block, 0, st>>>(P, G, A, box);
+    else      k_update<true, false><<<grid, block, 0, st>>>(P, G, A, box);
+  } else {
+    if (P.de) k_update<false, true><<<grid, block, 0, st>>>(P, G, A, box);
+    else      k_update<false, false><<<grid, block, 0, st>>>(P, G, A, box);
+  }
+  ++*launches;
+}
+
+void launch_timestep(cudaStream_t st, const Params& P, const Geom& G,
+                     const State& u, double* pressure, const double* width,
+                     unsigned long long* dt_bits, long long* launches)
+{
+  k_set_u64<<<1, 1, 0, st>>>(dt_bits, 0x7fefffffffffffffULL);  // DBL_MAX
+  ++*launches;
+  const size_t n = G.cells();
+  int blocks = (int) ((n + 255) / 256);
+  const int max_blocks = 148 * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (P.mhd) {
+    if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+    else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+  } else {
+    if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+    else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+  }
+  ++*launches;
+}
+
+void launch_wrap_axis(cudaStream_t st, double* p, int n0, int n1, int n2,
+                      int axis, int n, int g, int cen, long long* launches)
+{
+  const int ext[3] = { n2, n1, n0 };
+  size_t total = (size_t) 2 * g;
+  for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
+  if (total == 0) return;
+  int blocks = (int) ((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_wrap_axis<<<blocks, 256, 0, st>>>(p, n0, n1, n2, axis, n, g, cen);
+  ++*launches;
+}
+
+void launch_slab_copy(cudaStream_t st, double* field, int n0, int n1, int n2,
+                      int axis, int lo, int width, double* buffer, bool pack,
+                      long long* launches)
+{
+  const int ext[3] = { n2, n1, n0 };
+  size_t total = (size_t) width;
+  for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
+  if (total == 0) return;
+  int blocks = (int) ((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_slab_copy<<<blocks, 256, 0, st>>>(field, n0, n1, n2, axis, lo, width, buffer, pack ? 1 : 0);
+  ++*launches;
+}
+
+}  // namespace vlct

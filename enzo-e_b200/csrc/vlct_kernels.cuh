@@ -1,0 +1,100 @@
+// vlct_kernels.cuh -- launch interface between the C ABI (vlct_api.cu) and the
+// CUDA kernels (vlct_kernels.cu). Plain structs of device pointers; no ownership.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstddef>
+
+#include "../../include/vlct.h"
+
+namespace vlct {
+
+constexpr int kMaxPassive = VLCT_MAX_PASSIVE;
+
+/// extents of a cell-centred array including ghost zones
+struct Geom {
+  int mx, my, mz;
+  __host__ __device__ size_t cells() const
+  { return (size_t) mx * (size_t) my * (size_t) mz; }
+};
+
+/// the integration quantities of one state (all cell-centred, shape mz,my,mx)
+struct State {
+  double *rho, *vx, *vy, *vz, *etot, *eint;
+  double *bx, *by, *bz;
+  double *sc[kMaxPassive];
+};
+
+/// face-centred B: bi[0] (mz,my,mx+1), bi[1] (mz,my+1,mx), bi[2] (mz+1,my,mx)
+struct FaceB { double *bi[3]; };
+
+/// fluxes through the faces along one dimension. Every array uses the
+/// cell-centred strides (mz,my,mx); entry (k,j,i) is the face between cell
+/// (k,j,i) and its +1 neighbour along the sweep dimension.
+struct FluxSet {
+  double *rho, *mx_, *my_, *mz_, *e;
+  double *bx, *by, *bz;      // the component along the sweep is unused (NULL)
+  double *eint, *vbar;       // dual energy only
+  double *sc[kMaxPassive];
+};
+
+/// run-time constants of a handle
+struct Params {
+  double gamma, theta;
+  double density_floor, pressure_floor;
+  double de_eta;
+  double ggm1;          // (double)(float)(gamma*(gamma-1)), FluidProps.cpp:234
+  int nsc;
+  int mhd, de;
+  int riemann, recon;
+};
+
+struct Scratch {
+  State temp;           // temp_integration_map
+  FaceB tbi;            // temp_bfieldi_l_
+  FluxSet flux[3];
+  double *prim_p;       // primitive pressure of the current stage
+  double *prim_sc[kMaxPassive]; // specific passive scalars
+  double *edge[3];      // edge-centred E (cell strides)
+};
+
+/// primitive pressure (+ specific scalars) over [s, m-s)^3
+void launch_primitives(cudaStream_t st, const Params& P, const Geom& G,
+                       const State& cur, const Scratch& S, int stale,
+                       long long* launches);
+
+/// reconstruct -> fix longitudinal B -> Riemann -> passive fluxes along dim
+void launch_flux(cudaStream_t st, const Params& P, const Geom& G, int dim,
+                 int recon, const State& cur, const Scratch& S,
+                 const FaceB& bi_cur, int cur_stale, long long* launches);
+
+/// constrained transport: edge E, face-B update
+void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
+               const State& cur, const Scratch& S, const FaceB& bi0,
+               const FaceB& bi_out, double dt, const double* width, int stale,
+               long long* launches);
+
+/// centred B + flux divergence + sources + conserved update + floors/sync
+void launch_update(cudaStream_t st, const Params& P, const Geom& G,
+                   const State& u0, const State& out, const Scratch& S,
+                   const FaceB& bi_out, const double* accel[3], bool gravity,
+                   double dt, const double* width, int stale,
+                   long long* launches);
+
+/// DE sync + pressure field + CFL minimum over all cells; *dt_bits receives
+/// the bit pattern of the minimum local dt (not yet multiplied by courant)
+void launch_timestep(cudaStream_t st, const Params& P, const Geom& G,
+                     const State& u, double* pressure, const double* width,
+                     unsigned long long* dt_bits, long long* launches);
+
+/// periodic self-refresh of one field along one axis
+void launch_wrap_axis(cudaStream_t st, double* p, int n0, int n1, int n2,
+                      int axis, int n, int g, int cen, long long* launches);
+
+/// halo slab pack / unpack of one field along one axis
+/// lo..lo+g: range along the axis; the slab spans the full other extents
+void launch_slab_copy(cudaStream_t st, double* field, int n0, int n1, int n2,
+                      int axis, int lo, int width, double* buffer, bool pack,
+                      long long* launches);
+
+}  // namespace vlct

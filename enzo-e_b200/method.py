@@ -1,0 +1,191 @@
+"""Host-side mirror of the reference's Method plugin for VL+CT.
+
+`EnzoMethodMHDVlct` keeps the reference's surface -- construction from the
+parameter-file keys, `compute(block)`, `timestep(block)`, `name()`
+(src/Enzo/hydro-mhd/EnzoMethodMHDVlct.hpp:86-127) -- and forwards to the C ABI
+in csrc/libvlct_b200.so. `Block` stands in for the few things the Method reads
+from a Cello Block: the field arrays (Field::view), the active size and ghost
+depth, EnzoBlock::CellWidth and Block::dt().
+
+Fields may live in host memory (numpy arrays; staged through the GPU inside
+each call) or in device memory (torch CUDA tensors; the performance mode).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from . import lib as _libmod
+from .lib import VlctError
+
+# parameter-file keys understood by vlct_config_set
+METHOD_KEYS = ("riemann_solver", "reconstruct_method", "theta_limiter",
+               "mhd_choice", "time_scheme", "courant")
+
+
+def config_from_parameters(params, n_passive=0, has_acceleration=False):
+    """Build a vlct_config from {parameter-file key: value}.
+
+    Keys may be given in full ("Method:mhd_vlct:riemann_solver",
+    "Physics:fluid_props:eos:gamma") or, for the Method group, by their last
+    component ("riemann_solver")."""
+    lib = _libmod.load()
+    cfg = abi.VlctConfig()
+    lib.vlct_config_init(C.byref(cfg))
+    err = C.create_string_buffer(512)
+    for key, value in params.items():
+        full = key if ":" in key else "Method:mhd_vlct:" + key
+        if isinstance(value, bool):
+            value = "true" if value else "false"
+        elif isinstance(value, float):
+            value = repr(value)
+        rc = lib.vlct_config_set(C.byref(cfg), full.encode(),
+                                 str(value).encode(), err, len(err))
+        if rc != abi.VLCT_OK:
+            raise VlctError(rc, err.value.decode())
+    cfg.n_passive = n_passive
+    cfg.has_acceleration = 1 if has_acceleration else 0
+    return cfg
+
+
+class Block:
+    """The slice of a Cello Block that the Method touches."""
+
+    def __init__(self, fields, n, g, cell_width, passive=(), dt=0.0,
+                 stream=None):
+        self.fields = fields          # name -> numpy array | torch.Tensor
+        self.n = tuple(n)
+        self.g = tuple(g)
+        self.cell_width = tuple(cell_width)
+        self.passive = tuple(passive)
+        self.dt = dt
+        self.compute_done_count = 0
+        first = next(iter(fields.values()))
+        self.on_device = not isinstance(first, np.ndarray)
+        self._c = self._build(stream)
+
+    def compute_done(self):
+        """Method::compute must end by calling block->compute_done()
+        (src/Cello/problem_Method.hpp:47-55)."""
+        self.compute_done_count += 1
+
+    def _ptr(self, name, arr):
+        shape = abi.field_shape(name, *self.n, *self.g)
+        if tuple(arr.shape) != shape:
+            raise ValueError(f"{name}: shape {tuple(arr.shape)} != {shape}")
+        if self.on_device:
+            import torch
+            if arr.dtype != torch.float64 or not arr.is_contiguous() \
+                    or not arr.is_cuda:
+                raise ValueError(f"{name}: need a contiguous fp64 CUDA tensor")
+            return C.cast(arr.data_ptr(), C.POINTER(C.c_double))
+        if arr.dtype != np.float64 or not arr.flags.c_contiguous:
+            raise ValueError(f"{name}: need a C-contiguous float64 array")
+        return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+    def _build(self, stream):
+        nx, ny, nz = self.n
+        gx, gy, gz = self.g
+        blk = abi.VlctBlock(
+            nx=nx, ny=ny, nz=nz, gx=gx, gy=gy, gz=gz,
+            dx=self.cell_width[0], dy=self.cell_width[1],
+            dz=self.cell_width[2],
+            mem_space=abi.MEM_DEVICE if self.on_device else abi.MEM_HOST,
+            stream=stream)
+        for name in abi.CELL_FIELDS + abi.FACE_FIELDS + abi.OTHER_FIELDS:
+            arr = self.fields.get(name)
+            if arr is not None:
+                setattr(blk, name, self._ptr(name, arr))
+        for i, name in enumerate(self.passive):
+            blk.passive[i] = self._ptr("density", self.fields[name])
+        return blk
+
+    @property
+    def c_block(self):
+        return self._c
+
+
+class EnzoMethodMHDVlct:
+    """`Method` plugin "mhd_vlct", computed on the GPU.
+
+    Mirrors src/Enzo/hydro-mhd/EnzoMethodMHDVlct.{hpp,cpp}: the constructor
+    validates the parameters exactly as the reference's constructors do and
+    raises `VlctError` where the reference would ASSERT/ERROR."""
+
+    def __init__(self, params=None, config=None, n_passive=0,
+                 has_acceleration=False):
+        self._lib = _libmod.load()
+        if config is None:
+            config = config_from_parameters(params or {}, n_passive,
+                                            has_acceleration)
+        self.config = config
+        self._h = C.c_void_p()
+        rc = self._lib.vlct_create(C.byref(config), C.byref(self._h))
+        if rc != abi.VLCT_OK:
+            msg = self._lib.vlct_last_error(self._h).decode() if self._h \
+                else self._lib.vlct_status_string(rc).decode()
+            if self._h:
+                self._lib.vlct_destroy(self._h)
+                self._h = C.c_void_p()
+            raise VlctError(rc, msg)
+
+    # -- Method interface ---------------------------------------------------
+    def name(self):
+        return self._lib.vlct_name().decode()
+
+    def compute(self, block, dt=None):
+        """EnzoMethodMHDVlct::compute(Block*): advance by block.dt in place."""
+        dt = block.dt if dt is None else dt
+        self._check(self._lib.vlct_compute(self._h, C.byref(block.c_block),
+                                           float(dt)))
+        block.compute_done()
+
+    def timestep(self, block):
+        """EnzoMethodMHDVlct::timestep(Block*) (already times courant)."""
+        out = C.c_double(0.0)
+        self._check(self._lib.vlct_timestep(self._h, C.byref(block.c_block),
+                                            C.byref(out)))
+        return out.value
+
+    # -- refresh stand-ins ----------------------------------------------------
+    def refresh_periodic(self, block, axes=7):
+        self._check(self._lib.vlct_refresh_periodic(
+            self._h, C.byref(block.c_block), axes))
+
+    def halo_bytes(self, block, axis):
+        return self._lib.vlct_halo_bytes(self._h, C.byref(block.c_block), axis)
+
+    def halo_pack(self, block, axis, side, buffer):
+        self._check(self._lib.vlct_halo_pack(
+            self._h, C.byref(block.c_block), axis, side,
+            C.cast(buffer.data_ptr(), C.POINTER(C.c_double))))
+
+    def halo_unpack(self, block, axis, side, buffer):
+        self._check(self._lib.vlct_halo_unpack(
+            self._h, C.byref(block.c_block), axis, side,
+            C.cast(buffer.data_ptr(), C.POINTER(C.c_double))))
+
+    # -- instrumentation --------------------------------------------------------
+    def kernel_launches(self):
+        return int(self._lib.vlct_kernel_launches(self._h))
+
+    def scratch_bytes(self):
+        return int(self._lib.vlct_scratch_bytes(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.vlct_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vlct_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != abi.VLCT_OK:
+            raise VlctError(rc, self._lib.vlct_last_error(self._h).decode())
