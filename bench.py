@@ -1,0 +1,491 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the VL+CT hot path (EnzoMethodMHDVlct) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (reference CPU path)
+
+Workload (config.workload): BASELINE.json configs[2], the 3-D Orszag-Tang
+vortex on 512^3 cells per GPU, MHD VL+CT with PLM (theta 1.5) + HLLD + CT,
+fp64, one periodic brick per GPU (weak scaling: the global grid grows with N).
+
+A "step" is one full simulation cycle of the path on one block per GPU:
+    timestep() -> min over ranks -> ghost refresh (device wrap / NCCL exchange)
+    -> compute() (both VL stages incl. CT)
+metric = cell-updates/s = active cells of all ranks * steps / seconds, timed on
+the device with CUDA events, max over ranks.
+
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the roofline
+accounting (algorithmic bytes per kernel launch and per cell-update).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/sec (fp64 VL+CT MHD)"
+UNIT = "cell-updates/s"
+B_ALG_STEP = 416.0        # compulsory bytes per MHD cell-update
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+# --------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------
+PARAMS = {
+    "Method:mhd_vlct:mhd_choice": "constrained_transport",
+    "Method:mhd_vlct:riemann_solver": "hlld",
+    "Method:mhd_vlct:reconstruct_method": "plm",
+    "Method:mhd_vlct:theta_limiter": 1.5,
+    "Method:mhd_vlct:time_scheme": "vl",
+    "Method:mhd_vlct:courant": 0.3,
+    "Physics:fluid_props:eos:gamma": 5.0 / 3.0,
+    "Physics:fluid_props:floors:density": 1e-200,
+    "Physics:fluid_props:floors:pressure": 1e-200,
+}
+GHOST = (3, 3, 3)
+
+
+def workload_config(size, world, grid):
+    return {"workload": f"Orszag-Tang vortex, {size}^3 cells per GPU "
+                        f"(global {size * grid[0]}x{size * grid[1]}x{size * grid[2]}), "
+                        "MHD VL+CT: PLM(theta=1.5) + HLLD + CT, periodic",
+            "cells_per_gpu": size ** 3, "ghost_depth": 3,
+            "riemann_solver": "hlld", "reconstruct_method": "plm",
+            "courant": 0.3, "gamma": 5.0 / 3.0,
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} bricks",
+            "step": "timestep + dt min-reduce + ghost refresh + compute",
+            "l2_policy": "inputs (>=1.1 GB per field) exceed the 126 MB L2"}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_sample(seconds_target=12.0, block=48, threads=None, steps_cap=200):
+    """Time the reference CPU path (oracle/_ref when present, else the oracle
+    port) on `threads` host threads, one `block`^3 brick of the Orszag-Tang
+    workload per thread, for about `seconds_target` seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import oracle
+    from enzo_e_b200 import abi, problems
+
+    threads = threads or cpu_threads()
+    kind = "ref" if oracle.have_ref() else "oracle"
+    if kind == "oracle" and not oracle.have_oracle():
+        oracle.build("oracle")
+    # same parameters as PARAMS, set directly on the struct so that the CPU
+    # arm never loads the CUDA library
+    cfg = abi.default_config()
+    cfg.mhd_choice = abi.MHD_CHOICE["constrained_transport"]
+    cfg.riemann_solver = abi.RIEMANN["hlld"]
+    cfg.reconstruct_method = abi.RECON["plm"]
+    cfg.theta_limiter = 1.5
+    cfg.courant = 0.3
+    cfg.gamma = 5.0 / 3.0
+    cfg.density_floor = cfg.pressure_floor = 1e-200
+    n, g = (block, block, block), GHOST
+    width = (1.0 / 512,) * 3
+    workers = []
+    for t in range(threads):
+        lower = ((t % 8) * block * width[0], ((t // 8) % 8) * block * width[1],
+                 (t // 64) * block * width[2])
+        f = {k: v.numpy().copy() for k, v in problems.orszag_tang(
+            n, g, lower, width, device="cpu").items()}
+        blk = oracle.numpy_block(f, n, g, width)
+        workers.append((oracle.CpuMethod(cfg, g, kind=kind), blk, f))
+
+    def one_step(w):
+        m, blk, _ = w
+        dt = m.timestep(blk)
+        oracle.refresh_periodic(blk, 0)
+        m.compute(blk, dt)
+
+    # calibrate with one step on one thread
+    t0 = time.perf_counter()
+    one_step(workers[0])
+    per_step = time.perf_counter() - t0
+    nsteps = max(2, min(steps_cap, int(seconds_target / max(per_step, 1e-6))))
+
+    def loop(w):
+        for _ in range(nsteps):
+            one_step(w)
+
+    ths = [threading.Thread(target=loop, args=(w,)) for w in workers]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    elapsed = time.perf_counter() - t0
+    for m, _, _ in workers:
+        m.close()
+    cells = threads * block ** 3 * nsteps
+    return {"value": cells / elapsed, "unit": UNIT, "cores": threads,
+            "kind": "reference" if kind == "ref" else "port",
+            "sample": f"{threads} threads x one {block}^3 brick of the "
+                      f"Orszag-Tang workload x {nsteps} full steps "
+                      f"(timestep+refresh+compute), {elapsed:.1f} s",
+            "seconds": elapsed, "steps": nsteps}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    grid = _grid(args.gpus)
+    t_all = time.perf_counter()
+    samples = []
+    for _ in range(args.warmup):
+        run_cpu_sample(seconds_target=1.0, block=args.cpu_block)
+    per = max(2.0, min(20.0, 150.0 / max(1, args.steps)))
+    for _ in range(args.steps):
+        samples.append(run_cpu_sample(seconds_target=per, block=args.cpu_block))
+    value = statistics.median(s["value"] for s in samples)
+    cells_per_step = args.size ** 3 * args.gpus
+    best = samples[0]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * cells_per_step / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.size, args.gpus, grid),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": best["cores"],
+                             "kind": best["kind"], "sample": best["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "ms_per_step = time the CPU path would need for one step of "
+                    "the full workload at the sampled per-cell rate",
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def _grid(world):
+    from enzo_e_b200.domain import proc_grid
+    return proc_grid(world)
+
+
+# kernel name -> algorithmic bytes per processed unit (DESIGN.md "Measurement")
+def kernel_bytes_per_unit(name):
+    table = {"k_flux": 15 * 8,       # 7 cell fields + face B in, 7 fluxes out
+             "k_update": 31 * 8,     # 15 fluxes + 3 face B + 5 U0 in, 8 out
+             "k_edge_efield": 18 * 8,
+             "k_face_bfield": 9 * 8,
+             "k_primitives": 9 * 8,
+             "k_timestep": 9 * 8}
+    for key, val in table.items():
+        if name.startswith(key):
+            return val
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from enzo_e_b200 import problems
+    from enzo_e_b200.domain import Domain
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the VL+CT path has no "
+                         "CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    domain = Domain(rank, world)
+    grid = domain.grid
+    size = args.size
+    n_local = (size, size, size)
+    width = tuple(1.0 / (size * grid[a]) for a in range(3))
+    lower = domain.lower_corner(n_local, width)
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        fields = problems.orszag_tang(n_local, GHOST, lower, width, device=dev)
+        method = EnzoMethodMHDVlct(PARAMS)
+        block = Block(fields, n_local, GHOST, width, stream=stream.cuda_stream)
+        block.stream_is_current = True
+
+        def step():
+            dt = method.timestep(block)
+            dt = domain.global_dt(dt, dev)
+            domain.refresh(method, block)
+            method.compute(block, dt)
+            return dt
+
+        def sync_all():
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+
+        for _ in range(args.warmup):
+            step()
+        sync_all()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = method.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            dt = step()
+        e1.record(stream)
+        sync_all()
+        elapsed_ms = e0.elapsed_time(e1)
+        launches = method.kernel_launches() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        cells = size ** 3 * world * args.steps
+        value = cells / (elapsed_ms * 1e-3)
+
+        # ---- compute()-only timing and per-kernel profile (live, same process)
+        sync_all()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(max(2, args.steps // 2)):
+            method.compute(block, dt)
+        c1.record(stream)
+        sync_all()
+        compute_ms = c0.elapsed_time(c1) / max(2, args.steps // 2)
+
+        method.profile(True)
+        nprof = 2
+        for _ in range(nprof):
+            step()
+        sync_all()
+        report = method.profile_report()
+        method.profile(False)
+
+    hbm_gbs, peak_kind = measured_peaks()
+    # dominant kernel = largest share of the step
+    groups = {}
+    for name, (ms, calls) in report.items():
+        groups[name] = (ms, calls)
+    total_prof_ms = sum(ms for ms, _ in groups.values())
+    dom = max(groups, key=lambda k: groups[k][0])
+    dom_ms, dom_calls = groups[dom]
+    m = size + 2 * GHOST[0]
+    # units per launch of a PLM flux kernel: faces in [2, m-3) x [2, m-2)^2
+    if dom.startswith("k_flux") and dom.endswith("plm"):
+        units = (m - 5) * (m - 4) ** 2
+    elif dom.startswith("k_flux"):
+        units = (m - 1) * m * m
+    else:
+        units = m ** 3
+    bpu = kernel_bytes_per_unit(dom) or 0
+    dom_avg_ms = dom_ms / max(1, dom_calls)
+    achieved = units * bpu / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    traffic = None
+    try:   # filled in from the committed ncu capture, if any
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved,
+                "peak": hbm_gbs, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / hbm_gbs, "traffic": traffic,
+                "algorithmic_bytes_per_launch": units * bpu,
+                "avg_launch_ms": dom_avg_ms,
+                "share_of_step": dom_ms / total_prof_ms if total_prof_ms else None}
+    step_gbs = value * B_ALG_STEP / 1e9 / world
+    roofline_step = {"bound": "hbm", "bytes_per_cell_update": B_ALG_STEP,
+                     "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": step_gbs / hbm_gbs,
+                     "note": "per-GPU; 416 B = compulsory traffic of one MHD "
+                             "cell-update (SURVEY 8d); the path is bound by "
+                             "the FP64 pipe, see DESIGN.md"}
+    kernels = {k: {"ms_per_step": ms / nprof, "launches_per_step": calls / nprof}
+               for k, (ms, calls) in sorted(groups.items())}
+
+    # ---- end-to-end through the C ABI with HOST (pinned) buffers ----------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, method, fields, n_local, width, world, dev)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_baseline = run_cpu_sample(seconds_target=args.cpu_seconds,
+                                      block=args.cpu_block)
+        cpu_baseline = {k: cpu_baseline[k] for k in
+                        ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": elapsed_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(size, world, grid),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "roofline_step": roofline_step,
+                "cpu_baseline": cpu_baseline,
+                "compute_only_ms": compute_ms,
+                "compute_only_value": size ** 3 / (compute_ms * 1e-3),
+                "kernels": kernels, "last_dt": dt,
+                "scratch_gb": method.scratch_bytes() / 1e9}
+        print(json.dumps(line), flush=True)
+    method.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, method, fields, n_local, width, world, dev):
+    """Same metric through the C ABI with HOST buffers: every step copies the
+    block's fields pinned-host -> device, runs timestep + compute, and copies
+    the results back (all inside vlct_timestep / vlct_compute)."""
+    import torch
+    import torch.distributed as dist
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    from enzo_e_b200 import problems
+
+    host = {}
+    for k, v in fields.items():
+        t = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        t.copy_(v)
+        host[k] = t
+    torch.cuda.synchronize(dev)
+    host_np = {k: v.numpy() for k, v in host.items()}
+    m2 = EnzoMethodMHDVlct(PARAMS)
+    hb = Block(host_np, n_local, GHOST, width)
+    nbytes = problems.field_bytes(host)
+    cell_bytes = host["density"].numel() * 8
+    # timestep: H2D all fields, D2H pressure; compute: H2D all, D2H all but pressure
+    h2d = 2 * nbytes
+    d2h = cell_bytes + (nbytes - cell_bytes)
+    steps = max(2, min(args.steps, 4))
+    for _ in range(1):
+        dt = m2.timestep(hb)
+        m2.compute(hb, dt)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dt = m2.timestep(hb)
+        m2.compute(hb, dt)
+    elapsed = time.perf_counter() - t0
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    m2.close()
+    cells = n_local[0] * n_local[1] * n_local[2] * world * steps
+    return {"value": cells / elapsed, "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": 1e3 * elapsed / steps,
+            "path": "vlct_timestep + vlct_compute with mem_space=HOST "
+                    "(pinned host arrays, copies inside the calls)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512,
+                    help="cells per axis per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-block", type=int, default=48)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

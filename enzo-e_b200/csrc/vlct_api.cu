@@ -37,6 +37,7 @@ struct vlct_handle {
   vlct_block mirror;
   std::vector<void*> mirror_allocs;
   long long launches = 0;
+  Profiler prof;
   std::string last_error;
 };
 
@@ -287,18 +288,19 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     const FaceB& bi_cur = (stage == 0) ? bi : h->S.tbi;
     const FaceB& bi_out = (stage == 1 || nstages == 1) ? bi : h->S.tbi;
 
-    launch_primitives(st, P, G, cur, h->S, stale, &h->launches);
+    const LaunchCtx ctx{ st, &h->launches, &h->prof };
+    launch_primitives(ctx, P, G, cur, h->S, stale);
     const int cs = stale + immediate_staling(recon);
     for (int dim = 0; dim < 3; dim++)
-      launch_flux(st, P, G, dim, recon, cur, h->S, bi_cur, cs, &h->launches);
+      launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs);
     if (P.mhd)
-      launch_ct(st, P, G, cur, h->S, bi, bi_out, cur_dt, width, cs, &h->launches);
+      launch_ct(ctx, P, G, cur, h->S, bi, bi_out, cur_dt, width, cs);
     // gravity: full step only, i.e. stage index 1
     // (EnzoMHDIntegratorStageCommands.cpp:181,279)
     const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
                          accel[0] != nullptr;
-    launch_update(st, P, G, ext, out, h->S, bi_out, accel, gravity, cur_dt,
-                  width, cs, &h->launches);
+    launch_update(ctx, P, G, ext, out, h->S, bi_out, accel, gravity, cur_dt,
+                  width, cs);
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -424,7 +426,7 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
     db = &h->mirror;
   }
   const State u = state_of(h, db);
-  launch_timestep(st, h->P, G, u, db->pressure, width, h->d_dt_bits, &h->launches);
+  launch_timestep(LaunchCtx{ st, &h->launches, &h->prof }, h->P, G, u, db->pressure, width, h->d_dt_bits);
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
@@ -458,6 +460,42 @@ int vlct_synchronize(vlct_handle* h)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
   CUDA_TRY(h, cudaDeviceSynchronize());
+  return VLCT_OK;
+}
+
+// ---- per-kernel timing ---------------------------------------------------------
+int vlct_profile_enable(vlct_handle* h, int on)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  h->prof.collect();
+  h->prof.enabled = (on != 0);
+  return VLCT_OK;
+}
+
+int vlct_profile_reset(vlct_handle* h)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  h->prof.reset();
+  return VLCT_OK;
+}
+
+int vlct_profile_count(vlct_handle* h)
+{
+  if (h == nullptr) return 0;
+  h->prof.collect();
+  return (int) h->prof.names.size();
+}
+
+int vlct_profile_get(vlct_handle* h, int index, char* name, int name_len,
+                     double* total_ms, long long* calls)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  h->prof.collect();
+  if (index < 0 || index >= (int) h->prof.names.size())
+    return fail(h, VLCT_ERR_INTERNAL, "profile index out of range");
+  if (name && name_len > 0) snprintf(name, (size_t) name_len, "%s", h->prof.names[index].c_str());
+  if (total_ms) *total_ms = h->prof.total_ms[index];
+  if (calls) *calls = h->prof.calls[index];
   return VLCT_OK;
 }
 
@@ -499,8 +537,8 @@ int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
       return fail(h, VLCT_ERR_INVALID_BLOCK,
                   "periodic refresh needs n >= ghost depth along every axis");
     for (const RefreshField& f : fields)
-      launch_wrap_axis(st, f.p, f.n0, f.n1, f.n2, axis, n[axis], g[axis],
-                       f.face == axis ? 1 : 0, &h->launches);
+      launch_wrap_axis(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
+                       f.n2, axis, n[axis], g[axis], f.face == axis ? 1 : 0);
   }
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
@@ -551,8 +589,8 @@ int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
     int lo;
     if (pack) lo = (side == 0) ? g[axis] + cen : n[axis];
     else      lo = (side == 0) ? 0 : g[axis] + n[axis] + cen;
-    launch_slab_copy(st, f.p, f.n0, f.n1, f.n2, axis, lo, width, buffer + off,
-                     pack, &h->launches);
+    launch_slab_copy(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
+                     f.n2, axis, lo, width, buffer + off, pack);
     const int ext[3] = { f.n2, f.n1, f.n0 };
     size_t cnt = (size_t) width;
     for (int a = 0; a < 3; a++) if (a != axis) cnt *= (size_t) ext[a];

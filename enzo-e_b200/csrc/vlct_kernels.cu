@@ -29,6 +29,15 @@ namespace {
 
 struct Box { int lo[3], hi[3]; };  // [lo,hi) along x,y,z
 
+/// counts the launch and, when profiling is on, brackets it with CUDA events
+struct ScopedLaunch {
+  const LaunchCtx& c;
+  ScopedLaunch(const LaunchCtx& ctx, const char* name) : c(ctx)
+  { if (c.prof && c.prof->enabled) c.prof->begin(c.st, name); }
+  ~ScopedLaunch()
+  { if (c.prof && c.prof->enabled) c.prof->end(c.st); ++*c.launches; }
+};
+
 constexpr int kBlockX = 64;
 constexpr int kBlockY = 4;
 
@@ -568,16 +577,58 @@ inline ScalarPtrs scalar_ptrs(double* const* p, int n)
 }  // namespace
 
 // ---------------------------------------------------------------------------
+// profiler
+// ---------------------------------------------------------------------------
+void Profiler::begin(cudaStream_t st, const char* name)
+{
+  Entry e;
+  e.name = name;
+  cudaEventCreate(&e.beg);
+  cudaEventCreate(&e.end);
+  cudaEventRecord(e.beg, st);
+  pending.push_back(e);
+}
+
+void Profiler::end(cudaStream_t st)
+{ cudaEventRecord(pending.back().end, st); }
+
+void Profiler::collect()
+{
+  for (Entry& e : pending) {
+    cudaEventSynchronize(e.end);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.beg, e.end);
+    size_t idx = 0;
+    for (; idx < names.size(); idx++) if (names[idx] == e.name) break;
+    if (idx == names.size()) {
+      names.push_back(e.name); total_ms.push_back(0.); calls.push_back(0);
+    }
+    total_ms[idx] += (double) ms;
+    calls[idx] += 1;
+    cudaEventDestroy(e.beg);
+    cudaEventDestroy(e.end);
+  }
+  pending.clear();
+}
+
+void Profiler::reset()
+{
+  collect();
+  names.clear(); total_ms.clear(); calls.clear();
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-void launch_primitives(cudaStream_t st, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale,
-                       long long* launches)
+void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
+                       const State& cur, const Scratch& S, int stale)
 {
+  cudaStream_t st = ctx.st;
   const Box box = full_box(G, stale);
   if (empty(box)) return;
   const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
   const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
+  ScopedLaunch sl(ctx, "k_primitives");
   if (P.mhd) {
     if (P.de) k_primitives<true, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
     else      k_primitives<true, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
@@ -585,7 +636,6 @@ void launch_primitives(cudaStream_t st, const Params& P, const Geom& G,
     if (P.de) k_primitives<false, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
     else      k_primitives<false, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
   }
-  ++*launches;
 }
 
 namespace {
@@ -634,10 +684,11 @@ void flux_recon(cudaStream_t st, int recon, int solver, bool de, dim3 grid,
 
 }  // namespace
 
-void launch_flux(cudaStream_t st, const Params& P, const Geom& G, int dim,
+void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
                  int recon, const State& cur, const Scratch& S,
-                 const FaceB& bi_cur, int cs, long long* launches)
+                 const FaceB& bi_cur, int cs)
 {
+  cudaStream_t st = ctx.st;
   // non-stale faces: [cs, f-cs) on every axis of the face-shaped array
   Box box = full_box(G, cs);
   box.hi[dim] -= 1;
@@ -646,19 +697,22 @@ void launch_flux(cudaStream_t st, const Params& P, const Geom& G, int dim,
   const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
   const double* bi = P.mhd ? bi_cur.bi[dim] : nullptr;
   const bool de = P.de != 0;
+  static const char* const names[2][3] = {
+    { "k_flux_x_nn", "k_flux_y_nn", "k_flux_z_nn" },
+    { "k_flux_x_plm", "k_flux_y_plm", "k_flux_z_plm" } };
+  ScopedLaunch sl(ctx, names[recon == VLCT_RECON_NN ? 0 : 1][dim]);
   switch (dim) {
   case 0: flux_recon<0>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[0], box); break;
   case 1: flux_recon<1>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[1], box); break;
   default: flux_recon<2>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[2], box); break;
   }
-  ++*launches;
 }
 
-void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
+void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, double dt, const double* width, int s,
-               long long* launches)
+               const FaceB& bi_out, double dt, const double* width, int s)
 {
+  cudaStream_t st = ctx.st;
   const int m[3] = { G.mx, G.my, G.mz };
   const dim3 block(kBlockX, kBlockY);
   {
@@ -678,8 +732,8 @@ void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
     Box box;   // union of the three component boxes
     for (int a = 0; a < 3; a++) { box.lo[a] = s; box.hi[a] = m[a] - s - 1; }
     if (!empty(box)) {
+      ScopedLaunch sl(ctx, "k_edge_efield");
       k_edge_efield<<<grid_for(box), block, 0, st>>>(G, A, box);
-      ++*launches;
     }
   }
   {
@@ -698,17 +752,18 @@ void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
     Box box;
     for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
     if (!empty(box)) {
+      ScopedLaunch sl(ctx, "k_face_bfield");
       k_face_bfield<<<grid_for(box), block, 0, st>>>(G, A, box);
-      ++*launches;
     }
   }
 }
 
-void launch_update(cudaStream_t st, const Params& P, const Geom& G,
+void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& out, const Scratch& S,
                    const FaceB& bi_out, const double* accel[3], bool gravity,
-                   double dt, const double* width, int s, long long* launches)
+                   double dt, const double* width, int s)
 {
+  cudaStream_t st = ctx.st;
   UpdateArgs A;
   A.u0 = u0; A.out = out;
   for (int d = 0; d < 3; d++) {
@@ -725,6 +780,7 @@ void launch_update(cudaStream_t st, const Params& P, const Geom& G,
   const Box box = P.mhd ? full_box(G, s) : A.inner;
   if (empty(box)) return;
   const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
+  ScopedLaunch sl(ctx, "k_update");
   if (P.mhd) {
     if (P.de) k_update<true, true><<<grid, block, 0, st>>>(P, G, A, box);
     else      k_update<true, false><<<grid, block, 0, st>>>(P, G, A, box);
@@ -732,19 +788,20 @@ void launch_update(cudaStream_t st, const Params& P, const Geom& G,
     if (P.de) k_update<false, true><<<grid, block, 0, st>>>(P, G, A, box);
     else      k_update<false, false><<<grid, block, 0, st>>>(P, G, A, box);
   }
-  ++*launches;
 }
 
-void launch_timestep(cudaStream_t st, const Params& P, const Geom& G,
+void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
                      const State& u, double* pressure, const double* width,
-                     unsigned long long* dt_bits, long long* launches)
+                     unsigned long long* dt_bits)
 {
-  k_set_u64<<<1, 1, 0, st>>>(dt_bits, 0x7fefffffffffffffULL);  // DBL_MAX
-  ++*launches;
+  cudaStream_t st = ctx.st;
+  { ScopedLaunch sl0(ctx, "k_set_u64");
+    k_set_u64<<<1, 1, 0, st>>>(dt_bits, 0x7fefffffffffffffULL); }  // DBL_MAX
   const size_t n = G.cells();
   int blocks = (int) ((n + 255) / 256);
   const int max_blocks = 148 * 16;
   if (blocks > max_blocks) blocks = max_blocks;
+  ScopedLaunch sl(ctx, "k_timestep");
   if (P.mhd) {
     if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
     else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
@@ -752,34 +809,34 @@ void launch_timestep(cudaStream_t st, const Params& P, const Geom& G,
     if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
     else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
   }
-  ++*launches;
 }
 
-void launch_wrap_axis(cudaStream_t st, double* p, int n0, int n1, int n2,
-                      int axis, int n, int g, int cen, long long* launches)
+void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
+                      int axis, int n, int g, int cen)
 {
+  cudaStream_t st = ctx.st;
   const int ext[3] = { n2, n1, n0 };
   size_t total = (size_t) 2 * g;
   for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
   if (total == 0) return;
   int blocks = (int) ((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ScopedLaunch sl(ctx, "k_wrap_axis");
   k_wrap_axis<<<blocks, 256, 0, st>>>(p, n0, n1, n2, axis, n, g, cen);
-  ++*launches;
 }
 
-void launch_slab_copy(cudaStream_t st, double* field, int n0, int n1, int n2,
-                      int axis, int lo, int width, double* buffer, bool pack,
-                      long long* launches)
+void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,
+                      int axis, int lo, int width, double* buffer, bool pack)
 {
+  cudaStream_t st = ctx.st;
   const int ext[3] = { n2, n1, n0 };
   size_t total = (size_t) width;
   for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
   if (total == 0) return;
   int blocks = (int) ((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ScopedLaunch sl(ctx, pack ? "k_slab_pack" : "k_slab_unpack");
   k_slab_copy<<<blocks, 256, 0, st>>>(field, n0, n1, n2, axis, lo, width, buffer, pack ? 1 : 0);
-  ++*launches;
 }
 
 }  // namespace vlct

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 #include <cstddef>
+#include <string>
+#include <vector>
 
 #include "../../include/vlct.h"
 
@@ -58,43 +60,61 @@ struct Scratch {
   double *edge[3];      // edge-centred E (cell strides)
 };
 
+/// Optional per-kernel timing (CUDA events on the launching stream). Used by
+/// bench.py to measure the dominant kernel's launch duration live.
+struct Profiler {
+  struct Entry { const char* name; cudaEvent_t beg, end; };
+  bool enabled = false;
+  std::vector<Entry> pending;
+  std::vector<std::string> names;
+  std::vector<double> total_ms;
+  std::vector<long long> calls;
+  void begin(cudaStream_t st, const char* name);
+  void end(cudaStream_t st);
+  void collect();          // synchronises the recorded events
+  void reset();
+};
+
+/// what every launcher needs: the stream, the launch counter, the profiler
+struct LaunchCtx {
+  cudaStream_t st;
+  long long* launches;
+  Profiler* prof;
+};
+
 /// primitive pressure (+ specific scalars) over [s, m-s)^3
-void launch_primitives(cudaStream_t st, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale,
-                       long long* launches);
+void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
+                       const State& cur, const Scratch& S, int stale);
 
 /// reconstruct -> fix longitudinal B -> Riemann -> passive fluxes along dim
-void launch_flux(cudaStream_t st, const Params& P, const Geom& G, int dim,
+void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
                  int recon, const State& cur, const Scratch& S,
-                 const FaceB& bi_cur, int cur_stale, long long* launches);
+                 const FaceB& bi_cur, int cur_stale);
 
 /// constrained transport: edge E, face-B update
-void launch_ct(cudaStream_t st, const Params& P, const Geom& G,
+void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, double dt, const double* width, int stale,
-               long long* launches);
+               const FaceB& bi_out, double dt, const double* width, int stale);
 
 /// centred B + flux divergence + sources + conserved update + floors/sync
-void launch_update(cudaStream_t st, const Params& P, const Geom& G,
+void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& out, const Scratch& S,
                    const FaceB& bi_out, const double* accel[3], bool gravity,
-                   double dt, const double* width, int stale,
-                   long long* launches);
+                   double dt, const double* width, int stale);
 
 /// DE sync + pressure field + CFL minimum over all cells; *dt_bits receives
 /// the bit pattern of the minimum local dt (not yet multiplied by courant)
-void launch_timestep(cudaStream_t st, const Params& P, const Geom& G,
+void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
                      const State& u, double* pressure, const double* width,
-                     unsigned long long* dt_bits, long long* launches);
+                     unsigned long long* dt_bits);
 
 /// periodic self-refresh of one field along one axis
-void launch_wrap_axis(cudaStream_t st, double* p, int n0, int n1, int n2,
-                      int axis, int n, int g, int cen, long long* launches);
+void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
+                      int axis, int n, int g, int cen);
 
 /// halo slab pack / unpack of one field along one axis
 /// lo..lo+g: range along the axis; the slab spans the full other extents
-void launch_slab_copy(cudaStream_t st, double* field, int n0, int n1, int n2,
-                      int axis, int lo, int width, double* buffer, bool pack,
-                      long long* launches);
+void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,
+                      int axis, int lo, int width, double* buffer, bool pack);
 
 }  // namespace vlct

@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = (
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_last_error", "vlct_status_string",
     "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_synchronize",
+    "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
+    "vlct_profile_get",
     "vlct_refresh_periodic", "vlct_halo_bytes", "vlct_halo_pack",
     "vlct_halo_unpack",
 )
@@ -60,6 +62,11 @@ def load():
         "vlct_kernel_launches": (C.c_longlong, [C.c_void_p]),
         "vlct_scratch_bytes": (C.c_longlong, [C.c_void_p]),
         "vlct_synchronize": (C.c_int, [C.c_void_p]),
+        "vlct_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+        "vlct_profile_reset": (C.c_int, [C.c_void_p]),
+        "vlct_profile_count": (C.c_int, [C.c_void_p]),
+        "vlct_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p,
+                                       C.c_int, dp, C.POINTER(C.c_longlong)]),
         "vlct_refresh_periodic": (C.c_int, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_bytes": (C.c_longlong, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_pack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),

@@ -172,6 +172,22 @@ class EnzoMethodMHDVlct:
     def scratch_bytes(self):
         return int(self._lib.vlct_scratch_bytes(self._h))
 
+    def profile(self, on=True):
+        """Switch per-kernel CUDA-event timing on/off (clears old samples)."""
+        self._check(self._lib.vlct_profile_reset(self._h))
+        self._check(self._lib.vlct_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel name: (total ms, launches)} since profiling was enabled."""
+        out = {}
+        name = C.create_string_buffer(64)
+        ms, calls = C.c_double(0.0), C.c_longlong(0)
+        for i in range(self._lib.vlct_profile_count(self._h)):
+            self._check(self._lib.vlct_profile_get(
+                self._h, i, name, len(name), C.byref(ms), C.byref(calls)))
+            out[name.value.decode()] = (ms.value, calls.value)
+        return out
+
     def synchronize(self):
         self._check(self._lib.vlct_synchronize(self._h))
 

@@ -184,6 +184,16 @@ long long vlct_scratch_bytes(const vlct_handle *h);
 /* Block until all work submitted through this handle has finished. */
 int vlct_synchronize(vlct_handle *h);
 
+/* Per-kernel timing with CUDA events on the launching stream -- the device-side
+ * analogue of the reference's Performance regions around Method::compute
+ * (src/Cello/performance_Performance.hpp:36-65, control_compute.cpp:74,104).
+ * Off by default (two event records per launch when on). */
+int vlct_profile_enable(vlct_handle *h, int on);
+int vlct_profile_reset(vlct_handle *h);
+int vlct_profile_count(vlct_handle *h);
+int vlct_profile_get(vlct_handle *h, int index, char *name, int name_len,
+                     double *total_ms, long long *calls);
+
 /* ---- ghost-zone refresh on the device --------------
  * Stand-ins for the refresh phase that precedes compute() on a unigrid
  * (src/Cello/control_refresh.cpp:243-359, src/Cello/data_FieldFace.cpp).

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "Cello/cello.hpp"
 #include "Enzo/enzo.hpp"
@@ -70,17 +71,30 @@ namespace enzo {
 
 namespace {
 
-struct RefHandle {
+// The reference reaches its field descriptor and fluid properties through
+// process-wide accessors. Handles created with the same configuration share one
+// context, so several host threads (one handle each) can run concurrently
+// without ever rewriting those globals (bench.py's CPU baseline does that).
+struct RefContext {
   vlct_config cfg;
+  int g[3];
   FieldDescr descr;
   EnzoPhysicsFluidProps* fluid_props;
-  EnzoMethodMHDVlct* method;
   std::vector<std::string> passive_names;
+  int refcount;
 };
 
+struct RefHandle {
+  RefContext* ctx;
+  EnzoMethodMHDVlct* method;
+};
+
+std::vector<RefContext*> g_contexts;
+std::mutex g_mutex;
+
 void activate(RefHandle* h) {
-  if (g_field_descr != &h->descr) g_field_descr = &h->descr;
-  if (g_fluid_props != h->fluid_props) g_fluid_props = h->fluid_props;
+  if (g_field_descr != &h->ctx->descr) g_field_descr = &h->ctx->descr;
+  if (g_fluid_props != h->ctx->fluid_props) g_fluid_props = h->ctx->fluid_props;
 }
 
 std::string fmt_double(double v) {
@@ -109,9 +123,9 @@ const char* recon_name(int v) {
 void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
   FieldData& fd = blk.data()->field_data;
   fd.nx = b->nx; fd.ny = b->ny; fd.nz = b->nz;
-  fd.ptrs.assign(h->descr.field_count(), nullptr);
+  fd.ptrs.assign(h->ctx->descr.field_count(), nullptr);
   auto set = [&](const char* name, double* p) {
-    int id = h->descr.field_id(name);
+    int id = h->ctx->descr.field_id(name);
     if (id >= 0) {
       if (p == nullptr) {
         fprintf(stderr, "[vlct_ref] missing pointer for field %s\n", name);
@@ -136,8 +150,8 @@ void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
   set("acceleration_x", b->acceleration_x);
   set("acceleration_y", b->acceleration_y);
   set("acceleration_z", b->acceleration_z);
-  for (std::size_t i = 0; i < h->passive_names.size(); i++)
-    set(h->passive_names[i].c_str(), b->passive[i]);
+  for (std::size_t i = 0; i < h->ctx->passive_names.size(); i++)
+    set(h->ctx->passive_names[i].c_str(), b->passive[i]);
   blk.CellWidth[0] = b->dx; blk.CellWidth[1] = b->dy; blk.CellWidth[2] = b->dz;
   blk.data()->h[0] = b->dx; blk.data()->h[1] = b->dy; blk.data()->h[2] = b->dz;
 }
@@ -150,54 +164,67 @@ extern "C" {
 
 void* vlct_ref_create(const vlct_config* cfg, int gx, int gy, int gz)
 {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  RefContext* c = nullptr;
+  for (RefContext* cand : g_contexts) {
+    if (memcmp(&cand->cfg, cfg, sizeof(vlct_config)) == 0 &&
+        cand->g[0] == gx && cand->g[1] == gy && cand->g[2] == gz) { c = cand; break; }
+  }
+  if (c == nullptr) {
+    c = new RefContext;
+    memcpy(&c->cfg, cfg, sizeof(vlct_config));
+    c->g[0] = gx; c->g[1] = gy; c->g[2] = gz;
+    c->refcount = 0;
+    const bool mhd = (cfg->mhd_choice == VLCT_MHD_CONSTRAINED_TRANSPORT);
+    const bool de = (cfg->dual_energy != VLCT_DE_DISABLED);
+    c->descr.set_ghost_depth(gx, gy, gz);
+    c->descr.insert("density", 0,0,0);
+    c->descr.insert("velocity_x", 0,0,0);
+    c->descr.insert("velocity_y", 0,0,0);
+    c->descr.insert("velocity_z", 0,0,0);
+    c->descr.insert("total_energy", 0,0,0);
+    if (de) c->descr.insert("internal_energy", 0,0,0);
+    if (mhd) {
+      c->descr.insert("bfield_x", 0,0,0);
+      c->descr.insert("bfield_y", 0,0,0);
+      c->descr.insert("bfield_z", 0,0,0);
+      c->descr.insert("bfieldi_x", 1,0,0);
+      c->descr.insert("bfieldi_y", 0,1,0);
+      c->descr.insert("bfieldi_z", 0,0,1);
+    }
+    c->descr.insert("pressure", 0,0,0);
+    if (cfg->has_acceleration) {
+      c->descr.insert("acceleration_x", 0,0,0);
+      c->descr.insert("acceleration_y", 0,0,0);
+      c->descr.insert("acceleration_z", 0,0,0);
+    }
+    for (int i = 0; i < cfg->n_passive; i++) {
+      char name[32];
+      snprintf(name, sizeof(name), "passive_%d", i);
+      c->passive_names.push_back(name);
+      c->descr.insert(name, 0,0,0);
+      c->descr.groups()->add(name, "color");
+    }
+    EnzoDualEnergyConfig de_config = EnzoDualEnergyConfig::build_disabled();
+    if (cfg->dual_energy == VLCT_DE_MODERN) {
+      de_config = EnzoDualEnergyConfig::build_modern_formulation
+        (cfg->dual_energy_eta);
+    } else if (cfg->dual_energy == VLCT_DE_BRYAN95) {
+      de_config = EnzoDualEnergyConfig::build_bryan95_formulation
+        (cfg->dual_energy_eta, cfg->dual_energy_eta);
+    }
+    EnzoFluidFloorConfig floors(cfg->density_floor, cfg->pressure_floor, 0., 0.);
+    EnzoEOSVariant eos(EnzoEOSIdeal::construct(cfg->gamma));
+    c->fluid_props = new EnzoPhysicsFluidProps(de_config, floors, eos, 0.6);
+    g_contexts.push_back(c);
+  }
+  c->refcount++;
+
   RefHandle* h = new RefHandle;
-  h->cfg = *cfg;
-  const bool mhd = (cfg->mhd_choice == VLCT_MHD_CONSTRAINED_TRANSPORT);
-  const bool de = (cfg->dual_energy != VLCT_DE_DISABLED);
-
-  h->descr.set_ghost_depth(gx, gy, gz);
-  h->descr.insert("density", 0,0,0);
-  h->descr.insert("velocity_x", 0,0,0);
-  h->descr.insert("velocity_y", 0,0,0);
-  h->descr.insert("velocity_z", 0,0,0);
-  h->descr.insert("total_energy", 0,0,0);
-  if (de) h->descr.insert("internal_energy", 0,0,0);
-  if (mhd) {
-    h->descr.insert("bfield_x", 0,0,0);
-    h->descr.insert("bfield_y", 0,0,0);
-    h->descr.insert("bfield_z", 0,0,0);
-    h->descr.insert("bfieldi_x", 1,0,0);
-    h->descr.insert("bfieldi_y", 0,1,0);
-    h->descr.insert("bfieldi_z", 0,0,1);
-  }
-  h->descr.insert("pressure", 0,0,0);
-  if (cfg->has_acceleration) {
-    h->descr.insert("acceleration_x", 0,0,0);
-    h->descr.insert("acceleration_y", 0,0,0);
-    h->descr.insert("acceleration_z", 0,0,0);
-  }
-  for (int i = 0; i < cfg->n_passive; i++) {
-    char name[32];
-    snprintf(name, sizeof(name), "passive_%d", i);
-    h->passive_names.push_back(name);
-    h->descr.insert(name, 0,0,0);
-    h->descr.groups()->add(name, "color");
-  }
-
-  EnzoDualEnergyConfig de_config = EnzoDualEnergyConfig::build_disabled();
-  if (cfg->dual_energy == VLCT_DE_MODERN) {
-    de_config = EnzoDualEnergyConfig::build_modern_formulation
-      (cfg->dual_energy_eta);
-  } else if (cfg->dual_energy == VLCT_DE_BRYAN95) {
-    de_config = EnzoDualEnergyConfig::build_bryan95_formulation
-      (cfg->dual_energy_eta, cfg->dual_energy_eta);
-  }
-  EnzoFluidFloorConfig floors(cfg->density_floor, cfg->pressure_floor, 0., 0.);
-  EnzoEOSVariant eos(EnzoEOSIdeal::construct(cfg->gamma));
-  h->fluid_props = new EnzoPhysicsFluidProps(de_config, floors, eos, 0.6);
-
+  h->ctx = c;
   activate(h);
 
+  const bool mhd = (cfg->mhd_choice == VLCT_MHD_CONSTRAINED_TRANSPORT);
   ParameterGroup p;
   p.set("riemann_solver", riemann_name(cfg->riemann_solver));
   p.set("reconstruct_method", recon_name(cfg->reconstruct_method));
@@ -215,11 +242,18 @@ void vlct_ref_destroy(void* handle)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   if (h == nullptr) return;
+  std::lock_guard<std::mutex> lock(g_mutex);
   activate(h);
   delete h->method;
-  delete h->fluid_props;
-  if (g_field_descr == &h->descr) g_field_descr = nullptr;
-  if (g_fluid_props == h->fluid_props) g_fluid_props = nullptr;
+  RefContext* c = h->ctx;
+  if (--c->refcount == 0) {
+    if (g_field_descr == &c->descr) g_field_descr = nullptr;
+    if (g_fluid_props == c->fluid_props) g_fluid_props = nullptr;
+    delete c->fluid_props;
+    for (std::size_t i = 0; i < g_contexts.size(); i++)
+      if (g_contexts[i] == c) { g_contexts.erase(g_contexts.begin() + i); break; }
+    delete c;
+  }
   delete h;
 }
 
@@ -227,7 +261,7 @@ int vlct_ref_compute(void* handle, const vlct_block* b, double dt)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   activate(h);
-  EnzoBlock blk(&h->descr);
+  EnzoBlock blk(&h->ctx->descr);
   bind_block(h, blk, b);
   blk.set_dt(dt);
   h->method->compute(&blk);
@@ -238,7 +272,7 @@ int vlct_ref_timestep(void* handle, const vlct_block* b, double* dt_out)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   activate(h);
-  EnzoBlock blk(&h->descr);
+  EnzoBlock blk(&h->ctx->descr);
   bind_block(h, blk, b);
   *dt_out = h->method->timestep(&blk);
   return 0;
