@@ -1,0 +1,117 @@
+"""CPU: pin the oracle.
+
+1. The plain-C restatement (oracle/vlct_oracle.c) and -- where it is available
+   -- the reference's own compiled sources (oracle/_ref) reproduce the golden
+   L1 error norms that the reference's vlct answer tests hard-code
+   (input/vlct/run_MHD_linear_wave_test.py:178-188,
+    input/vlct/run_HD_linear_wave_test.py:70-80), with the reference's own
+   tolerance (rtol 1e-13, atol 7e-14; input/vlct/testing_utils.py:275-292).
+2. The restatement is bit-identical to the compiled reference on seeded random
+   states for every solver / reconstructor / dual-energy / scalar combination.
+"""
+import numpy as np
+import pytest
+
+import problems as P
+from helpers import (make_config, random_state, copy_state, passive_names,
+                     bit_equal, max_abs_diff, oracle)
+
+
+@pytest.mark.parametrize("name", sorted(P.MHD_WAVES))
+def test_mhd_linear_wave_n16_golden(name):
+    l1, dts, _ = P.run_linear_wave(name, 16, mhd=True, kind="oracle")
+    assert P.golden_isclose(l1, P.GOLDEN_MHD[(name, 16)]), (l1, len(dts))
+
+
+@pytest.mark.parametrize("name", sorted(P.HD_WAVES))
+def test_hd_linear_wave_n16_golden(name):
+    l1, dts, _ = P.run_linear_wave(name, 16, mhd=False, kind="oracle")
+    assert P.golden_isclose(l1, P.GOLDEN_HD[(name, 16)]), (l1, len(dts))
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["fast", "entropy"])
+def test_mhd_linear_wave_n32_golden(name):
+    l1, _, _ = P.run_linear_wave(name, 32, mhd=True, kind="oracle")
+    assert P.golden_isclose(l1, P.GOLDEN_MHD[(name, 32)]), l1
+
+
+@pytest.mark.slow
+def test_hd_linear_wave_n32_golden():
+    l1, _, _ = P.run_linear_wave("sound", 32, mhd=False, kind="oracle")
+    assert P.golden_isclose(l1, P.GOLDEN_HD[("sound", 32)]), l1
+
+
+def test_compiled_reference_reproduces_golden():
+    """The compiled reference itself, driven by our cycle loop + ICs: pins the
+    IC restatement, the refresh and the loop independently of vlct_oracle.c."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    l1, dts_ref, f_ref = P.run_linear_wave("fast", 16, mhd=True, kind="ref")
+    assert P.golden_isclose(l1, P.GOLDEN_MHD[("fast", 16)]), l1
+    l1o, dts_or, f_or = P.run_linear_wave("fast", 16, mhd=True, kind="oracle")
+    assert dts_ref == dts_or
+    assert all(bit_equal(f_ref, f_or).values())
+
+
+RANDOM_CASES = {
+    "mhd_hlld_plm": dict(riemann="hlld", recon="plm", theta=1.5, mhd=True),
+    "mhd_hlld_plm_theta1": dict(riemann="hlld", recon="plm", theta=1.0, mhd=True),
+    "mhd_hlld_athena_de_sc": dict(riemann="hlld", recon="plm_athena", mhd=True,
+                                  dual_energy=True, n_passive=2),
+    "mhd_hlld_nn": dict(riemann="hlld", recon="nn", mhd=True),
+    "mhd_hlle_plm_de": dict(riemann="hlle", recon="plm", mhd=True,
+                            dual_energy=True),
+    "mhd_hlle_euler": dict(riemann="hlle", recon="plm", mhd=True,
+                           time_scheme="euler", courant=0.5),
+    "hd_hllc_plm": dict(riemann="hllc", recon="plm", mhd=False),
+    "hd_hllc_de_sc": dict(riemann="hllc", recon="plm", mhd=False,
+                          dual_energy=True, gamma=1.4, n_passive=3),
+    "hd_hllc_gravity": dict(riemann="hllc", recon="plm_athena", mhd=False,
+                            accel=True),
+    "mhd_hlld_gravity_de_eta0": dict(riemann="hlld", recon="plm", mhd=True,
+                                     accel=True, dual_energy=True, eta=0.0),
+    "mhd_hlld_floors": dict(riemann="hlld", recon="plm", mhd=True,
+                            dfloor=0.95, pfloor=0.55),
+}
+
+
+def _run(cfg, host, n, g, d, nsteps, kind):
+    f = copy_state(host)
+    blk = oracle.numpy_block(f, n, g, d, passive_names(cfg))
+    m = oracle.CpuMethod(cfg, g, kind=kind)
+    dts = []
+    for _ in range(nsteps):
+        dt = m.timestep(blk)
+        m.compute(blk, dt)
+        dts.append(dt)
+    m.close()
+    return f, dts
+
+
+@pytest.mark.parametrize("name", sorted(RANDOM_CASES))
+def test_oracle_bit_identical_to_compiled_reference(name):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    cfg = make_config(**RANDOM_CASES[name])
+    n, g, d = (14, 10, 8), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=21)
+    want, dts_want = _run(cfg, host, n, g, d, 3, "ref")
+    got, dts_got = _run(cfg, host, n, g, d, 3, "oracle")
+    assert dts_got == dts_want
+    eq = bit_equal(want, got)
+    bad = {k: max_abs_diff(want, got)[k] for k, ok in eq.items() if not ok}
+    assert not bad, bad
+    # the update did something
+    assert not np.array_equal(want["density"], host["density"])
+
+
+def test_oracle_active_floors_really_trigger():
+    """the 'floors' case above must actually exercise the floor branches"""
+    cfg = make_config(**RANDOM_CASES["mhd_hlld_floors"])
+    n, g, d = (14, 10, 8), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=21)
+    got, _ = _run(cfg, host, n, g, d, 1, "oracle")
+    act = got["density"][3:-3, 3:-3, 3:-3]
+    assert np.min(act) >= 0.95
+    assert np.any(act == 0.95)
