@@ -1,0 +1,197 @@
+"""CPU, world_size 2 over gloo: the unigrid driver's neighbour / message-ordering
+logic (enzo-e_b200/domain.py). The CUDA pack/unpack/wrap kernels are replaced
+by numpy stand-ins with the same slab convention as csrc (vlct_api.cu
+halo_copy); the GPU versions are checked against these same stand-ins in
+test_gpu_domain.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+FIELDS = ["density", "velocity_x", "bfield_x", "bfieldi_x", "bfieldi_y",
+          "bfieldi_z"]
+
+
+def face_axis(name):
+    return {"bfieldi_x": 0, "bfieldi_y": 1, "bfieldi_z": 2}.get(name, -1)
+
+
+class HostBlock:
+    def __init__(self, fields, n, g):
+        self.fields, self.n, self.g = fields, n, g
+
+
+class HostKernels:
+    """numpy restatement of k_slab_copy / k_wrap_axis index conventions"""
+
+    def halo_bytes(self, blk, axis):
+        total = 0
+        for name in FIELDS:
+            a = blk.fields[name]
+            shp = list(a.shape[::-1])        # (x, y, z) extents
+            shp[axis] = blk.g[axis]
+            total += shp[0] * shp[1] * shp[2]
+        return total * 8
+
+    @staticmethod
+    def _slab(a, axis, lo, width):
+        sl = [slice(None)] * 3
+        sl[2 - axis] = slice(lo, lo + width)
+        return tuple(sl)
+
+    def halo_pack(self, blk, axis, side, buf):
+        off = 0
+        n, g = blk.n[axis], blk.g[axis]
+        for name in FIELDS:
+            a = blk.fields[name]
+            cen = 1 if face_axis(name) == axis else 0
+            lo = (g + cen) if side == 0 else n
+            s = a[self._slab(a, axis, lo, g)]
+            buf[off:off + s.size] = torch.from_numpy(np.ascontiguousarray(s).ravel())
+            off += s.size
+
+    def halo_unpack(self, blk, axis, side, buf):
+        off = 0
+        n, g = blk.n[axis], blk.g[axis]
+        for name in FIELDS:
+            a = blk.fields[name]
+            cen = 1 if face_axis(name) == axis else 0
+            lo = 0 if side == 0 else g + n + cen
+            view = a[self._slab(a, axis, lo, g)]
+            view[...] = buf[off:off + view.size].numpy().reshape(view.shape)
+            off += view.size
+
+    def wrap(self, blk, axes):
+        for axis in range(3):
+            if not axes & (1 << axis):
+                continue
+            n, g = blk.n[axis], blk.g[axis]
+            for name in FIELDS:
+                a = blk.fields[name]
+                cen = 1 if face_axis(name) == axis else 0
+                a[self._slab(a, axis, 0, g)] = a[self._slab(a, axis, n, g)]
+                a[self._slab(a, axis, g + n + cen, g)] = \
+                    a[self._slab(a, axis, g + cen, g)]
+
+
+def global_value(name, ix, iy, iz, N):
+    """a periodic integer-valued function of the GLOBAL index (faces share
+    the index of the cell on their upper side)"""
+    h = {"density": 1, "velocity_x": 2, "bfield_x": 3, "bfieldi_x": 4,
+         "bfieldi_y": 5, "bfieldi_z": 6}[name]
+    return (h * 1000003 + (ix % N[0]) * 10007 + (iy % N[1]) * 101
+            + (iz % N[2])).astype(np.float64)
+
+
+def make_block(coords, n, g, N, fill_ghosts):
+    from enzo_e_b200 import abi
+    f = {}
+    for name in FIELDS:
+        shp = abi.field_shape(name, *n, *g)
+        iz, iy, ix = np.meshgrid(np.arange(shp[0]), np.arange(shp[1]),
+                                 np.arange(shp[2]), indexing="ij")
+        gi = [ix - g[0] + coords[0] * n[0], iy - g[1] + coords[1] * n[1],
+              iz - g[2] + coords[2] * n[2]]
+        full = global_value(name, gi[0], gi[1], gi[2], N)
+        if fill_ghosts:
+            f[name] = full
+        else:
+            a = np.full(shp, -1.0)
+            fa = face_axis(name)
+            sl = tuple(slice(g[2 - k], g[2 - k] + n[2 - k] + (1 if fa == 2 - k else 0))
+                       for k in range(3))
+            a[sl] = full[sl]
+            f[name] = a
+    return HostBlock(f, n, g)
+
+
+def _worker(rank, world, port, grid, result_q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from enzo_e_b200.domain import Domain
+        dom = Domain(rank, world, grid=grid)
+        n, g = (6, 5, 4), (3, 3, 3)
+        N = tuple(n[a] * grid[a] for a in range(3))
+        blk = make_block(dom.coords, n, g, N, fill_ghosts=False)
+        want = make_block(dom.coords, n, g, N, fill_ghosts=True)
+        k = HostKernels()
+        dom.refresh(k, blk, pack=k.halo_pack, unpack=k.halo_unpack,
+                    wrap=k.wrap,
+                    alloc=lambda nbytes: torch.empty(nbytes // 8,
+                                                     dtype=torch.float64))
+        bad = [name for name in FIELDS
+               if not np.array_equal(blk.fields[name], want.fields[name])]
+        dt = dom.global_dt(0.5 + rank, device="cpu")
+        result_q.put((rank, bad, dt))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (2, 1, 1), (1, 2, 1)])
+def test_refresh_two_ranks(grid):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad, dt in results:
+        assert not bad, f"rank {rank}: ghost zones wrong in {bad}"
+        assert dt == 0.5
+
+
+def test_proc_grid_and_neighbours():
+    from enzo_e_b200.domain import Domain, proc_grid
+    assert proc_grid(1) == (1, 1, 1)
+    assert proc_grid(2) == (1, 1, 2)
+    assert proc_grid(4) == (1, 2, 2)
+    assert proc_grid(8) == (2, 2, 2)
+    for world in (2, 4, 8, 6, 12):
+        g = proc_grid(world)
+        assert g[0] * g[1] * g[2] == world
+        seen = set()
+        for r in range(world):
+            d = Domain(r, world)
+            seen.add(d.coords)
+            for axis in range(3):
+                up = d.neighbor(axis, +1)
+                assert Domain(up, world).neighbor(axis, -1) == r
+        assert len(seen) == world
+
+
+def test_single_rank_refresh_wraps():
+    from enzo_e_b200.domain import Domain
+    dom = Domain(0, 1)
+    n, g = (6, 5, 4), (3, 3, 3)
+    blk = make_block((0, 0, 0), n, g, n, fill_ghosts=False)
+    want = make_block((0, 0, 0), n, g, n, fill_ghosts=True)
+    k = HostKernels()
+    dom.refresh(k, blk, pack=k.halo_pack, unpack=k.halo_unpack, wrap=k.wrap,
+                alloc=lambda nbytes: torch.empty(nbytes // 8, dtype=torch.float64))
+    for name in FIELDS:
+        assert np.array_equal(blk.fields[name], want.fields[name]), name

@@ -62,8 +62,8 @@ RANDOM_CASES = {
     "mhd_hlld_nn": dict(riemann="hlld", recon="nn", mhd=True),
     "mhd_hlle_plm_de": dict(riemann="hlle", recon="plm", mhd=True,
                             dual_energy=True),
-    "mhd_hlle_euler": dict(riemann="hlle", recon="plm", mhd=True,
-                           time_scheme="euler", courant=0.5),
+    "hd_hllc_euler": dict(riemann="hllc", recon="plm", mhd=False,
+                          time_scheme="euler", courant=0.5),
     "hd_hllc_plm": dict(riemann="hllc", recon="plm", mhd=False),
     "hd_hllc_de_sc": dict(riemann="hllc", recon="plm", mhd=False,
                           dual_energy=True, gamma=1.4, n_passive=3),
