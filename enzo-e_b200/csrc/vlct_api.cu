@@ -114,7 +114,6 @@ int alloc_scratch(vlct_handle* h, const Geom& G)
     if (P.de) { ALLOC(F.eint, n); ALLOC(F.vbar, n); }
     for (int s = 0; s < P.nsc; s++) ALLOC(F.sc[s], n);
   }
-  ALLOC(S.prim_p, n);
   for (int s = 0; s < P.nsc; s++) ALLOC(S.prim_sc[s], n);
   if (P.mhd) for (int d = 0; d < 3; d++) ALLOC(S.edge[d], n);
 #undef ALLOC
@@ -299,8 +298,8 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     // (EnzoMHDIntegratorStageCommands.cpp:181,279)
     const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
                          accel[0] != nullptr;
-    launch_update(ctx, P, G, ext, out, h->S, bi_out, accel, gravity, cur_dt,
-                  width, cs);
+    launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
+                  cur_dt, width, cs);
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());

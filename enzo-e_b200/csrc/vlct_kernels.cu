@@ -4,9 +4,10 @@
 // compute_update_stage, hydro-mhd/EnzoMHDIntegratorStageCommands.cpp:102-203)
 // is executed as
 //
-//   k_primitives   pressure (+ specific scalars) of the stage's input state
-//   k_flux<x|y|z>  fused  reconstruct -> longitudinal-B fix -> Riemann ->
-//                  passive-scalar fluxes; nothing but the fluxes reaches HBM
+//   k_specific_scalars   passive scalars / density (only when scalars exist)
+//   k_flux_x, k_flux_march<y|z>  (vlct_flux.cu) fused  primitives ->
+//                  reconstruct -> longitudinal-B fix -> Riemann -> passive
+//                  fluxes; nothing but the fluxes reaches HBM
 //   k_edge_efield  fused  cell-centred E -> upwind weights -> edge E
 //   k_face_bfield  CT update of the three face-centred components
 //   k_update       fused  centred B -> flux divergence (+ dual-energy source,
@@ -18,7 +19,7 @@
 // Regions: every kernel works on the reference's stale-depth-trimmed index
 // boxes so that even the ghost-zone content left behind is identical.
 // All arithmetic is fp64; compile with -fmad=false for bit parity.
-#include "vlct_kernels.cuh"
+#include "vlct_device.cuh"
 #include "vlct_physics.cuh"
 
 #include <cfloat>
@@ -26,17 +27,6 @@
 namespace vlct {
 
 namespace {
-
-struct Box { int lo[3], hi[3]; };  // [lo,hi) along x,y,z
-
-/// counts the launch and, when profiling is on, brackets it with CUDA events
-struct ScopedLaunch {
-  const LaunchCtx& c;
-  ScopedLaunch(const LaunchCtx& ctx, const char* name) : c(ctx)
-  { if (c.prof && c.prof->enabled) c.prof->begin(c.st, name); }
-  ~ScopedLaunch()
-  { if (c.prof && c.prof->enabled) c.prof->end(c.st); ++*c.launches; }
-};
 
 constexpr int kBlockX = 64;
 constexpr int kBlockY = 4;
@@ -47,8 +37,6 @@ inline dim3 grid_for(const Box& b)
   return dim3((unsigned) ((nx + kBlockX - 1) / kBlockX),
               (unsigned) ((ny + kBlockY - 1) / kBlockY), (unsigned) nz);
 }
-inline bool empty(const Box& b)
-{ return b.hi[0] <= b.lo[0] || b.hi[1] <= b.lo[1] || b.hi[2] <= b.lo[2]; }
 
 #define VLCT_THREAD_IN_BOX(box, i, j, k)                                     \
   const int i = (box).lo[0] + (int) (blockIdx.x * blockDim.x + threadIdx.x); \
@@ -56,144 +44,20 @@ inline bool empty(const Box& b)
   const int k = (box).lo[2] + (int) blockIdx.z;                              \
   if (i >= (box).hi[0] || j >= (box).hi[1] || k >= (box).hi[2]) return;
 
-__device__ __forceinline__ size_t cidx(const Geom& G, int k, int j, int i)
-{ return ((size_t) k * (size_t) G.my + (size_t) j) * (size_t) G.mx + (size_t) i; }
-
-/// index into the face-centred array of component d
-__device__ __forceinline__ size_t fidx(const Geom& G, int d, int k, int j, int i)
-{
-  const size_t n2 = (size_t) G.mx + (d == 0), n1 = (size_t) G.my + (d == 1);
-  return ((size_t) k * n1 + (size_t) j) * n2 + (size_t) i;
-}
-
-struct ScalarPtrs { double* p[kMaxPassive]; };
-
 // ---------------------------------------------------------------------------
-// primitives: EnzoPhysicsFluidProps::primitive_from_integration
-// (fluid-props/EnzoPhysicsFluidProps.cpp:64-138) and
-// EnzoComputePressure::compute_pressure (fluid-props/EnzoComputePressure.cpp:82-198)
+// specific passive scalars: EnzoPhysicsFluidProps::primitive_from_integration
+// (fluid-props/EnzoPhysicsFluidProps.cpp:64-138). The pressure part of that
+// routine is evaluated on the fly inside the flux kernels (vlct_flux.cu).
 // ---------------------------------------------------------------------------
-template <bool MHD, bool DE>
-__device__ __forceinline__ double pressure_of(const Params& P, const State& u,
-                                              size_t c)
-{
-  const double gm1 = P.gamma - 1.0;
-  if (DE) {
-    return gm1 * __ldg(u.rho + c) * __ldg(u.eint + c);
-  } else {
-    const double vx = __ldg(u.vx + c), vy = __ldg(u.vy + c), vz = __ldg(u.vz + c);
-    const double ke = 0.5 * (vx * vx + vy * vy + vz * vz);
-    double me_den = 0.;
-    if (MHD) {
-      const double bx = __ldg(u.bx + c), by = __ldg(u.by + c), bz = __ldg(u.bz + c);
-      me_den = 0.5 * (bx * bx + by * by + bz * bz);
-    }
-    return gm1 * (__ldg(u.rho + c) * (__ldg(u.etot + c) - ke) - me_den);
-  }
-}
-
-template <bool MHD, bool DE>
 __global__ void __launch_bounds__(kBlockX * kBlockY)
-k_primitives(const Params P, const Geom G, const State u, double* prim_p,
-             const ScalarPtrs spec, const Box box)
+k_specific_scalars(const int nsc, const Geom G, const State u,
+                   const ScalarPtrs spec, const Box box)
 {
   VLCT_THREAD_IN_BOX(box, i, j, k);
   const size_t c = cidx(G, k, j, i);
-  prim_p[c] = pressure_of<MHD, DE>(P, u, c);
-  for (int s = 0; s < P.nsc; s++)
-    spec.p[s][c] = __ldg(u.sc[s] + c) / __ldg(u.rho + c);
-}
-
-// ---------------------------------------------------------------------------
-// fluxes along one dimension
-//   reconstruction  toolkit/EnzoReconstructorNN.cpp:14-48,
-//                   toolkit/EnzoReconstructorPLM.hpp:166-248
-//   B fix           toolkit/EnzoBfieldMethodCT.cpp:122-166
-//   Riemann         riemann/EnzoRiemannImpl.hpp:266-338
-//   passive flux    riemann/EnzoRiemannUtils.hpp:267-314
-// ---------------------------------------------------------------------------
-template <int RECON>
-__device__ __forceinline__ void
-recon_pair(const double* __restrict__ a, size_t c, ptrdiff_t sd, double theta,
-           bool use_floor, double floor_, double& wl, double& wr)
-{
-  if (RECON == RECON_NN) {
-    wl = __ldg(a + c);
-    wr = __ldg(a + c + sd);
-  } else {
-    const double w0 = __ldg(a + c - sd), w1 = __ldg(a + c);
-    const double w2 = __ldg(a + c + sd), w3 = __ldg(a + c + 2 * sd);
-    const double dvl = limited_slope<RECON>(w0, w1, w2, theta);
-    const double dvr = limited_slope<RECON>(w1, w2, w3, theta);
-    const double hl = dvl * 0.5, hr = dvr * 0.5;
-    wl = w1 + hl;   // left state of face c  <- cell c   (val + half_dv)
-    wr = w2 - hr;   // right state of face c <- cell c+1 (val - half_dv)
-    if (use_floor) {
-      wl = apply_floor(wl, floor_);
-      wr = apply_floor(wr, floor_);
-    }
-  }
-}
-
-template <int DIM, int RECON, int SOLVER, bool DE>
-__global__ void __launch_bounds__(kBlockX * kBlockY)
-k_flux(const Params P, const Geom G, const State u,
-       const double* __restrict__ prim_p, const ScalarPtrs spec,
-       const double* __restrict__ bi, const FluxSet F, const Box box)
-{
-  constexpr bool MHD = (SOLVER != SOLVER_HLLC);
-  constexpr int JD = (DIM + 1) % 3, KD = (DIM + 2) % 3;
-  VLCT_THREAD_IN_BOX(box, i, j, k);
-  const size_t c = cidx(G, k, j, i);
-  const ptrdiff_t sd = (DIM == 0) ? 1
-                     : (DIM == 1) ? (ptrdiff_t) G.mx
-                                  : (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
-  const double* v[3] = { u.vx, u.vy, u.vz };
-  const double* b[3] = { u.bx, u.by, u.bz };
-  const double theta = P.theta;
-
-  Prim wl, wr;
-  recon_pair<RECON>(u.rho, c, sd, theta, true, P.density_floor, wl.rho, wr.rho);
-  recon_pair<RECON>(v[DIM], c, sd, theta, false, 0., wl.vi, wr.vi);
-  recon_pair<RECON>(v[JD], c, sd, theta, false, 0., wl.vj, wr.vj);
-  recon_pair<RECON>(v[KD], c, sd, theta, false, 0., wl.vk, wr.vk);
-  recon_pair<RECON>(prim_p, c, sd, theta, true, P.pressure_floor, wl.p, wr.p);
-  if (MHD) {
-    recon_pair<RECON>(b[JD], c, sd, theta, false, 0., wl.bj, wr.bj);
-    recon_pair<RECON>(b[KD], c, sd, theta, false, 0., wl.bk, wr.bk);
-    // face f of the sweep <-> index f+1 of the face-centred array
-    const int di = (DIM == 0), dj = (DIM == 1), dk = (DIM == 2);
-    const double blong = __ldg(bi + fidx(G, DIM, k + dk, j + dj, i + di));
-    wl.bi = blong;
-    wr.bi = blong;
-  } else {
-    wl.bi = wl.bj = wl.bk = 0.;
-    wr.bi = wr.bj = wr.bk = 0.;
-  }
-
-  Flux f;
-  riemann_solve<SOLVER, DE>(P.gamma, wl, wr, f);
-
-  double* fm[3] = { F.mx_, F.my_, F.mz_ };
-  F.rho[c] = f.rho;
-  fm[DIM][c] = f.mi;
-  fm[JD][c] = f.mj;
-  fm[KD][c] = f.mk;
-  F.e[c] = f.e;
-  if (MHD) {
-    double* fb[3] = { F.bx, F.by, F.bz };
-    fb[JD][c] = f.bj;
-    fb[KD][c] = f.bk;
-  }
-  if (DE) {
-    F.eint[c] = f.eint;
-    F.vbar[c] = f.vbar;
-  }
-  for (int s = 0; s < P.nsc; s++) {
-    double sl, sr;
-    recon_pair<RECON>(spec.p[s], c, sd, theta, false, 0., sl, sr);
-    F.sc[s][c] = passive_flux(sl, sr, f.rho);
-  }
+  const double rho = __ldg(u.rho + c);
+  for (int s = 0; s < nsc; s++)
+    spec.p[s][c] = __ldg(u.sc[s] + c) / rho;
 }
 
 // ---------------------------------------------------------------------------
@@ -312,7 +176,8 @@ struct UpdateArgs {
   State u0, out;
   FluxSet flux[3];
   const double* bi_out[3];
-  const double* prim_p;
+  const double* cur_rho;     // density / internal energy of the stage's input
+  const double* cur_eint;    // state (dual-energy source term only)
   const double* accel[3];
   double dtd[3];
   double dt;
@@ -383,7 +248,12 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
   // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
   double d_rho = 0., d_mx = 0., d_my = 0., d_mz = 0., d_e = 0., d_eint = 0.;
   double p_floored = 0.;
-  if (DE) p_floored = apply_floor(__ldg(A.prim_p + c), P.pressure_floor);
+  if (DE) {
+    // cell-centred primitive pressure of the current stage
+    // (EnzoComputePressure.cpp: p = (gamma-1) rho eint with dual energy)
+    const double p = (P.gamma - 1.0) * __ldg(A.cur_rho + c) * __ldg(A.cur_eint + c);
+    p_floored = apply_floor(p, P.pressure_floor);
+  }
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const FluxSet& F = A.flux[d];
@@ -559,21 +429,6 @@ k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
   }
 }
 
-inline Box full_box(const Geom& G, int s)
-{
-  Box b;
-  b.lo[0] = b.lo[1] = b.lo[2] = s;
-  b.hi[0] = G.mx - s; b.hi[1] = G.my - s; b.hi[2] = G.mz - s;
-  return b;
-}
-
-inline ScalarPtrs scalar_ptrs(double* const* p, int n)
-{
-  ScalarPtrs s;
-  for (int i = 0; i < kMaxPassive; i++) s.p[i] = (i < n) ? p[i] : nullptr;
-  return s;
-}
-
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -623,89 +478,12 @@ void Profiler::reset()
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
                        const State& cur, const Scratch& S, int stale)
 {
-  cudaStream_t st = ctx.st;
+  if (P.nsc == 0) return;   // pressure is computed inside the flux kernels
   const Box box = full_box(G, stale);
   if (empty(box)) return;
-  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
-  const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
-  ScopedLaunch sl(ctx, "k_primitives");
-  if (P.mhd) {
-    if (P.de) k_primitives<true, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
-    else      k_primitives<true, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
-  } else {
-    if (P.de) k_primitives<false, true><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
-    else      k_primitives<false, false><<<grid, block, 0, st>>>(P, G, cur, S.prim_p, spec, box);
-  }
-}
-
-namespace {
-
-template <int DIM, int RECON, int SOLVER>
-void flux_de(cudaStream_t st, bool de, dim3 grid, dim3 block, const Params& P,
-             const Geom& G, const State& cur, const double* prim_p,
-             const ScalarPtrs& spec, const double* bi, const FluxSet& F,
-             const Box& box)
-{
-  if (de) k_flux<DIM, RECON, SOLVER, true><<<grid, block, 0, st>>>(P, G, cur, prim_p, spec, bi, F, box);
-  else    k_flux<DIM, RECON, SOLVER, false><<<grid, block, 0, st>>>(P, G, cur, prim_p, spec, bi, F, box);
-}
-
-template <int DIM, int RECON>
-void flux_solver(cudaStream_t st, int solver, bool de, dim3 grid, dim3 block,
-                 const Params& P, const Geom& G, const State& cur,
-                 const double* prim_p, const ScalarPtrs& spec, const double* bi,
-                 const FluxSet& F, const Box& box)
-{
-  switch (solver) {
-  case VLCT_RIEMANN_HLLD:
-    flux_de<DIM, RECON, SOLVER_HLLD>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  case VLCT_RIEMANN_HLLE:
-    flux_de<DIM, RECON, SOLVER_HLLE>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  default:
-    flux_de<DIM, RECON, SOLVER_HLLC>(st, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  }
-}
-
-template <int DIM>
-void flux_recon(cudaStream_t st, int recon, int solver, bool de, dim3 grid,
-                dim3 block, const Params& P, const Geom& G, const State& cur,
-                const double* prim_p, const ScalarPtrs& spec, const double* bi,
-                const FluxSet& F, const Box& box)
-{
-  switch (recon) {
-  case VLCT_RECON_NN:
-    flux_solver<DIM, RECON_NN>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  case VLCT_RECON_PLM_ATHENA:
-    flux_solver<DIM, RECON_PLM_ATHENA>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  default:
-    flux_solver<DIM, RECON_PLM_ENZO>(st, solver, de, grid, block, P, G, cur, prim_p, spec, bi, F, box); break;
-  }
-}
-
-}  // namespace
-
-void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
-                 int recon, const State& cur, const Scratch& S,
-                 const FaceB& bi_cur, int cs)
-{
-  cudaStream_t st = ctx.st;
-  // non-stale faces: [cs, f-cs) on every axis of the face-shaped array
-  Box box = full_box(G, cs);
-  box.hi[dim] -= 1;
-  if (empty(box)) return;
-  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
-  const ScalarPtrs spec = scalar_ptrs(S.prim_sc, P.nsc);
-  const double* bi = P.mhd ? bi_cur.bi[dim] : nullptr;
-  const bool de = P.de != 0;
-  static const char* const names[2][3] = {
-    { "k_flux_x_nn", "k_flux_y_nn", "k_flux_z_nn" },
-    { "k_flux_x_plm", "k_flux_y_plm", "k_flux_z_plm" } };
-  ScopedLaunch sl(ctx, names[recon == VLCT_RECON_NN ? 0 : 1][dim]);
-  switch (dim) {
-  case 0: flux_recon<0>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[0], box); break;
-  case 1: flux_recon<1>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[1], box); break;
-  default: flux_recon<2>(st, recon, P.riemann, de, grid, block, P, G, cur, S.prim_p, spec, bi, S.flux[2], box); break;
-  }
+  ScopedLaunch sl(ctx, "k_specific_scalars");
+  k_specific_scalars<<<grid_for(box), dim3(kBlockX, kBlockY), 0, ctx.st>>>(
+      P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
 }
 
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
@@ -759,9 +537,10 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
 }
 
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                   const State& u0, const State& out, const Scratch& S,
-                   const FaceB& bi_out, const double* accel[3], bool gravity,
-                   double dt, const double* width, int s)
+                   const State& u0, const State& cur, const State& out,
+                   const Scratch& S, const FaceB& bi_out,
+                   const double* accel[3], bool gravity, double dt,
+                   const double* width, int s)
 {
   cudaStream_t st = ctx.st;
   UpdateArgs A;
@@ -772,7 +551,8 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
     A.accel[d] = gravity ? accel[d] : nullptr;
     A.dtd[d] = dt / width[d];
   }
-  A.prim_p = S.prim_p;
+  A.cur_rho = cur.rho;
+  A.cur_eint = cur.eint;
   A.dt = dt;
   A.gravity = gravity ? 1 : 0;
   A.inner = full_box(G, s + 1);

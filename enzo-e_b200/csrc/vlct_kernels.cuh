@@ -55,7 +55,6 @@ struct Scratch {
   State temp;           // temp_integration_map
   FaceB tbi;            // temp_bfieldi_l_
   FluxSet flux[3];
-  double *prim_p;       // primitive pressure of the current stage
   double *prim_sc[kMaxPassive]; // specific passive scalars
   double *edge[3];      // edge-centred E (cell strides)
 };
@@ -82,7 +81,8 @@ struct LaunchCtx {
   Profiler* prof;
 };
 
-/// primitive pressure (+ specific scalars) over [s, m-s)^3
+/// specific passive scalars over [s, m-s)^3 (no-op without scalars; the
+/// primitive pressure is computed on the fly by the flux kernels)
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
                        const State& cur, const Scratch& S, int stale);
 
@@ -98,9 +98,10 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
 
 /// centred B + flux divergence + sources + conserved update + floors/sync
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                   const State& u0, const State& out, const Scratch& S,
-                   const FaceB& bi_out, const double* accel[3], bool gravity,
-                   double dt, const double* width, int stale);
+                   const State& u0, const State& cur, const State& out,
+                   const Scratch& S, const FaceB& bi_out,
+                   const double* accel[3], bool gravity, double dt,
+                   const double* width, int stale);
 
 /// DE sync + pressure field + CFL minimum over all cells; *dt_bits receives
 /// the bit pattern of the minimum local dt (not yet multiplied by courant)

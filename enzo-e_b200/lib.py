@@ -10,7 +10,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvlct_b200.so")
+LIB_PATH = os.environ.get("VLCT_B200_LIB") or os.path.join(
+    _HERE, "csrc", "libvlct_b200.so")   # env override: A/B builds while tuning
 
 # every symbol include/vlct.h declares
 EXPORTED_SYMBOLS = (
