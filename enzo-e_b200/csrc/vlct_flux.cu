@@ -64,6 +64,23 @@ __device__ __forceinline__ void load_cell(const Params& P, const State& u,
   if (MHD) { w[W_BJ] = b[JD]; w[W_BK] = b[KD]; }
 }
 
+__device__ __forceinline__ void prefetch_l1(const double* p)
+{
+#ifndef VLCT_NO_PREFETCH
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#endif
+}
+
+/// pull the lines of cell c into L1 ahead of the load_cell that will need them
+template <bool MHD, bool DE>
+__device__ __forceinline__ void prefetch_cell(const State& u, size_t c)
+{
+  prefetch_l1(u.rho + c);
+  prefetch_l1(u.vx + c); prefetch_l1(u.vy + c); prefetch_l1(u.vz + c);
+  if (MHD) { prefetch_l1(u.bx + c); prefetch_l1(u.by + c); prefetch_l1(u.bz + c); }
+  if (DE) prefetch_l1(u.eint + c); else prefetch_l1(u.etot + c);
+}
+
 template <bool MHD>
 __device__ __forceinline__ void apply_floors(const Params& P,
                                              double (&w)[NVars<MHD>::n])
@@ -145,11 +162,14 @@ solve_and_store(const Params& P, const double* wl_, const double* wr_,
 #define VLCT_FLUX_MINBLOCKS 4     // 128-thread blocks per SM => <=128 registers
 #endif
 constexpr int kXWarps = 4;
+constexpr int kXRows = 8;        // rows a warp walks through, one after another
 
 template <int RECON, int SOLVER, bool DE>
 __global__ void __launch_bounds__(kXWarps * 32, VLCT_FLUX_MINBLOCKS)
-k_flux_x(const Params P, const Geom G, const State u, const ScalarPtrs spec,
-         const double* __restrict__ bi, const FluxSet F, const Box box)
+k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
+         const __grid_constant__ State u, const __grid_constant__ ScalarPtrs spec,
+         const double* __restrict__ bi, const __grid_constant__ FluxSet F,
+         const __grid_constant__ Box box)
 {
   constexpr bool MHD = (SOLVER != SOLVER_HLLC);
   constexpr int NV = NVars<MHD>::n;
@@ -163,76 +183,93 @@ k_flux_x(const Params P, const Geom G, const State u, const ScalarPtrs spec,
   const int nfx = box.hi[0] - box.lo[0];
   const int wpr = (nfx + 31) >> 5;        // warps per row
   const int nyb = box.hi[1] - box.lo[1], nzb = box.hi[2] - box.lo[2];
-  const long long gw = (long long) blockIdx.x * kXWarps + w;
-  if (gw >= (long long) wpr * nyb * nzb) return;
-  const int seg = (int) (gw % wpr);
-  const long long row = gw / wpr;
-  const int j = box.lo[1] + (int) (row % nyb), k = box.lo[2] + (int) (row / nyb);
+  // (32-bit index arithmetic: the launcher checks that the counts fit)
+  const unsigned nrows = (unsigned) nyb * (unsigned) nzb;
+  const unsigned ngroups = (nrows + kXRows - 1) / kXRows;
+  const unsigned gw = blockIdx.x * kXWarps + w;
+  if (gw >= (unsigned) wpr * ngroups) return;
+  // consecutive warps take consecutive segments of the same rows
+  const int seg = (int) (gw % (unsigned) wpr);
+  const unsigned row0 = (gw / (unsigned) wpr) * kXRows;
+  const unsigned row1 = (row0 + kXRows < nrows) ? row0 + kXRows : nrows;
   const int f0 = box.lo[0] + seg * 32;
   const int nf = min(32, box.hi[0] - f0);
-  const size_t rowbase = cidx(G, k, j, 0);
+  const int i = f0 + lane;                // own cell = left cell of own face
 
-  // own cell (left cell of this lane's face)
-  const int i = f0 + lane;
-  double W[NV];
-#pragma unroll
-  for (int v = 0; v < NV; v++) W[v] = 0.;
-  if (i < G.mx) {
-    load_cell<0, MHD, DE>(P, u, rowbase + i, W);
-#pragma unroll
-    for (int v = 0; v < NV; v++) sW[w][v][lane + H] = W[v];
-  }
   // the cells beyond the warp's 32: three lanes fetch one extra cell each
-  {
-    int ecell = -1, epos = 0;
-    if (PLM) {
-      if (lane == 0)      { ecell = f0 - 1;  epos = 0; }
-      else if (lane == 1) { ecell = f0 + 32; epos = 33; }
-      else if (lane == 2) { ecell = f0 + 33; epos = 34; }
-    } else if (lane == 0) { ecell = f0 + 32; epos = 32; }
-    if (ecell >= 0 && ecell < G.mx) {
+  int ecell = -1, epos = 0;
+  if (PLM) {
+    if (lane == 0)      { ecell = f0 - 1;  epos = 0; }
+    else if (lane == 1) { ecell = f0 + 32; epos = 33; }
+    else if (lane == 2) { ecell = f0 + 33; epos = 34; }
+  } else if (lane == 0) { ecell = f0 + 32; epos = 32; }
+  if (ecell >= G.mx) ecell = -1;
+
+  // (j,k) of the current row, advanced incrementally
+  int j = box.lo[1] + (int) (row0 % (unsigned) nyb);
+  int k = box.lo[2] + (int) (row0 / (unsigned) nyb);
+#pragma unroll 1
+  for (unsigned row = row0; row < row1; row++) {
+    const size_t rowbase = cidx(G, k, j, 0);
+    const int jc = j, kc = k;
+    if (++j == box.hi[1]) { j = box.lo[1]; k++; }
+    if (row + 1 < row1 && i < G.mx) {
+      prefetch_cell<MHD, DE>(u, cidx(G, k, j, i));
+      if (MHD) prefetch_l1(bi + fidx(G, 0, k, j, i + 1));
+    }
+    double W[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) W[v] = 0.;
+    if (i < G.mx) {
+      load_cell<0, MHD, DE>(P, u, rowbase + i, W);
+#pragma unroll
+      for (int v = 0; v < NV; v++) sW[w][v][lane + H] = W[v];
+    }
+    if (ecell >= 0) {
       double E[NV];
       load_cell<0, MHD, DE>(P, u, rowbase + ecell, E);
 #pragma unroll
       for (int v = 0; v < NV; v++) sW[w][v][epos] = E[v];
     }
-  }
-  __syncwarp();
-
-  double wl[NV], wr[NV];
-  if (PLM) {
-    // limited slope of the own cell, once; the neighbour's comes from its lane
-    double dv[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-      dv[v] = limited_slope<RECON>(sW[w][v][lane], W[v], sW[w][v][lane + 2], P.theta);
-      sD[w][v][lane] = dv[v];
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int v = 0; v < NV; v++)
-        sD[w][v][32] = limited_slope<RECON>(sW[w][v][32], sW[w][v][33],
-                                            sW[w][v][34], P.theta);
-    }
     __syncwarp();
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-      wl[v] = W[v] + dv[v] * 0.5;
-      wr[v] = sW[w][v][lane + 2] - sD[w][v][lane + 1] * 0.5;
-    }
-    apply_floors<MHD>(P, wl);
-    apply_floors<MHD>(P, wr);
-  } else {
-#pragma unroll
-    for (int v = 0; v < NV; v++) { wl[v] = W[v]; wr[v] = sW[w][v][lane + 1]; }
-  }
-  if (lane >= nf) return;
 
-  const size_t c = rowbase + i;
-  double blong = 0.;
-  // face f of the sweep <-> index f+1 of the face-centred array
-  if (MHD) blong = __ldg(bi + fidx(G, 0, k, j, i + 1));
-  solve_and_store<0, RECON, SOLVER, DE>(P, wl, wr, blong, F, spec, c, 1);
+    double wl[NV], wr[NV];
+    if (PLM) {
+      // limited slope of the own cell, once; the neighbour's comes from its lane
+      double dv[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        dv[v] = limited_slope<RECON>(sW[w][v][lane], W[v], sW[w][v][lane + 2], P.theta);
+        sD[w][v][lane] = dv[v];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+          sD[w][v][32] = limited_slope<RECON>(sW[w][v][32], sW[w][v][33],
+                                              sW[w][v][34], P.theta);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        wl[v] = W[v] + dv[v] * 0.5;
+        wr[v] = sW[w][v][lane + 2] - sD[w][v][lane + 1] * 0.5;
+      }
+      apply_floors<MHD>(P, wl);
+      apply_floors<MHD>(P, wr);
+    } else {
+#pragma unroll
+      for (int v = 0; v < NV; v++) { wl[v] = W[v]; wr[v] = sW[w][v][lane + 1]; }
+    }
+    __syncwarp();   // strip is rewritten by the next row
+
+    if (lane < nf) {
+      const size_t c = rowbase + i;
+      double blong = 0.;
+      // face f of the sweep <-> index f+1 of the face-centred array
+      if (MHD) blong = __ldg(bi + fidx(G, 0, kc, jc, i + 1));
+      solve_and_store<0, RECON, SOLVER, DE>(P, wl, wr, blong, F, spec, c, 1);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -242,9 +279,11 @@ constexpr int kMarchThreads = 128;
 
 template <int DIM, int RECON, int SOLVER, bool DE>
 __global__ void __launch_bounds__(kMarchThreads, VLCT_FLUX_MINBLOCKS)
-k_flux_march(const Params P, const Geom G, const State u, const ScalarPtrs spec,
-             const double* __restrict__ bi, const FluxSet F, const Box box,
-             const int chunk)
+k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
+             const __grid_constant__ State u,
+             const __grid_constant__ ScalarPtrs spec,
+             const double* __restrict__ bi, const __grid_constant__ FluxSet F,
+             const __grid_constant__ Box box, const int chunk)
 {
   static_assert(DIM == 1 || DIM == 2, "marching sweeps are y and z");
   constexpr bool MHD = (SOLVER != SOLVER_HLLC);
@@ -254,10 +293,10 @@ k_flux_march(const Params P, const Geom G, const State u, const ScalarPtrs spec,
 
   const int nxb = box.hi[0] - box.lo[0];
   const int nob = box.hi[OD] - box.lo[OD];
-  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long) nxb * nob) return;
-  const int i = box.lo[0] + (int) (t % nxb);
-  const int o = box.lo[OD] + (int) (t / nxb);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned) nxb * (unsigned) nob) return;
+  const int i = box.lo[0] + (int) (t % (unsigned) nxb);
+  const int o = box.lo[OD] + (int) (t / (unsigned) nxb);
   const int f0 = box.lo[DIM] + (int) blockIdx.y * chunk;
   const int f1 = min(f0 + chunk, box.hi[DIM]);
   const int j = (DIM == 1) ? f0 : o, k = (DIM == 1) ? o : f0;
@@ -283,9 +322,15 @@ k_flux_march(const Params P, const Geom G, const State u, const ScalarPtrs spec,
     load_cell<DIM, MHD, DE>(P, u, c, Wc);
   }
 
+  const int mdim = (DIM == 1) ? G.my : G.mz;
+  constexpr int kAhead = 2;                 // prefetch distance, in faces
 #pragma unroll 1
   for (int f = f0; f < f1; f++, c += sd, fb += sd) {
     double Wn[NV], wr[NV], wl_next[NV];
+    if (f + (PLM ? 2 : 1) + kAhead < mdim) {
+      prefetch_cell<MHD, DE>(u, c + ((PLM ? 2 : 1) + kAhead) * sd);
+      if (MHD) prefetch_l1(bi + fb + kAhead * sd);
+    }
     if (PLM) {
       load_cell<DIM, MHD, DE>(P, u, c + 2 * sd, Wn);
 #pragma unroll
@@ -327,7 +372,8 @@ void flux_go(const FluxLaunch& L)
   const Box& b = L.box;
   if constexpr (DIM == 0) {
     const long long wpr = (b.hi[0] - b.lo[0] + 31) / 32;
-    const long long warps = wpr * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    const long long rows = (long long) (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    const long long warps = wpr * ((rows + kXRows - 1) / kXRows);
     const unsigned grid = (unsigned) ((warps + kXWarps - 1) / kXWarps);
     k_flux_x<RECON, SOLVER, DE><<<grid, kXWarps * 32, 0, L.st>>>(
         L.P, L.G, L.cur, L.spec, L.bi, L.F, b);

@@ -28,28 +28,31 @@ namespace vlct {
 
 namespace {
 
-constexpr int kBlockX = 64;
-constexpr int kBlockY = 4;
+// Cell-parallel kernels: a block owns kBlock consecutive entries of the
+// flattened (y,x) plane of the box (no partially filled rows: 514 of 518 wide
+// boxes would otherwise waste 10-20 % of the threads), blockIdx.y is z.
+constexpr int kBlock = 256;
 
 inline dim3 grid_for(const Box& b)
 {
-  const int nx = b.hi[0] - b.lo[0], ny = b.hi[1] - b.lo[1], nz = b.hi[2] - b.lo[2];
-  return dim3((unsigned) ((nx + kBlockX - 1) / kBlockX),
-              (unsigned) ((ny + kBlockY - 1) / kBlockY), (unsigned) nz);
+  const unsigned nx = b.hi[0] - b.lo[0], ny = b.hi[1] - b.lo[1], nz = b.hi[2] - b.lo[2];
+  return dim3((nx * ny + kBlock - 1) / kBlock, nz, 1);
 }
 
-#define VLCT_THREAD_IN_BOX(box, i, j, k)                                     \
-  const int i = (box).lo[0] + (int) (blockIdx.x * blockDim.x + threadIdx.x); \
-  const int j = (box).lo[1] + (int) (blockIdx.y * blockDim.y + threadIdx.y); \
-  const int k = (box).lo[2] + (int) blockIdx.z;                              \
-  if (i >= (box).hi[0] || j >= (box).hi[1] || k >= (box).hi[2]) return;
+#define VLCT_THREAD_IN_BOX(box, i, j, k)                                       \
+  const unsigned nxb__ = (box).hi[0] - (box).lo[0];                            \
+  const unsigned t__ = blockIdx.x * kBlock + threadIdx.x;                      \
+  if (t__ >= nxb__ * (unsigned) ((box).hi[1] - (box).lo[1])) return;           \
+  const int i = (box).lo[0] + (int) (t__ % nxb__);                             \
+  const int j = (box).lo[1] + (int) (t__ / nxb__);                             \
+  const int k = (box).lo[2] + (int) blockIdx.y;
 
 // ---------------------------------------------------------------------------
 // specific passive scalars: EnzoPhysicsFluidProps::primitive_from_integration
 // (fluid-props/EnzoPhysicsFluidProps.cpp:64-138). The pressure part of that
 // routine is evaluated on the fly inside the flux kernels (vlct_flux.cu).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockX * kBlockY)
+__global__ void __launch_bounds__(kBlock)
 k_specific_scalars(const int nsc, const Geom G, const State u,
                    const ScalarPtrs spec, const Box box)
 {
@@ -121,7 +124,7 @@ __device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
   A.edge[D][c] = 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
 }
 
-__global__ void __launch_bounds__(kBlockX * kBlockY)
+__global__ void __launch_bounds__(kBlock)
 k_edge_efield(const Geom G, const EdgeArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(box, i, j, k);
@@ -157,7 +160,7 @@ __device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
   A.bi_out[D][f] = __ldg(A.bi0[D] + f) - E_k_term + E_j_term;
 }
 
-__global__ void __launch_bounds__(kBlockX * kBlockY)
+__global__ void __launch_bounds__(kBlock)
 k_face_bfield(const Geom G, const FaceArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(box, i, j, k);
@@ -221,7 +224,7 @@ floor_energy_and_sync(const Params& P, double rho, double vx, double vy,
 }
 
 template <bool MHD, bool DE>
-__global__ void __launch_bounds__(kBlockX * kBlockY)
+__global__ void __launch_bounds__(kBlock)
 k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(box, i, j, k);
@@ -482,7 +485,7 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
   const Box box = full_box(G, stale);
   if (empty(box)) return;
   ScopedLaunch sl(ctx, "k_specific_scalars");
-  k_specific_scalars<<<grid_for(box), dim3(kBlockX, kBlockY), 0, ctx.st>>>(
+  k_specific_scalars<<<grid_for(box), kBlock, 0, ctx.st>>>(
       P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
 }
 
@@ -492,7 +495,7 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
 {
   cudaStream_t st = ctx.st;
   const int m[3] = { G.mx, G.my, G.mz };
-  const dim3 block(kBlockX, kBlockY);
+  const int block = kBlock;
   {
     EdgeArgs A;
     A.v[0] = cur.vx; A.v[1] = cur.vy; A.v[2] = cur.vz;
@@ -559,7 +562,7 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   // with CT the centred B is rewritten on the whole [s, m-s)^3 region
   const Box box = P.mhd ? full_box(G, s) : A.inner;
   if (empty(box)) return;
-  const dim3 block(kBlockX, kBlockY), grid = grid_for(box);
+  const int block = kBlock; const dim3 grid = grid_for(box);
   ScopedLaunch sl(ctx, "k_update");
   if (P.mhd) {
     if (P.de) k_update<true, true><<<grid, block, 0, st>>>(P, G, A, box);
