@@ -37,6 +37,7 @@ struct vlct_handle {
   vlct_block mirror;
   std::vector<void*> mirror_allocs;
   long long launches = 0;
+  long long copied_bytes[2] = { 0, 0 };   // H2D, D2H staged for HOST blocks
   Profiler prof;
   std::string last_error;
 };
@@ -228,26 +229,40 @@ int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
   return VLCT_OK;
 }
 
-/// copy the listed members between the host block and its device mirror
+/// which fields one entry point reads (H2D) and writes (D2H)
+enum CopySet { COPY_COMPUTE_IN, COPY_COMPUTE_OUT, COPY_TIMESTEP_IN };
+
+bool in_copy_set(const vlct_handle* h, double* vlct_block::*m, CopySet set)
+{
+  const bool face = (m == &vlct_block::bfieldi_x || m == &vlct_block::bfieldi_y ||
+                     m == &vlct_block::bfieldi_z);
+  const bool accel = (m == &vlct_block::acceleration_x ||
+                      m == &vlct_block::acceleration_y ||
+                      m == &vlct_block::acceleration_z);
+  if (m == &vlct_block::pressure) return false;   // output of timestep only
+  switch (set) {
+  case COPY_COMPUTE_IN:  return accel ? (h->cfg.has_acceleration != 0) : true;
+  case COPY_COMPUTE_OUT: return !accel;            // compute never writes them
+  case COPY_TIMESTEP_IN: return !face && !accel;   // cell-centred state only
+  }
+  return true;
+}
+
+/// copy a set of fields between the host block and its device mirror
 int mirror_copy(vlct_handle* h, const vlct_block* host, const Geom& G,
-                cudaStream_t st, bool to_device, bool inputs_only_changed)
+                cudaStream_t st, bool to_device, CopySet set)
 {
   for (int f = 0; f < kNumFields; f++) {
     double* hp = host->*(kFields[f].member);
     double* dp = h->mirror.*(kFields[f].member);
     if (hp == nullptr || dp == nullptr) continue;
-    if (!to_device && inputs_only_changed) {
-      // compute() never modifies pressure or the acceleration fields
-      if (kFields[f].member == &vlct_block::pressure ||
-          kFields[f].member == &vlct_block::acceleration_x ||
-          kFields[f].member == &vlct_block::acceleration_y ||
-          kFields[f].member == &vlct_block::acceleration_z) continue;
-    }
+    if (!in_copy_set(h, kFields[f].member, set)) continue;
     const size_t bytes = field_count(G, kFields[f].face) * sizeof(double);
     CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) dp : (void*) hp,
                                 to_device ? (void*) hp : (void*) dp, bytes,
                                 to_device ? cudaMemcpyHostToDevice
                                           : cudaMemcpyDeviceToHost, st));
+    h->copied_bytes[to_device ? 0 : 1] += (long long) bytes;
   }
   for (int s = 0; s < h->P.nsc; s++) {
     const size_t bytes = G.cells() * sizeof(double);
@@ -257,6 +272,7 @@ int mirror_copy(vlct_handle* h, const vlct_block* host, const Geom& G,
                                 to_device ? (void*) hp : (void*) dp, bytes,
                                 to_device ? cudaMemcpyHostToDevice
                                           : cudaMemcpyDeviceToHost, st));
+    h->copied_bytes[to_device ? 0 : 1] += (long long) bytes;
   }
   return VLCT_OK;
 }
@@ -398,9 +414,9 @@ int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
   // HOST: stage through the device mirror; synchronous
   cudaStream_t st = h->own_stream;
   if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
-  if ((rc = mirror_copy(h, b, G, st, true, false)) != VLCT_OK) return rc;
+  if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
   if ((rc = compute_on_device(h, &h->mirror, G, dt, st)) != VLCT_OK) return rc;
-  if ((rc = mirror_copy(h, b, G, st, false, true)) != VLCT_OK) return rc;
+  if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(st));
   return VLCT_OK;
 }
@@ -421,7 +437,7 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   } else {
     st = h->own_stream;
     if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
-    if ((rc = mirror_copy(h, b, G, st, true, false)) != VLCT_OK) return rc;
+    if ((rc = mirror_copy(h, b, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
     db = &h->mirror;
   }
   const State u = state_of(h, db);
@@ -433,9 +449,11 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
     // timestep writes "pressure" and (dual energy) total/internal energy
     const size_t bytes = G.cells() * sizeof(double);
     CUDA_TRY(h, cudaMemcpyAsync(b->pressure, db->pressure, bytes, cudaMemcpyDeviceToHost, st));
+    h->copied_bytes[1] += (long long) bytes;
     if (h->P.de) {
       CUDA_TRY(h, cudaMemcpyAsync(b->total_energy, db->total_energy, bytes, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(h, cudaMemcpyAsync(b->internal_energy, db->internal_energy, bytes, cudaMemcpyDeviceToHost, st));
+      h->copied_bytes[1] += 2 * (long long) bytes;
     }
   }
   CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -454,6 +472,9 @@ long long vlct_kernel_launches(const vlct_handle* h)
 
 long long vlct_scratch_bytes(const vlct_handle* h)
 { return h ? h->scratch_bytes : 0; }
+
+long long vlct_staged_bytes(const vlct_handle* h, int direction)
+{ return (h && (direction == 0 || direction == 1)) ? h->copied_bytes[direction] : 0; }
 
 int vlct_synchronize(vlct_handle* h)
 {

@@ -18,7 +18,8 @@ EXPORTED_SYMBOLS = (
     "vlct_config_init", "vlct_config_set", "vlct_config_validate",
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_last_error", "vlct_status_string",
-    "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_synchronize",
+    "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_staged_bytes",
+    "vlct_synchronize",
     "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
     "vlct_profile_get",
     "vlct_refresh_periodic", "vlct_halo_bytes", "vlct_halo_pack",
@@ -62,6 +63,7 @@ def load():
         "vlct_status_string": (C.c_char_p, [C.c_int]),
         "vlct_kernel_launches": (C.c_longlong, [C.c_void_p]),
         "vlct_scratch_bytes": (C.c_longlong, [C.c_void_p]),
+        "vlct_staged_bytes": (C.c_longlong, [C.c_void_p, C.c_int]),
         "vlct_synchronize": (C.c_int, [C.c_void_p]),
         "vlct_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
         "vlct_profile_reset": (C.c_int, [C.c_void_p]),

@@ -172,6 +172,11 @@ class EnzoMethodMHDVlct:
     def scratch_bytes(self):
         return int(self._lib.vlct_scratch_bytes(self._h))
 
+    def staged_bytes(self):
+        """(host->device, device->host) bytes copied so far for HOST blocks"""
+        return (int(self._lib.vlct_staged_bytes(self._h, 0)),
+                int(self._lib.vlct_staged_bytes(self._h, 1)))
+
     def profile(self, on=True):
         """Switch per-kernel CUDA-event timing on/off (clears old samples)."""
         self._check(self._lib.vlct_profile_reset(self._h))

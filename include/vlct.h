@@ -181,6 +181,10 @@ long long vlct_kernel_launches(const vlct_handle *h);
 /* Bytes of device scratch currently owned by the handle. */
 long long vlct_scratch_bytes(const vlct_handle *h);
 
+/* Bytes staged so far for VLCT_MEM_HOST blocks: direction 0 = host->device,
+ * 1 = device->host (bench.py reports them per step as e2e.h2d/d2h bytes). */
+long long vlct_staged_bytes(const vlct_handle *h, int direction);
+
 /* Block until all work submitted through this handle has finished. */
 int vlct_synchronize(vlct_handle *h);
 

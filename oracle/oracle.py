@@ -25,6 +25,10 @@ from enzo_e_b200 import abi  # noqa: E402  (struct layouts only)
 
 ORACLE_LIB = os.path.join(_HERE, "libvlct_oracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libvlct_ref.so")
+# integration/EnzoMethodMHDVlctGpu (the reference-side C++ binding of the CUDA
+# library) behind the same Block/Field stand-ins -- a GPU path, listed here only
+# because it is built by oracle/Makefile against the reference's headers
+ADAPTER_LIB = os.path.join(_HERE, "_ref", "libvlct_adapter.so")
 
 
 def build(target="all"):
@@ -41,18 +45,23 @@ def have_oracle():
     return os.path.exists(ORACLE_LIB)
 
 
+def have_adapter():
+    return os.path.exists(ADAPTER_LIB)
+
+
 _libs = {}
 
 
 def _load(kind):
     if kind in _libs:
         return _libs[kind]
-    path = {"oracle": ORACLE_LIB, "ref": REF_LIB}[kind]
+    path = {"oracle": ORACLE_LIB, "ref": REF_LIB, "adapter": ADAPTER_LIB}[kind]
     if not os.path.exists(path):
         raise FileNotFoundError(
             f"{path} is missing: run `make -C oracle` (kind={kind})")
     lib = C.CDLL(path)
-    pfx = "vlct_oracle" if kind == "oracle" else "vlct_ref"
+    pfx = {"oracle": "vlct_oracle", "ref": "vlct_ref",
+           "adapter": "vlct_adapter"}[kind]
     create = getattr(lib, pfx + "_create")
     create.restype = C.c_void_p
     create.argtypes = [C.POINTER(abi.VlctConfig), C.c_int, C.c_int, C.c_int]

@@ -20,6 +20,22 @@
 
 #include "../../include/vlct.h"
 
+// Two flavours of this file are built:
+//   default                  drives the reference's own EnzoMethodMHDVlct
+//                            (libvlct_ref.so, entry points vlct_ref_*)
+//   -DVLCT_SHIM_GPU_ADAPTER  drives integration/EnzoMethodMHDVlctGpu -- the
+//                            reference-side binding of the CUDA library --
+//                            through the very same Block/Field stand-ins
+//                            (libvlct_adapter.so, entry points vlct_adapter_*)
+#ifdef VLCT_SHIM_GPU_ADAPTER
+#include "../../integration/EnzoMethodMHDVlctGpu.hpp"
+typedef EnzoMethodMHDVlctGpu ShimMethod;
+#define SHIM_FN(name) vlct_adapter_##name
+#else
+typedef EnzoMethodMHDVlct ShimMethod;
+#define SHIM_FN(name) vlct_ref_##name
+#endif
+
 //----------------------------------------------------------------------
 // global state the reference reaches through cello:: / enzo:: accessors
 //----------------------------------------------------------------------
@@ -86,7 +102,7 @@ struct RefContext {
 
 struct RefHandle {
   RefContext* ctx;
-  EnzoMethodMHDVlct* method;
+  ShimMethod* method;
 };
 
 std::vector<RefContext*> g_contexts;
@@ -162,7 +178,7 @@ void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
 
 extern "C" {
 
-void* vlct_ref_create(const vlct_config* cfg, int gx, int gy, int gz)
+void* SHIM_FN(create)(const vlct_config* cfg, int gx, int gy, int gz)
 {
   std::lock_guard<std::mutex> lock(g_mutex);
   RefContext* c = nullptr;
@@ -234,11 +250,11 @@ void* vlct_ref_create(const vlct_config* cfg, int gx, int gy, int gz)
     p.set("mhd_choice", mhd ? "constrained_transport" : "no_bfield");
   if (cfg->courant >= 0) p.set("courant", fmt_double(cfg->courant));
 
-  h->method = new EnzoMethodMHDVlct(p, false);
+  h->method = new ShimMethod(p, false);
   return h;
 }
 
-void vlct_ref_destroy(void* handle)
+void SHIM_FN(destroy)(void* handle)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   if (h == nullptr) return;
@@ -257,7 +273,7 @@ void vlct_ref_destroy(void* handle)
   delete h;
 }
 
-int vlct_ref_compute(void* handle, const vlct_block* b, double dt)
+int SHIM_FN(compute)(void* handle, const vlct_block* b, double dt)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   activate(h);
@@ -268,7 +284,7 @@ int vlct_ref_compute(void* handle, const vlct_block* b, double dt)
   return (blk.compute_done_count == 1) ? 0 : 1;
 }
 
-int vlct_ref_timestep(void* handle, const vlct_block* b, double* dt_out)
+int SHIM_FN(timestep)(void* handle, const vlct_block* b, double* dt_out)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   activate(h);
@@ -278,7 +294,7 @@ int vlct_ref_timestep(void* handle, const vlct_block* b, double* dt_out)
   return 0;
 }
 
-const char* vlct_ref_name(void* handle)
+const char* SHIM_FN(name)(void* handle)
 {
   static std::string name;
   name = static_cast<RefHandle*>(handle)->method->name();
