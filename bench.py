@@ -322,8 +322,8 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         fields = problems.orszag_tang(n_local, GHOST, lower, width, device=dev)
         method = EnzoMethodMHDVlct(PARAMS)
-        block = Block(fields, n_local, GHOST, width, stream=stream.cuda_stream)
-        block.stream_is_current = True
+        block = Block(fields, n_local, GHOST, width)   # torch's current stream
+        assert block.stream_is_current
 
         def step():
             dt = method.timestep(block)

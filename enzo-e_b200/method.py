@@ -62,6 +62,15 @@ class Block:
         self.compute_done_count = 0
         first = next(iter(fields.values()))
         self.on_device = not isinstance(first, np.ndarray)
+        self.stream_is_current = False
+        if self.on_device and stream is None:
+            # run on torch's current stream, so that the library's kernels are
+            # ordered after whatever produced the tensors (the C ABI's own
+            # default -- stream NULL -- is a private non-blocking stream, which
+            # would NOT wait for torch's work). 0x1 is cudaStreamLegacy.
+            import torch
+            stream = torch.cuda.current_stream(first.device).cuda_stream or 0x1
+            self.stream_is_current = True
         self._c = self._build(stream)
 
     def compute_done(self):

@@ -112,7 +112,11 @@ typedef struct vlct_block {
                                     staged H2D/D2H inside the call;
                                     VLCT_MEM_DEVICE: device pointers         */
   void *stream;                  /* cudaStream_t (DEVICE only); NULL = the
-                                    library's own stream                     */
+                                    library's own non-blocking stream, which
+                                    does NOT wait for work the caller queued
+                                    on other streams: pass the stream that
+                                    produced the data (cudaStreamLegacy for
+                                    the default stream) or synchronise first */
 } vlct_block;
 
 typedef struct vlct_handle vlct_handle;

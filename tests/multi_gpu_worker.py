@@ -1,0 +1,92 @@
+"""Worker for test_gpu_multi.py (launched with torch.distributed.run, one rank
+per GPU): a periodic Orszag-Tang domain split into bricks, advanced with NCCL
+ghost exchange + dt all-reduce; rank 0 compares the gathered result with a
+single-block run of the same global domain -- bit for bit (block-decomposition
+invariance, input/vlct/run_MHD_linear_wave_test.py:81-156)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from enzo_e_b200 import problems
+    from enzo_e_b200.domain import Domain
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    n_scalars = 1
+    params = {"mhd_choice": "constrained_transport", "riemann_solver": "hlld",
+              "reconstruct_method": "plm", "theta_limiter": 1.5,
+              "courant": 0.3,
+              "Physics:fluid_props:floors:density": 1e-200,
+              "Physics:fluid_props:floors:pressure": 1e-200}
+    dom = Domain(rank, world)
+    g = (3, 3, 3)
+    n_local = (24, 20, 16)
+    N = tuple(n_local[a] * dom.grid[a] for a in range(3))
+    width = tuple(1.0 / N[a] for a in range(3))
+    passive = tuple(f"passive_{k}" for k in range(n_scalars))
+
+    def run(domain, n, lower):
+        f = problems.orszag_tang(n, g, lower, width, device=dev,
+                                 n_passive=n_scalars)
+        m = EnzoMethodMHDVlct(params, n_passive=n_scalars)
+        blk = Block(f, n, g, width, passive=passive)
+        dts = []
+        for _ in range(nsteps):
+            dt = domain.global_dt(m.timestep(blk), dev)
+            domain.refresh(m, blk)
+            m.compute(blk, dt)
+            dts.append(dt)
+        m.synchronize()
+        m.close()
+        return f, dts
+
+    f, dts = run(dom, n_local, dom.lower_corner(n_local, width))
+    ok = True
+    names = sorted(f)
+    # gather the active zones on rank 0
+    for name in names:
+        t = f[name].contiguous()
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, parts, dst=0)
+        if rank == 0:
+            f[name] = parts
+    if rank == 0:
+        single = Domain(0, 1)
+        fs, dts_s = run(single, N, (0.0, 0.0, 0.0))
+        if dts != dts_s:
+            print("dt sequences differ", dts, dts_s)
+            ok = False
+        for name in names:
+            face = {"bfieldi_x": 0, "bfieldi_y": 1, "bfieldi_z": 2}.get(name, -1)
+            for r in range(world):
+                c = Domain(r, world).coords
+                part = f[name][r]
+                sl_loc, sl_glob = [], []
+                for ax in (2, 1, 0):          # array axes z, y, x
+                    ext = n_local[ax] + (1 if face == ax else 0)
+                    sl_loc.append(slice(g[ax], g[ax] + ext))
+                    lo = g[ax] + c[ax] * n_local[ax]
+                    sl_glob.append(slice(lo, lo + ext))
+                if not torch.equal(part[tuple(sl_loc)], fs[name][tuple(sl_glob)]):
+                    diff = (part[tuple(sl_loc)] - fs[name][tuple(sl_glob)]).abs().max().item()
+                    print(f"MISMATCH {name} rank {r}: max diff {diff:.3e}")
+                    ok = False
+        print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAIL", "world", world, "grid",
+              dom.grid, "dts", dts)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
