@@ -118,6 +118,9 @@ int alloc_scratch(vlct_handle* h, const Geom& G)
   for (int s = 0; s < P.nsc; s++) ALLOC(S.prim_sc[s], n);
   if (P.mhd) for (int d = 0; d < 3; d++) ALLOC(S.edge[d], n);
 #undef ALLOC
+  // dev_alloc's memsets run on the legacy default stream; the kernels run on a
+  // non-blocking stream that does not order against it
+  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
   return VLCT_OK;
 }
 
@@ -225,6 +228,8 @@ int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
       h->mirror.passive[s] = p;
     }
   }
+  // the zero-fill above must not overtake the H2D copies on the work stream
+  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
   h->have_mirror = true;
   return VLCT_OK;
 }

@@ -349,8 +349,9 @@ k_timestep(const Params P, const Geom G, const State u, double* pressure,
     }
     pressure[c] = p;
     double cs;
-    if (MHD) cs = eos_cfast_max(P.gamma, rho, p, bx, by, bz);
-    else     cs = sqrt(eos_cs2(P.gamma, rho, p));
+    ExactOps op;   // HBM-bound kernel: the built-in operators are fine here
+    if (MHD) cs = eos_cfast_max(op, P.gamma, rho, p, bx, by, bz);
+    else     cs = sqrt(eos_cs2(op, P.gamma, rho, p));
     const double local_dt = min3(dx / (fabs(vx) + cs), dy / (fabs(vy) + cs),
                                  dz / (fabs(vz) + cs));
     local_min = std_min(local_min, local_dt);

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_staged_bytes",
     "vlct_synchronize",
     "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
-    "vlct_profile_get",
+    "vlct_profile_get", "vlct_selftest_fpops",
     "vlct_refresh_periodic", "vlct_halo_bytes", "vlct_halo_pack",
     "vlct_halo_unpack",
 )
@@ -70,6 +70,8 @@ def load():
         "vlct_profile_count": (C.c_int, [C.c_void_p]),
         "vlct_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p,
                                        C.c_int, dp, C.POINTER(C.c_longlong)]),
+        "vlct_selftest_fpops": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_int,
+                                          C.POINTER(C.c_longlong)]),
         "vlct_refresh_periodic": (C.c_int, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_bytes": (C.c_longlong, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_pack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),

@@ -202,6 +202,18 @@ int vlct_profile_count(vlct_handle *h);
 int vlct_profile_get(vlct_handle *h, int index, char *name, int name_len,
                      double *total_ms, long long *calls);
 
+/* Device self-test of the straight-line fp64 division / reciprocal / square
+ * root used by the flux kernels (csrc/vlct_fpops.cuh): evaluates n operand
+ * tuples generated from `seed` (mode 0: solver-like magnitudes, 1: arbitrary
+ * bit patterns, 2: specials) and compares with the built-in IEEE operators.
+ * counters_out[8] = for op in (div, rcp, sqrt, div2): { results that passed
+ * the range guard but differ from the built-in (must be 0), results flagged
+ * for re-evaluation with the built-in }. No reference counterpart: the
+ * reference's arithmetic is the compiler's (value-safe, OPTIMIZE_FP=OFF,
+ * CMakeLists.txt:275-283), which is what this test pins the kernels to. */
+int vlct_selftest_fpops(long long n, unsigned long long seed, int mode,
+                        long long *counters_out);
+
 /* ---- ghost-zone refresh on the device --------------
  * Stand-ins for the refresh phase that precedes compute() on a unigrid
  * (src/Cello/control_refresh.cpp:243-359, src/Cello/data_FieldFace.cpp).
