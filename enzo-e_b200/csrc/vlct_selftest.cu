@@ -47,12 +47,13 @@ __device__ __forceinline__ bool same_bits(double x, double y)
   return a == b;
 }
 
+// ops: div, rcp, sqrt, shared-reciprocal pair (quotz + quot), divz
 // counters: [op][0] = guarded-ok results that differ from the built-in (must be
 // 0), [op][1] = results flagged for the slow path
 __global__ void k_selftest(long long n, unsigned long long seed, int mode,
                            unsigned long long* counters)
 {
-  unsigned long long wrong[4] = { 0, 0, 0, 0 }, slow[4] = { 0, 0, 0, 0 };
+  unsigned long long wrong[5] = { 0, 0, 0, 0, 0 }, slow[5] = { 0, 0, 0, 0, 0 };
   for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < n;
        t += (long long) gridDim.x * blockDim.x) {
     const unsigned long long h0 = mix64(seed + 3ULL * (unsigned long long) t);
@@ -65,11 +66,14 @@ __global__ void k_selftest(long long n, unsigned long long seed, int mode,
       if (op.bad) slow[1]++; else if (!same_bits(q, 1.0 / b)) wrong[1]++; }
     { FastOps op; const double q = op.sqrt(a);
       if (op.bad) slow[2]++; else if (!same_bits(q, ::sqrt(a))) wrong[2]++; }
-    { FastOps op; double q1, q2; op.div2(a, c, b, q1, q2);
+    { FastOps op; const double r = op.prep(b);
+      const double q1 = op.quotz(a, b, r), q2 = op.quot(c, b, r);
       if (op.bad) slow[3]++;
       else if (!same_bits(q1, a / b) || !same_bits(q2, c / b)) wrong[3]++; }
+    { FastOps op; const double q = op.divz(a, b);
+      if (op.bad) slow[4]++; else if (!same_bits(q, a / b)) wrong[4]++; }
   }
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 5; i++) {
     if (wrong[i]) atomicAdd(counters + 2 * i, wrong[i]);
     if (slow[i]) atomicAdd(counters + 2 * i + 1, slow[i]);
   }
@@ -84,13 +88,13 @@ extern "C" int vlct_selftest_fpops(long long n, unsigned long long seed, int mod
   if (n <= 0 || counters_out == nullptr || mode < 0 || mode > 2)
     return VLCT_ERR_INVALID_CONFIG;
   unsigned long long* d = nullptr;
-  if (cudaMalloc(&d, 8 * sizeof(unsigned long long)) != cudaSuccess) return VLCT_ERR_CUDA;
-  cudaMemset(d, 0, 8 * sizeof(unsigned long long));
+  if (cudaMalloc(&d, 10 * sizeof(unsigned long long)) != cudaSuccess) return VLCT_ERR_CUDA;
+  cudaMemset(d, 0, 10 * sizeof(unsigned long long));
   vlct::k_selftest<<<148 * 8, 256>>>(n, seed, mode, d);
-  unsigned long long h[8];
+  unsigned long long h[10];
   const cudaError_t err = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (err != cudaSuccess) return VLCT_ERR_CUDA;
-  for (int i = 0; i < 8; i++) counters_out[i] = (long long) h[i];
+  for (int i = 0; i < 10; i++) counters_out[i] = (long long) h[i];
   return VLCT_OK;
 }

@@ -206,7 +206,8 @@ int vlct_profile_get(vlct_handle *h, int index, char *name, int name_len,
  * root used by the flux kernels (csrc/vlct_fpops.cuh): evaluates n operand
  * tuples generated from `seed` (mode 0: solver-like magnitudes, 1: arbitrary
  * bit patterns, 2: specials) and compares with the built-in IEEE operators.
- * counters_out[8] = for op in (div, rcp, sqrt, div2): { results that passed
+ * counters_out[10] = for op in (div, rcp, sqrt, shared-reciprocal pair,
+ * divz = division with zero-numerator select): { results that passed
  * the range guard but differ from the built-in (must be 0), results flagged
  * for re-evaluation with the built-in }. No reference counterpart: the
  * reference's arithmetic is the compiler's (value-safe, OPTIMIZE_FP=OFF,

@@ -34,6 +34,8 @@ for l in lines[start:end]:
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
     if m:
         instr.append((int(m.group(1), 16), m.group(3), cur))
+if len(data) % len(instr) == 0:
+    data = data[:len(instr)]   # ncu repeats the table once per view
 assert len(instr) == len(data), (len(instr), len(data))
 per = collections.Counter()
 perop = collections.defaultdict(collections.Counter)
