@@ -175,13 +175,17 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   constexpr int NV = NVars<MHD>::n;
   constexpr bool PLM = (RECON != RECON_NN);
   constexpr int H = PLM ? 1 : 0;          // cells needed left of the first face
-  // strip position p <-> cell f0 - H + p; PLM needs cells f0-1 .. f0+33
+  // Faces per warp. With PLM the 32 lanes own 32 cells (one limited slope
+  // each) and solve the 31 faces between them: a 32nd face would need a 33rd
+  // slope, evaluated by one lane while 31 wait (+20 % instructions).
+  constexpr int FPW = PLM ? 31 : 32;
+  // strip position p <-> cell f0 - H + p; PLM needs cells f0-1 .. f0+32
   __shared__ double sW[kXWarps][NV][36];
-  __shared__ double sD[kXWarps][PLM ? NV : 1][PLM ? 34 : 1];
+  __shared__ double sD[kXWarps][PLM ? NV : 1][PLM ? 32 : 1];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nfx = box.hi[0] - box.lo[0];
-  const int wpr = (nfx + 31) >> 5;        // warps per row
+  const int wpr = (nfx + FPW - 1) / FPW;  // warps per row
   const int nyb = box.hi[1] - box.lo[1], nzb = box.hi[2] - box.lo[2];
   // (32-bit index arithmetic: the launcher checks that the counts fit)
   const unsigned nrows = (unsigned) nyb * (unsigned) nzb;
@@ -192,16 +196,15 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   const int seg = (int) (gw % (unsigned) wpr);
   const unsigned row0 = (gw / (unsigned) wpr) * kXRows;
   const unsigned row1 = (row0 + kXRows < nrows) ? row0 + kXRows : nrows;
-  const int f0 = box.lo[0] + seg * 32;
-  const int nf = min(32, box.hi[0] - f0);
+  const int f0 = box.lo[0] + seg * FPW;
+  const int nf = min(FPW, box.hi[0] - f0);
   const int i = f0 + lane;                // own cell = left cell of own face
 
-  // the cells beyond the warp's 32: three lanes fetch one extra cell each
+  // the cells beyond the warp's 32: one or two lanes fetch an extra cell each
   int ecell = -1, epos = 0;
   if (PLM) {
     if (lane == 0)      { ecell = f0 - 1;  epos = 0; }
     else if (lane == 1) { ecell = f0 + 32; epos = 33; }
-    else if (lane == 2) { ecell = f0 + 33; epos = 34; }
   } else if (lane == 0) { ecell = f0 + 32; epos = 32; }
   if (ecell >= G.mx) ecell = -1;
 
@@ -242,17 +245,11 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
         dv[v] = limited_slope<RECON>(sW[w][v][lane], W[v], sW[w][v][lane + 2], P.theta);
         sD[w][v][lane] = dv[v];
       }
-      if (lane == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; v++)
-          sD[w][v][32] = limited_slope<RECON>(sW[w][v][32], sW[w][v][33],
-                                              sW[w][v][34], P.theta);
-      }
       __syncwarp();
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         wl[v] = W[v] + dv[v] * 0.5;
-        wr[v] = sW[w][v][lane + 2] - sD[w][v][lane + 1] * 0.5;
+        wr[v] = sW[w][v][lane + 2] - sD[w][v][(lane + 1) & 31] * 0.5;
       }
       apply_floors<MHD>(P, wl);
       apply_floors<MHD>(P, wr);
@@ -371,7 +368,8 @@ void flux_go(const FluxLaunch& L)
 {
   const Box& b = L.box;
   if constexpr (DIM == 0) {
-    const long long wpr = (b.hi[0] - b.lo[0] + 31) / 32;
+    constexpr int fpw = (RECON != RECON_NN) ? 31 : 32;   // k_flux_x: FPW
+    const long long wpr = (b.hi[0] - b.lo[0] + fpw - 1) / fpw;
     const long long rows = (long long) (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
     const long long warps = wpr * ((rows + kXRows - 1) / kXRows);
     const unsigned grid = (unsigned) ((warps + kXWarps - 1) / kXWarps);
