@@ -31,6 +31,7 @@ struct vlct_handle {
   std::vector<void*> allocations;
   long long scratch_bytes = 0;
   unsigned long long* d_dt_bits = nullptr;
+  double* d_step = nullptr;   // per-stage dt/dx, dt/dy, dt/dz, dt (k_step_params)
   unsigned long long* h_dt_bits = nullptr;   // pinned
   // device mirror of a HOST block (mem_space == VLCT_MEM_HOST)
   bool have_mirror = false;
@@ -287,7 +288,7 @@ int immediate_staling(int recon) { return recon == VLCT_RECON_NN ? 0 : 1; }
 
 /// the stage loop of EnzoMethodMHDVlct::compute on device pointers
 int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
-                      double dt, cudaStream_t st)
+                      double dt, const double* dt_dev, cudaStream_t st)
 {
   const Params& P = h->P;
   const State ext = state_of(h, b);
@@ -297,10 +298,14 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
   const double* accel[3] = { b->acceleration_x, b->acceleration_y,
                              b->acceleration_z };
   const int nstages = (h->cfg.time_scheme == VLCT_TIME_EULER) ? 1 : 2;
+  // dt may live on the device (vlct_compute_dev): the stage constants are
+  // formed there, so a step never has to wait for the host
+  launch_step_params(LaunchCtx{ st, &h->launches, &h->prof }, dt_dev, dt, nstages,
+                     width, h->d_step);
   int stale = 0;
   for (int stage = 0; stage < nstages; stage++) {
     const bool final_stage = (stage + 1) == nstages;
-    const double cur_dt = (!final_stage) ? dt / 2. : dt;
+    const double* step_params = h->d_step + 4 * stage;
     const int recon = (nstages == 2 && stage == 0) ? VLCT_RECON_NN
                                                    : h->cfg.reconstruct_method;
     const State& cur = (stage == 0) ? ext : h->S.temp;
@@ -314,13 +319,13 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     for (int dim = 0; dim < 3; dim++)
       launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs);
     if (P.mhd)
-      launch_ct(ctx, P, G, cur, h->S, bi, bi_out, cur_dt, width, cs);
+      launch_ct(ctx, P, G, cur, h->S, bi, bi_out, step_params, cs);
     // gravity: full step only, i.e. stage index 1
     // (EnzoMHDIntegratorStageCommands.cpp:181,279)
     const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
                          accel[0] != nullptr;
     launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
-                  cur_dt, width, cs);
+                  step_params, cs);
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -377,6 +382,7 @@ int vlct_create(const vlct_config* cfg, vlct_handle** out)
 
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaMalloc((void**) &h->d_dt_bits, sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMalloc((void**) &h->d_step, 8 * sizeof(double)));
   CUDA_TRY(h, cudaMallocHost((void**) &h->h_dt_bits, sizeof(unsigned long long)));
   return VLCT_OK;
 }
@@ -390,13 +396,17 @@ void vlct_destroy(vlct_handle* h)
     for (void* p : h->allocations) cudaFree(p);
     for (void* p : h->mirror_allocs) cudaFree(p);
     if (h->d_dt_bits) cudaFree(h->d_dt_bits);
+    if (h->d_step) cudaFree(h->d_step);
     if (h->h_dt_bits) cudaFreeHost(h->h_dt_bits);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
   }
   delete h;
 }
 
-int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
+}  // extern "C"
+
+namespace {
+int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* dt_dev)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
@@ -414,15 +424,62 @@ int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
   }
   if (b->mem_space == VLCT_MEM_DEVICE) {
     cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
-    return compute_on_device(h, b, G, dt, st);
+    return compute_on_device(h, b, G, dt, dt_dev, st);
   }
+  if (dt_dev != nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_compute_dev needs a block in device memory");
   // HOST: stage through the device mirror; synchronous
   cudaStream_t st = h->own_stream;
   if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
   if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
-  if ((rc = compute_on_device(h, &h->mirror, G, dt, st)) != VLCT_OK) return rc;
+  if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
   if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  return VLCT_OK;
+}
+
+/// launches DE sync + pressure + CFL minimum on the block's stream
+int timestep_launch(vlct_handle* h, const vlct_block* db, const Geom& G,
+                    cudaStream_t st)
+{
+  const double width[3] = { db->dx, db->dy, db->dz };
+  const State u = state_of(h, db);
+  launch_timestep(LaunchCtx{ st, &h->launches, &h->prof }, h->P, G, u, db->pressure, width, h->d_dt_bits);
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
+{ return compute_entry(h, b, dt, nullptr); }
+
+int vlct_compute_dev(vlct_handle* h, const vlct_block* b, const double* dt_device)
+{
+  if (h != nullptr && dt_device == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device is NULL");
+  return compute_entry(h, b, 0.0, dt_device);
+}
+
+int vlct_timestep_dev(vlct_handle* h, const vlct_block* b, double* dt_device)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  if (dt_device == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device is NULL");
+  int rc = check_block(h, b, true);
+  if (rc != VLCT_OK) return rc;
+  if (b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_timestep_dev needs a block in device memory");
+  const Geom G = geom_of(b);
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  if ((rc = timestep_launch(h, b, G, st)) != VLCT_OK) return rc;
+  // "Multiply resulting dt by CourantSafetyNumber" (cpp:585-587), on the device
+  launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+                   h->cfg.courant, dt_device);
+  CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
 }
 
@@ -434,7 +491,6 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   int rc = check_block(h, b, true);
   if (rc != VLCT_OK) return rc;
   const Geom G = geom_of(b);
-  const double width[3] = { b->dx, b->dy, b->dz };
   cudaStream_t st;
   const vlct_block* db = b;
   if (b->mem_space == VLCT_MEM_DEVICE) {
@@ -445,9 +501,7 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
     if ((rc = mirror_copy(h, b, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
     db = &h->mirror;
   }
-  const State u = state_of(h, db);
-  launch_timestep(LaunchCtx{ st, &h->launches, &h->prof }, h->P, G, u, db->pressure, width, h->d_dt_bits);
-  CUDA_TRY(h, cudaGetLastError());
+  if ((rc = timestep_launch(h, db, G, st)) != VLCT_OK) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
   if (b->mem_space == VLCT_MEM_HOST) {

@@ -137,7 +137,7 @@ struct FaceArgs {
   const double* edge[3];
   const double* bi0[3];
   double* bi_out[3];
-  double dtd[3];            // dt / width along x,y,z
+  const double* sp;         // step parameters of the stage: dt/dx, dt/dy, dt/dz, dt
   Box box[3];
 };
 
@@ -154,8 +154,8 @@ __device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
   const size_t e = cidx(G, k - (D == 2), j - (D == 1), i - (D == 0));
   const double ek_Rj = __ldg(A.edge[KD] + e), ek_Lj = __ldg(A.edge[KD] + e - st[JD]);
   const double ej_Rk = __ldg(A.edge[JD] + e), ej_Lk = __ldg(A.edge[JD] + e - st[KD]);
-  const double E_k_term = A.dtd[JD] * (ek_Rj - ek_Lj);
-  const double E_j_term = A.dtd[KD] * (ej_Rk - ej_Lk);
+  const double E_k_term = __ldg(A.sp + JD) * (ek_Rj - ek_Lj);
+  const double E_j_term = __ldg(A.sp + KD) * (ej_Rk - ej_Lk);
   const size_t f = fidx(G, D, k, j, i);
   A.bi_out[D][f] = __ldg(A.bi0[D] + f) - E_k_term + E_j_term;
 }
@@ -182,8 +182,7 @@ struct UpdateArgs {
   const double* cur_rho;     // density / internal energy of the stage's input
   const double* cur_eint;    // state (dual-energy source term only)
   const double* accel[3];
-  double dtd[3];
-  double dt;
+  const double* sp;          // dt/dx, dt/dy, dt/dz, dt of the stage
   int gravity;
   Box inner;                 // [s+1, m-s-1)^3: conserved update + floors
 };
@@ -248,6 +247,7 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
   if (i < in.lo[0] || i >= in.hi[0] || j < in.lo[1] || j >= in.hi[1] ||
       k < in.lo[2] || k >= in.hi[2]) return;
 
+  const double dtd[3] = { __ldg(A.sp), __ldg(A.sp + 1), __ldg(A.sp + 2) };
   // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
   double d_rho = 0., d_mx = 0., d_my = 0., d_mz = 0., d_e = 0., d_eint = 0.;
   double p_floored = 0.;
@@ -261,7 +261,7 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
   for (int d = 0; d < 3; d++) {
     const FluxSet& F = A.flux[d];
     const size_t l = c - st[d];
-    const double dtdx = A.dtd[d];
+    const double dtdx = dtd[d];
     d_rho -= dtdx * (__ldg(F.rho + c) - __ldg(F.rho + l));
     d_mx -= dtdx * (__ldg(F.mx_ + c) - __ldg(F.mx_ + l));
     d_my -= dtdx * (__ldg(F.my_ + c) - __ldg(F.my_ + l));
@@ -279,7 +279,7 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
   if (A.gravity) {
     const double ax = __ldg(A.accel[0] + c), ay = __ldg(A.accel[1] + c),
                  az = __ldg(A.accel[2] + c);
-    const double dt = A.dt;
+    const double dt = __ldg(A.sp + 3);
     d_mx += dt * old_rho * ax;
     d_my += dt * old_rho * ay;
     d_mz += dt * old_rho * az;
@@ -292,7 +292,7 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       const double* Fs = A.flux[d].sc[s];
-      d_s -= A.dtd[d] * (__ldg(Fs + c) - __ldg(Fs + c - st[d]));
+      d_s -= dtd[d] * (__ldg(Fs + c) - __ldg(Fs + c - st[d]));
     }
     A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
   }
@@ -382,6 +382,28 @@ k_timestep(const Params P, const Geom G, const State u, double* pressure,
 }
 
 __global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+
+/// dt_out = courant * (minimum found by k_timestep); cpp:585-587
+__global__ void k_finish_dt(const unsigned long long* bits, double courant,
+                            double* dt_out)
+{ *dt_out = __longlong_as_double((long long) *bits) * courant; }
+
+/// Per-stage constants of one step, from a dt that lives on the host or on the
+/// device: out[4*stage + {0,1,2,3}] = dt_stage/dx, /dy, /dz, dt_stage, where
+/// dt_stage = dt/2 for the predictor of the two-stage scheme
+/// (EnzoMethodMHDVlct.cpp:462-464) and dt otherwise.
+__global__ void k_step_params(const double* dt_dev, double dt_host, int nstages,
+                              double wx, double wy, double wz, double* out)
+{
+  const double dt = dt_dev ? *dt_dev : dt_host;
+  for (int stage = 0; stage < nstages; stage++) {
+    const double cur = (stage + 1 < nstages) ? dt / 2. : dt;
+    out[4 * stage + 0] = cur / wx;
+    out[4 * stage + 1] = cur / wy;
+    out[4 * stage + 2] = cur / wz;
+    out[4 * stage + 3] = cur;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // ghost-zone helpers (stand-ins for the refresh phase on a unigrid)
@@ -492,7 +514,7 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
 
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, double dt, const double* width, int s)
+               const FaceB& bi_out, const double* step_params, int s)
 {
   cudaStream_t st = ctx.st;
   const int m[3] = { G.mx, G.my, G.mz };
@@ -520,11 +542,11 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
   }
   {
     FaceArgs A;
+    A.sp = step_params;
     for (int d = 0; d < 3; d++) {
       A.edge[d] = S.edge[d];
       A.bi0[d] = bi0.bi[d];
       A.bi_out[d] = bi_out.bi[d];
-      A.dtd[d] = dt / width[d];
       // CT.cpp:646-667: interior faces along d, inner cells along j,k
       for (int a = 0; a < 3; a++) {
         A.box[d].lo[a] = s + 1;
@@ -543,8 +565,8 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
-                   const double* accel[3], bool gravity, double dt,
-                   const double* width, int s)
+                   const double* accel[3], bool gravity,
+                   const double* step_params, int s)
 {
   cudaStream_t st = ctx.st;
   UpdateArgs A;
@@ -553,11 +575,10 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
     A.flux[d] = S.flux[d];
     A.bi_out[d] = bi_out.bi[d];
     A.accel[d] = gravity ? accel[d] : nullptr;
-    A.dtd[d] = dt / width[d];
   }
   A.cur_rho = cur.rho;
   A.cur_eint = cur.eint;
-  A.dt = dt;
+  A.sp = step_params;
   A.gravity = gravity ? 1 : 0;
   A.inner = full_box(G, s + 1);
   // with CT the centred B is rewritten on the whole [s, m-s)^3 region
@@ -593,6 +614,21 @@ void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
     if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
     else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
   }
+}
+
+void launch_finish_dt(const LaunchCtx& ctx, const unsigned long long* bits,
+                      double courant, double* dt_out)
+{
+  ScopedLaunch sl(ctx, "k_finish_dt");
+  k_finish_dt<<<1, 1, 0, ctx.st>>>(bits, courant, dt_out);
+}
+
+void launch_step_params(const LaunchCtx& ctx, const double* dt_dev, double dt_host,
+                        int nstages, const double* width, double* out)
+{
+  ScopedLaunch sl(ctx, "k_step_params");
+  k_step_params<<<1, 1, 0, ctx.st>>>(dt_dev, dt_host, nstages, width[0], width[1],
+                                     width[2], out);
 }
 
 void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,

@@ -92,16 +92,25 @@ void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
                  const FaceB& bi_cur, int cur_stale);
 
 /// constrained transport: edge E, face-B update
+/// (step_params: dt/dx, dt/dy, dt/dz, dt of the stage, in device memory)
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, double dt, const double* width, int stale);
+               const FaceB& bi_out, const double* step_params, int stale);
 
 /// centred B + flux divergence + sources + conserved update + floors/sync
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
-                   const double* accel[3], bool gravity, double dt,
-                   const double* width, int stale);
+                   const double* accel[3], bool gravity,
+                   const double* step_params, int stale);
+
+/// the per-stage constants of a step from a host or device dt (see k_step_params)
+void launch_step_params(const LaunchCtx& ctx, const double* dt_dev, double dt_host,
+                        int nstages, const double* width, double* out);
+
+/// *dt_out = courant * minimum of k_timestep, on the device
+void launch_finish_dt(const LaunchCtx& ctx, const unsigned long long* bits,
+                      double courant, double* dt_out);
 
 /// DE sync + pressure field + CFL minimum over all cells; *dt_bits receives
 /// the bit pattern of the minimum local dt (not yet multiplied by courant)

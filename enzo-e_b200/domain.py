@@ -109,6 +109,12 @@ class Domain:
             unpack(block, axis, 1, recv_hi)
 
     def global_dt(self, dt, device=None):
+        if hasattr(dt, "data_ptr"):
+            # device-resident dt (Method.timestep_dev): reduce in place on the
+            # stream, nothing comes back to the host
+            if self.world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MIN)
+            return dt
         if self.world == 1:
             return dt
         t = torch.tensor([dt], dtype=torch.float64,

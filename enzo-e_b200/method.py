@@ -143,11 +143,31 @@ class EnzoMethodMHDVlct:
         return self._lib.vlct_name().decode()
 
     def compute(self, block, dt=None):
-        """EnzoMethodMHDVlct::compute(Block*): advance by block.dt in place."""
+        """EnzoMethodMHDVlct::compute(Block*): advance by block.dt in place.
+
+        dt may be a one-element fp64 CUDA tensor (see timestep_dev): the step
+        then reads it on the device and nothing waits for the host."""
         dt = block.dt if dt is None else dt
-        self._check(self._lib.vlct_compute(self._h, C.byref(block.c_block),
-                                           float(dt)))
+        if hasattr(dt, "data_ptr"):
+            self._check(self._lib.vlct_compute_dev(
+                self._h, C.byref(block.c_block),
+                C.cast(dt.data_ptr(), C.POINTER(C.c_double))))
+        else:
+            self._check(self._lib.vlct_compute(self._h, C.byref(block.c_block),
+                                               float(dt)))
         block.compute_done()
+
+    def timestep_dev(self, block, out=None):
+        """timestep() without the host round trip: returns a one-element fp64
+        CUDA tensor holding courant * min(...), filled asynchronously."""
+        import torch
+        if out is None:
+            dev = next(iter(block.fields.values())).device
+            out = torch.empty(1, dtype=torch.float64, device=dev)
+        self._check(self._lib.vlct_timestep_dev(
+            self._h, C.byref(block.c_block),
+            C.cast(out.data_ptr(), C.POINTER(C.c_double))))
+        return out
 
     def timestep(self, block):
         """EnzoMethodMHDVlct::timestep(Block*) (already times courant)."""

@@ -172,6 +172,18 @@ int vlct_compute(vlct_handle *h, const vlct_block *block, double dt);
  * EnzoMHDIntegratorStageCommands.cpp:299-366) of dx_i/(|v_i| + c_signal). */
 int vlct_timestep(vlct_handle *h, const vlct_block *block, double *dt_out);
 
+/* The same two entry points with the timestep kept in DEVICE memory, for
+ * drivers whose fields are device-resident (VLCT_MEM_DEVICE blocks only):
+ * vlct_timestep_dev writes courant * min(...) to *dt_device without waiting for
+ * the host, vlct_compute_dev reads the step's dt from *dt_device (after, e.g.,
+ * an NCCL min-all-reduce over blocks -- the stand-in for the reduction of
+ * src/Cello/control_stopping.cpp:96-142). Both are asynchronous on
+ * block->stream, so consecutive cycles queue back to back. Results are
+ * bit-identical to vlct_timestep / vlct_compute. */
+int vlct_timestep_dev(vlct_handle *h, const vlct_block *block, double *dt_device);
+int vlct_compute_dev(vlct_handle *h, const vlct_block *block,
+                     const double *dt_device);
+
 /* Message of the last failure on this handle (never NULL). */
 const char *vlct_last_error(const vlct_handle *h);
 const char *vlct_status_string(int status);

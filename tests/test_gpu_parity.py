@@ -82,6 +82,33 @@ def test_three_steps_bit_exact(name, device_resident):
     assert not bad, f"fields differ from the oracle: {bad}"
 
 
+@pytest.mark.parametrize("name", ["mhd_hlld_plm", "hd_hllc_plm_de_scalars",
+                                  "mhd_hlld_gravity_de_eta0"])
+def test_device_resident_timestep_is_bit_exact(name):
+    """vlct_timestep_dev + vlct_compute_dev (dt never leaves the device) give
+    the same bits as the host-dt entry points and the oracle."""
+    import torch
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**CASES[name])
+    n, g, d = (20, 12, 10), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=3)
+    want, dts_want = run_cpu(cfg, host, n, g, d, 3)
+    dev = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+    method = EnzoMethodMHDVlct(config=cfg)
+    block = Block(dev, n, g, d, passive=passive_names(cfg))
+    dts = []
+    for _ in range(3):
+        dt = method.timestep_dev(block)
+        method.compute(block, dt)
+        dts.append(dt)           # read back only after all steps are queued
+    method.synchronize()
+    torch.cuda.synchronize()
+    assert [float(t.item()) for t in dts] == dts_want
+    got = {k: v.cpu().numpy() for k, v in dev.items()}
+    method.close()
+    assert all(bit_equal(want, got).values())
+
+
 def test_larger_ghost_depth_and_odd_shape():
     cfg = make_config(riemann="hlld", recon="plm", mhd=True)
     n, g, d = (17, 9, 7), (4, 4, 4), (0.1, 0.1, 0.1)
