@@ -26,6 +26,13 @@ struct vlct_handle {
   Params P;
   int device = -1;
   cudaStream_t own_stream = nullptr;
+  // HOST blocks: H2D / D2H streams of the staging pipeline, event pool
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+  // options (vlct_set_option)
+  long long host_pipeline_levels = -1;   // -1 auto, 0 off, n > 0: n z levels per pass
+  long long device_pipeline_levels = 0;  // test hook: run DEVICE steps in passes too
   Geom G{0, 0, 0};
   Scratch S;
   std::vector<void*> allocations;
@@ -254,41 +261,111 @@ bool in_copy_set(const vlct_handle* h, double* vlct_block::*m, CopySet set)
   return true;
 }
 
-/// copy a set of fields between the host block and its device mirror
+/// copy the z levels [z0, z1) of a set of fields between the host block and
+/// its device mirror (z is the slowest axis: a range of levels is contiguous).
+/// z1 >= mz means "to the end", which for bfieldi_z includes its extra level.
 int mirror_copy(vlct_handle* h, const vlct_block* host, const Geom& G,
-                cudaStream_t st, bool to_device, CopySet set)
+                cudaStream_t st, bool to_device, CopySet set,
+                int z0 = 0, int z1 = 1 << 30)
 {
+  if (z0 < 0) z0 = 0;
+  auto copy = [&](double* hp, double* dp, int face) -> int {
+    const size_t plane = (size_t) (G.mx + (face == 0)) * (size_t) (G.my + (face == 1));
+    const int levels = G.mz + (face == 2);
+    const int hi = (z1 >= G.mz) ? levels : z1;
+    if (hi <= z0) return VLCT_OK;
+    const size_t off = plane * (size_t) z0;
+    const size_t bytes = plane * (size_t) (hi - z0) * sizeof(double);
+    CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) (dp + off) : (void*) (hp + off),
+                                to_device ? (void*) (hp + off) : (void*) (dp + off),
+                                bytes, to_device ? cudaMemcpyHostToDevice
+                                                 : cudaMemcpyDeviceToHost, st));
+    h->copied_bytes[to_device ? 0 : 1] += (long long) bytes;
+    return VLCT_OK;
+  };
+  int rc;
   for (int f = 0; f < kNumFields; f++) {
     double* hp = host->*(kFields[f].member);
     double* dp = h->mirror.*(kFields[f].member);
     if (hp == nullptr || dp == nullptr) continue;
     if (!in_copy_set(h, kFields[f].member, set)) continue;
-    const size_t bytes = field_count(G, kFields[f].face) * sizeof(double);
-    CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) dp : (void*) hp,
-                                to_device ? (void*) hp : (void*) dp, bytes,
-                                to_device ? cudaMemcpyHostToDevice
-                                          : cudaMemcpyDeviceToHost, st));
-    h->copied_bytes[to_device ? 0 : 1] += (long long) bytes;
+    if ((rc = copy(hp, dp, kFields[f].face)) != VLCT_OK) return rc;
   }
-  for (int s = 0; s < h->P.nsc; s++) {
-    const size_t bytes = G.cells() * sizeof(double);
-    double* hp = host->passive[s];
-    double* dp = h->mirror.passive[s];
-    CUDA_TRY(h, cudaMemcpyAsync(to_device ? (void*) dp : (void*) hp,
-                                to_device ? (void*) hp : (void*) dp, bytes,
-                                to_device ? cudaMemcpyHostToDevice
-                                          : cudaMemcpyDeviceToHost, st));
-    h->copied_bytes[to_device ? 0 : 1] += (long long) bytes;
+  for (int s = 0; s < h->P.nsc; s++)
+    if ((rc = copy(host->passive[s], h->mirror.passive[s], -1)) != VLCT_OK) return rc;
+  return VLCT_OK;
+}
+
+/// an event from the handle's pool (no timing), recorded on st
+int record_event(vlct_handle* h, cudaStream_t st, cudaEvent_t* out)
+{
+  if (h->events_used == h->events.size()) {
+    cudaEvent_t e;
+    CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->events.push_back(e);
   }
+  *out = h->events[h->events_used++];
+  CUDA_TRY(h, cudaEventRecord(*out, st));
   return VLCT_OK;
 }
 
 int total_staling(int recon) { return recon == VLCT_RECON_NN ? 1 : 2; }
 int immediate_staling(int recon) { return recon == VLCT_RECON_NN ? 0 : 1; }
 
-/// the stage loop of EnzoMethodMHDVlct::compute on device pointers
+// ---- z-skewed partial execution of a step -------------------------------------
+// A step may be executed in several passes, each restricted to a range of z
+// levels. Every kernel of the step is a pure function of its inputs at a given
+// index, so the passes give bit-identical results as long as (i) each kernel's
+// index box is tiled exactly once by the passes and (ii) a kernel only runs
+// where everything it reads has already been produced. (ii) is what the lags
+// below encode. With k the z index of a kernel (cells; faces for the z sweep
+// and for the z component of the face-B update), the reads are
+//   SCAL(k)    <- stage input k
+//   FLUX_XY(k) <- stage input k, SCAL k, face B k
+//   FLUX_Z(f)  <- stage input / SCAL f-1..f+2 (PLM; f..f+1 with NN), z-face f+1
+//   EDGE(k)    <- FLUX_XY k..k+1, FLUX_Z k, stage input k..k+1
+//   FACE(k)    <- EDGE k-1..k
+//   UPDATE(k)  <- FLUX_XY k, FLUX_Z k-1..k, FACE k..k+1
+// and the second stage's input is the first stage's UPDATE / FACE output.
+//   an END cut at z   : the pass covers indices below  z + kEndLag[stage][kernel]
+//   a START cut at z  : the pass covers indices from   z - kStartLag[stage][kernel]
+// Upstream kernels have the larger lag in both tables, so a pass never needs
+// anything outside itself and the passes before it. The stage-1 rows carry
+// one level of slack beyond the data dependence: flux / edge scratch arrays
+// are shared by the two stages, and the slack keeps a later pass's stage-1
+// reads clear of what the earlier pass's stage 2 has overwritten. The fields
+// themselves are updated in place by the last stage only below / above
+// everything the first stage of a later pass still reads.
+enum KernelId { K_SCAL = 0, K_FLUX_XY, K_FLUX_Z, K_EDGE, K_FACE, K_UPDATE, K_COUNT };
+enum { CUT_NONE = 0, CUT_END = 1, CUT_START = 2 };
+struct ZCut { int kind; int z; };
+
+//                                   SCAL XY  Z  EDGE FACE UPDATE
+const int kEndLag[2][K_COUNT]   = { { 6,  6,  5,  5,  5,  4 },     // first of two stages
+                                    { 3,  2,  1,  1,  1,  0 } };   // last stage
+const int kStartLag[2][K_COUNT] = { { 4,  4,  4,  4,  3,  3 },
+                                    { 2,  1,  1,  1,  0,  0 } };
+/// input levels a pass needs beyond an END cut / before a START cut
+constexpr int kEndReach = 6, kStartReach = 4;
+
+int cut_index(const ZCut& c, int row, KernelId id)
+{ return (c.kind == CUT_END) ? c.z + kEndLag[row][id] : c.z - kStartLag[row][id]; }
+
+/// the clip of one kernel of one stage for the pass (lo, hi]
+ZClip pass_clip(const ZCut& lo, const ZCut& hi, int row, KernelId id)
+{
+  ZClip z = kNoClip;
+  if (lo.kind != CUT_NONE) z.lo = cut_index(lo, row, id);
+  if (hi.kind != CUT_NONE) z.hi = cut_index(hi, row, id);
+  return z;
+}
+
+/// the stage loop of EnzoMethodMHDVlct::compute on device pointers, restricted
+/// to the pass between two cuts (CUT_NONE on both sides = the whole block)
 int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
-                      double dt, const double* dt_dev, cudaStream_t st)
+                      double dt, const double* dt_dev, cudaStream_t st,
+                      ZCut zlo = ZCut{ CUT_NONE, 0 }, ZCut zhi = ZCut{ CUT_NONE, 0 },
+                      bool set_step_params = true)
 {
   const Params& P = h->P;
   const State ext = state_of(h, b);
@@ -300,8 +377,9 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
   const int nstages = (h->cfg.time_scheme == VLCT_TIME_EULER) ? 1 : 2;
   // dt may live on the device (vlct_compute_dev): the stage constants are
   // formed there, so a step never has to wait for the host
-  launch_step_params(LaunchCtx{ st, &h->launches, &h->prof }, dt_dev, dt, nstages,
-                     width, h->d_step);
+  if (set_step_params)
+    launch_step_params(LaunchCtx{ st, &h->launches, &h->prof }, dt_dev, dt, nstages,
+                       width, h->d_step);
   int stale = 0;
   for (int stage = 0; stage < nstages; stage++) {
     const bool final_stage = (stage + 1) == nstages;
@@ -314,18 +392,21 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     const FaceB& bi_out = (stage == 1 || nstages == 1) ? bi : h->S.tbi;
 
     const LaunchCtx ctx{ st, &h->launches, &h->prof };
-    launch_primitives(ctx, P, G, cur, h->S, stale);
+    const int row = final_stage ? 1 : 0;
+    launch_primitives(ctx, P, G, cur, h->S, stale, pass_clip(zlo, zhi, row, K_SCAL));
     const int cs = stale + immediate_staling(recon);
     for (int dim = 0; dim < 3; dim++)
-      launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs);
+      launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs,
+                  pass_clip(zlo, zhi, row, dim == 2 ? K_FLUX_Z : K_FLUX_XY));
     if (P.mhd)
-      launch_ct(ctx, P, G, cur, h->S, bi, bi_out, step_params, cs);
+      launch_ct(ctx, P, G, cur, h->S, bi, bi_out, step_params, cs,
+                pass_clip(zlo, zhi, row, K_EDGE), pass_clip(zlo, zhi, row, K_FACE));
     // gravity: full step only, i.e. stage index 1
     // (EnzoMHDIntegratorStageCommands.cpp:181,279)
     const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
                          accel[0] != nullptr;
     launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
-                  step_params, cs);
+                  step_params, cs, pass_clip(zlo, zhi, row, K_UPDATE));
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -381,6 +462,8 @@ int vlct_create(const vlct_config* cfg, vlct_handle** out)
   P.recon = cfg->reconstruct_method;
 
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaMalloc((void**) &h->d_dt_bits, sizeof(unsigned long long)));
   CUDA_TRY(h, cudaMalloc((void**) &h->d_step, 8 * sizeof(double)));
   CUDA_TRY(h, cudaMallocHost((void**) &h->h_dt_bits, sizeof(unsigned long long)));
@@ -398,6 +481,9 @@ void vlct_destroy(vlct_handle* h)
     if (h->d_dt_bits) cudaFree(h->d_dt_bits);
     if (h->d_step) cudaFree(h->d_step);
     if (h->h_dt_bits) cudaFreeHost(h->h_dt_bits);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->in_stream) cudaStreamDestroy(h->in_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
   }
   delete h;
@@ -406,6 +492,72 @@ void vlct_destroy(vlct_handle* h)
 }  // extern "C"
 
 namespace {
+
+/// levels per pass of the HOST staging pipeline (0 = one shot)
+int host_levels(const vlct_handle* h, const Geom& G)
+{
+  if (h->cfg.time_scheme == VLCT_TIME_EULER) return 0;  // single-stage: one pass
+  if (h->host_pipeline_levels == 0) return 0;
+  if (h->host_pipeline_levels > 0) return (int) h->host_pipeline_levels;
+  // auto: ~32 passes, and only when a field is large enough for the copies to
+  // matter (>= 32 MB); small blocks go through in one shot
+  if (G.cells() * sizeof(double) < ((size_t) 32 << 20)) return 0;
+  const int lv = (G.mz + 31) / 32;
+  return lv < 4 ? 4 : lv;
+}
+
+/// A whole step as consecutive z passes separated by END cuts, `levels` input
+/// levels per pass. With a HOST block each pass's input levels are copied to
+/// the device mirror on in_stream while the previous pass computes, and the
+/// levels a pass has finished are copied back on out_stream while the next
+/// one computes, so H2D, kernels and D2H overlap (PCIe is full duplex).
+int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* dev,
+                      const Geom& G, double dt, const double* dt_dev,
+                      cudaStream_t st, int levels)
+{
+  const bool staged = (host != nullptr);
+  int rc;
+  h->events_used = 0;
+  ZCut prev{ CUT_NONE, 0 };
+  int uploaded = 0, downloaded = 0;
+  bool first = true;
+  while (uploaded < G.mz) {
+    const int up_to = (uploaded + levels < G.mz) ? uploaded + levels : G.mz;
+    if (staged) {
+      if ((rc = mirror_copy(h, host, G, h->in_stream, true, COPY_COMPUTE_IN,
+                            uploaded, up_to)) != VLCT_OK) return rc;
+      cudaEvent_t ev;
+      if ((rc = record_event(h, h->in_stream, &ev)) != VLCT_OK) return rc;
+      CUDA_TRY(h, cudaStreamWaitEvent(st, ev, 0));
+    }
+    uploaded = up_to;
+    ZCut cut{ CUT_NONE, 0 };
+    if (uploaded < G.mz) {
+      cut = ZCut{ CUT_END, uploaded - kEndReach };
+      // nothing new below the cut yet: keep uploading
+      if (cut.z <= (prev.kind == CUT_END ? prev.z : 0)) continue;
+    }
+    if ((rc = compute_on_device(h, dev, G, dt, dt_dev, st, prev, cut, first)) != VLCT_OK)
+      return rc;
+    first = false;
+    if (staged) {
+      cudaEvent_t ev;
+      if ((rc = record_event(h, st, &ev)) != VLCT_OK) return rc;
+      CUDA_TRY(h, cudaStreamWaitEvent(h->out_stream, ev, 0));
+      const int done = (cut.kind == CUT_END) ? cut.z : (1 << 30);
+      if ((rc = mirror_copy(h, host, G, h->out_stream, false, COPY_COMPUTE_OUT,
+                            downloaded, done)) != VLCT_OK) return rc;
+      downloaded = done;
+    }
+    prev = cut;
+  }
+  if (staged) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->out_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  return VLCT_OK;
+}
+
 int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* dt_dev)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
@@ -424,6 +576,9 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
   }
   if (b->mem_space == VLCT_MEM_DEVICE) {
     cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+    if (h->device_pipeline_levels > 0 && h->cfg.time_scheme != VLCT_TIME_EULER)
+      return compute_in_passes(h, nullptr, b, G, dt, dt_dev, st,
+                               (int) h->device_pipeline_levels);
     return compute_on_device(h, b, G, dt, dt_dev, st);
   }
   if (dt_dev != nullptr)
@@ -432,6 +587,8 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
   // HOST: stage through the device mirror; synchronous
   cudaStream_t st = h->own_stream;
   if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
+  if (const int levels = host_levels(h, G))
+    return compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels);
   if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
   if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
   if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
@@ -441,12 +598,55 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
 
 /// launches DE sync + pressure + CFL minimum on the block's stream
 int timestep_launch(vlct_handle* h, const vlct_block* db, const Geom& G,
-                    cudaStream_t st)
+                    cudaStream_t st, ZClip zc = kNoClip, bool reset = true)
 {
   const double width[3] = { db->dx, db->dy, db->dz };
   const State u = state_of(h, db);
-  launch_timestep(LaunchCtx{ st, &h->launches, &h->prof }, h->P, G, u, db->pressure, width, h->d_dt_bits);
+  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  if (reset) launch_timestep_reset(ctx, h->d_dt_bits);
+  launch_timestep(ctx, h->P, G, u, db->pressure, width, h->d_dt_bits, zc);
   CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
+/// vlct_timestep of a HOST block as a pipeline over z: H2D of the next levels,
+/// the CFL kernel on the current ones and D2H of what it wrote overlap
+int timestep_host_pipelined(vlct_handle* h, const vlct_block* b, const Geom& G,
+                            cudaStream_t st, int levels)
+{
+  int rc;
+  h->events_used = 0;
+  const vlct_block* db = &h->mirror;
+  const size_t plane = (size_t) G.mx * (size_t) G.my;
+  bool first = true;
+  for (int z0 = 0; z0 < G.mz; z0 += levels) {
+    const int z1 = (z0 + levels < G.mz) ? z0 + levels : G.mz;
+    if ((rc = mirror_copy(h, b, G, h->in_stream, true, COPY_TIMESTEP_IN, z0, z1)) != VLCT_OK)
+      return rc;
+    cudaEvent_t ev;
+    if ((rc = record_event(h, h->in_stream, &ev)) != VLCT_OK) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, ev, 0));
+    if ((rc = timestep_launch(h, db, G, st, ZClip{ z0, z1 }, first)) != VLCT_OK) return rc;
+    first = false;
+    if ((rc = record_event(h, st, &ev)) != VLCT_OK) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->out_stream, ev, 0));
+    const size_t off = plane * (size_t) z0;
+    const size_t bytes = plane * (size_t) (z1 - z0) * sizeof(double);
+    CUDA_TRY(h, cudaMemcpyAsync(b->pressure + off, db->pressure + off, bytes,
+                                cudaMemcpyDeviceToHost, h->out_stream));
+    h->copied_bytes[1] += (long long) bytes;
+    if (h->P.de) {
+      CUDA_TRY(h, cudaMemcpyAsync(b->total_energy + off, db->total_energy + off, bytes,
+                                  cudaMemcpyDeviceToHost, h->out_stream));
+      CUDA_TRY(h, cudaMemcpyAsync(b->internal_energy + off, db->internal_energy + off,
+                                  bytes, cudaMemcpyDeviceToHost, h->out_stream));
+      h->copied_bytes[1] += 2 * (long long) bytes;
+    }
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  CUDA_TRY(h, cudaStreamSynchronize(h->out_stream));
   return VLCT_OK;
 }
 }  // namespace
@@ -498,6 +698,16 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   } else {
     st = h->own_stream;
     if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
+    int levels = host_levels(h, G);
+    if (h->cfg.time_scheme == VLCT_TIME_EULER && h->host_pipeline_levels > 0)
+      levels = (int) h->host_pipeline_levels;   // no stage coupling in timestep
+    if (levels > 0) {
+      if ((rc = timestep_host_pipelined(h, b, G, st, levels)) != VLCT_OK) return rc;
+      double dt_min;
+      memcpy(&dt_min, h->h_dt_bits, sizeof(double));
+      *dt_out = dt_min * h->cfg.courant;
+      return VLCT_OK;
+    }
     if ((rc = mirror_copy(h, b, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
     db = &h->mirror;
   }
@@ -521,6 +731,58 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   // "Multiply resulting dt by CourantSafetyNumber" (cpp:585-587)
   *dt_out = dt_baryons * h->cfg.courant;
   return VLCT_OK;
+}
+
+int vlct_set_option(vlct_handle* h, const char* key, long long value)
+{
+  if (h == nullptr || key == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (strcmp(key, "host_pipeline_levels") == 0) {
+    if (value < -1) return fail(h, VLCT_ERR_INVALID_CONFIG, "host_pipeline_levels >= -1");
+    h->host_pipeline_levels = value;
+  } else if (strcmp(key, "device_pipeline_levels") == 0) {
+    if (value < 0) return fail(h, VLCT_ERR_INVALID_CONFIG, "device_pipeline_levels >= 0");
+    h->device_pipeline_levels = value;
+  } else {
+    return fail(h, VLCT_ERR_UNKNOWN_KEY, "unknown option \"%s\"", key);
+  }
+  return VLCT_OK;
+}
+
+int vlct_compute_dev_part(vlct_handle* h, const vlct_block* b,
+                          const double* dt_device, int part, int z_lo, int z_hi)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  if (dt_device == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device is NULL");
+  int rc = check_block(h, b, false);
+  if (rc != VLCT_OK) return rc;
+  if (b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_compute_dev_part needs a block in device memory");
+  if (h->cfg.time_scheme == VLCT_TIME_EULER)
+    return fail(h, VLCT_ERR_INVALID_CONFIG,
+                "vlct_compute_dev_part supports the two-stage \"vl\" scheme only");
+  const Geom G = geom_of(b);
+  // the interior pass must not read a z ghost level, the other two must not
+  // overlap each other
+  if (z_lo < b->gz + kStartReach || z_hi > G.mz - b->gz - kEndReach || z_hi <= z_lo)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "interior range [%d,%d) must satisfy gz+%d <= z_lo < z_hi <= mz-gz-%d",
+                z_lo, z_hi, kStartReach, kEndReach);
+  if (h->G.mx == 0) {
+    if ((rc = alloc_scratch(h, G)) != VLCT_OK) return rc;
+  } else if (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz) {
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "all blocks handled by one handle must share one shape");
+  }
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  const ZCut none{ CUT_NONE, 0 }, start{ CUT_START, z_lo }, end{ CUT_END, z_hi };
+  switch (part) {
+  case VLCT_PART_INTERIOR: return compute_on_device(h, b, G, 0.0, dt_device, st, start, end, true);
+  case VLCT_PART_LOWER:    return compute_on_device(h, b, G, 0.0, dt_device, st, none, start, false);
+  case VLCT_PART_UPPER:    return compute_on_device(h, b, G, 0.0, dt_device, st, end, none, false);
+  default: return fail(h, VLCT_ERR_INVALID_BLOCK, "unknown part %d", part);
+  }
 }
 
 const char* vlct_last_error(const vlct_handle* h)

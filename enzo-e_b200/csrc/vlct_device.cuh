@@ -29,6 +29,14 @@ inline Box full_box(const Geom& G, int s)
   return b;
 }
 
+/// clip a box along z; false if nothing is left
+inline bool clip_z(Box& b, const ZClip& zc)
+{
+  if (b.lo[2] < zc.lo) b.lo[2] = zc.lo;
+  if (b.hi[2] > zc.hi) b.hi[2] = zc.hi;
+  return !empty(b);
+}
+
 __device__ __forceinline__ size_t cidx(const Geom& G, int k, int j, int i)
 { return ((size_t) k * (size_t) G.my + (size_t) j) * (size_t) G.mx + (size_t) i; }
 

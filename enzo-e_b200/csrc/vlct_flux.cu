@@ -422,12 +422,12 @@ void flux_recon(const FluxLaunch& L, int recon, int solver, bool de)
 
 void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
                  int recon, const State& cur, const Scratch& S,
-                 const FaceB& bi_cur, int cs)
+                 const FaceB& bi_cur, int cs, ZClip zc)
 {
   // non-stale faces: [cs, f-cs) on every axis of the face-shaped array
   Box box = full_box(G, cs);
   box.hi[dim] -= 1;
-  if (empty(box)) return;
+  if (!clip_z(box, zc)) return;
   FluxLaunch L{ ctx.st, P, G, cur, scalar_ptrs(S.prim_sc, P.nsc),
                 P.mhd ? bi_cur.bi[dim] : nullptr, S.flux[dim], box };
   const bool de = P.de != 0;

@@ -324,11 +324,12 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
 template <bool MHD, bool DE>
 __global__ void __launch_bounds__(256)
 k_timestep(const Params P, const Geom G, const State u, double* pressure,
-           double dx, double dy, double dz, unsigned long long* dt_bits)
+           double dx, double dy, double dz, unsigned long long* dt_bits,
+           const size_t c_begin, const size_t c_end)
 {
-  const size_t n = G.cells();
+  const size_t n = c_end;
   double local_min = DBL_MAX;
-  for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < n;
+  for (size_t c = c_begin + (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < n;
        c += (size_t) gridDim.x * blockDim.x) {
     const double rho = u.rho[c];
     const double vx = u.vx[c], vy = u.vy[c], vz = u.vz[c];
@@ -502,11 +503,11 @@ void Profiler::reset()
 // launchers
 // ---------------------------------------------------------------------------
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale)
+                       const State& cur, const Scratch& S, int stale, ZClip zc)
 {
   if (P.nsc == 0) return;   // pressure is computed inside the flux kernels
-  const Box box = full_box(G, stale);
-  if (empty(box)) return;
+  Box box = full_box(G, stale);
+  if (!clip_z(box, zc)) return;
   ScopedLaunch sl(ctx, "k_specific_scalars");
   k_specific_scalars<<<grid_for(box), kBlock, 0, ctx.st>>>(
       P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
@@ -514,7 +515,8 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
 
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, const double* step_params, int s)
+               const FaceB& bi_out, const double* step_params, int s,
+               ZClip z_edge, ZClip z_face)
 {
   cudaStream_t st = ctx.st;
   const int m[3] = { G.mx, G.my, G.mz };
@@ -535,7 +537,9 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     }
     Box box;   // union of the three component boxes
     for (int a = 0; a < 3; a++) { box.lo[a] = s; box.hi[a] = m[a] - s - 1; }
-    if (!empty(box)) {
+    // (the per-component boxes are tested per thread: clipping the launch box
+    // clips all three)
+    if (clip_z(box, z_edge)) {
       ScopedLaunch sl(ctx, "k_edge_efield");
       k_edge_efield<<<grid_for(box), block, 0, st>>>(G, A, box);
     }
@@ -555,7 +559,7 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     }
     Box box;
     for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
-    if (!empty(box)) {
+    if (clip_z(box, z_face)) {
       ScopedLaunch sl(ctx, "k_face_bfield");
       k_face_bfield<<<grid_for(box), block, 0, st>>>(G, A, box);
     }
@@ -566,7 +570,7 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
                    const double* accel[3], bool gravity,
-                   const double* step_params, int s)
+                   const double* step_params, int s, ZClip zc)
 {
   cudaStream_t st = ctx.st;
   UpdateArgs A;
@@ -582,8 +586,8 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   A.gravity = gravity ? 1 : 0;
   A.inner = full_box(G, s + 1);
   // with CT the centred B is rewritten on the whole [s, m-s)^3 region
-  const Box box = P.mhd ? full_box(G, s) : A.inner;
-  if (empty(box)) return;
+  Box box = P.mhd ? full_box(G, s) : A.inner;
+  if (!clip_z(box, zc)) return;
   const int block = kBlock; const dim3 grid = grid_for(box);
   ScopedLaunch sl(ctx, "k_update");
   if (P.mhd) {
@@ -595,24 +599,32 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   }
 }
 
+void launch_timestep_reset(const LaunchCtx& ctx, unsigned long long* dt_bits)
+{
+  ScopedLaunch sl0(ctx, "k_set_u64");
+  k_set_u64<<<1, 1, 0, ctx.st>>>(dt_bits, 0x7fefffffffffffffULL);   // DBL_MAX
+}
+
 void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
                      const State& u, double* pressure, const double* width,
-                     unsigned long long* dt_bits)
+                     unsigned long long* dt_bits, ZClip zc)
 {
   cudaStream_t st = ctx.st;
-  { ScopedLaunch sl0(ctx, "k_set_u64");
-    k_set_u64<<<1, 1, 0, st>>>(dt_bits, 0x7fefffffffffffffULL); }  // DBL_MAX
-  const size_t n = G.cells();
+  const int zlo = zc.lo < 0 ? 0 : zc.lo, zhi = zc.hi > G.mz ? G.mz : zc.hi;
+  if (zhi <= zlo) return;
+  const size_t plane = (size_t) G.mx * (size_t) G.my;
+  const size_t c0 = plane * (size_t) zlo, c1 = plane * (size_t) zhi;
+  const size_t n = c1 - c0;
   int blocks = (int) ((n + 255) / 256);
   const int max_blocks = 148 * 16;
   if (blocks > max_blocks) blocks = max_blocks;
   ScopedLaunch sl(ctx, "k_timestep");
   if (P.mhd) {
-    if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
-    else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+    if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
+    else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
   } else {
-    if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
-    else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits);
+    if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
+    else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
   }
 }
 

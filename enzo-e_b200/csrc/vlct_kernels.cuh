@@ -81,28 +81,42 @@ struct LaunchCtx {
   Profiler* prof;
 };
 
+/// A half-open range [lo, hi) along z that a launch is clipped to, in the
+/// kernel's own z index space (cells for the cell kernels and the x / y
+/// sweeps, faces for the z sweep). Kernels are pure functions of their inputs
+/// at a given index, so any partition of a launch's index box into clipped
+/// launches gives bit-identical results; vlct_api.cu uses this to run a step
+/// as a z-skewed pipeline (HOST staging overlapped with the kernels, ghost
+/// exchange overlapped with the interior).
+struct ZClip {
+  int lo, hi;
+};
+constexpr ZClip kNoClip{ -(1 << 30), 1 << 30 };
+
 /// specific passive scalars over [s, m-s)^3 (no-op without scalars; the
 /// primitive pressure is computed on the fly by the flux kernels)
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale);
+                       const State& cur, const Scratch& S, int stale,
+                       ZClip zc = kNoClip);
 
 /// reconstruct -> fix longitudinal B -> Riemann -> passive fluxes along dim
 void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
                  int recon, const State& cur, const Scratch& S,
-                 const FaceB& bi_cur, int cur_stale);
+                 const FaceB& bi_cur, int cur_stale, ZClip zc = kNoClip);
 
 /// constrained transport: edge E, face-B update
 /// (step_params: dt/dx, dt/dy, dt/dz, dt of the stage, in device memory)
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const State& cur, const Scratch& S, const FaceB& bi0,
-               const FaceB& bi_out, const double* step_params, int stale);
+               const FaceB& bi_out, const double* step_params, int stale,
+               ZClip z_edge = kNoClip, ZClip z_face = kNoClip);
 
 /// centred B + flux divergence + sources + conserved update + floors/sync
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
                    const double* accel[3], bool gravity,
-                   const double* step_params, int stale);
+                   const double* step_params, int stale, ZClip zc = kNoClip);
 
 /// the per-stage constants of a step from a host or device dt (see k_step_params)
 void launch_step_params(const LaunchCtx& ctx, const double* dt_dev, double dt_host,
@@ -113,10 +127,14 @@ void launch_finish_dt(const LaunchCtx& ctx, const unsigned long long* bits,
                       double courant, double* dt_out);
 
 /// DE sync + pressure field + CFL minimum over all cells; *dt_bits receives
-/// the bit pattern of the minimum local dt (not yet multiplied by courant)
+/// the bit pattern of the minimum local dt (not yet multiplied by courant).
+/// launch_timestep_reset sets *dt_bits to DBL_MAX; launch_timestep folds the
+/// cells of z levels [zc.lo, zc.hi) into it (atomicMin), so a block may be
+/// processed in several launches.
+void launch_timestep_reset(const LaunchCtx& ctx, unsigned long long* dt_bits);
 void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
                      const State& u, double* pressure, const double* width,
-                     unsigned long long* dt_bits);
+                     unsigned long long* dt_bits, ZClip zc = kNoClip);
 
 /// periodic self-refresh of one field along one axis
 void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,

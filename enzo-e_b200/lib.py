@@ -17,7 +17,9 @@ LIB_PATH = os.environ.get("VLCT_B200_LIB") or os.path.join(
 EXPORTED_SYMBOLS = (
     "vlct_config_init", "vlct_config_set", "vlct_config_validate",
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
-    "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev", "vlct_last_error", "vlct_status_string",
+    "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
+    "vlct_compute_dev_part", "vlct_set_option",
+    "vlct_last_error", "vlct_status_string",
     "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_staged_bytes",
     "vlct_synchronize",
     "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
@@ -61,6 +63,9 @@ def load():
         "vlct_timestep": (C.c_int, [C.c_void_p, blkp, dp]),
         "vlct_timestep_dev": (C.c_int, [C.c_void_p, blkp, dp]),
         "vlct_compute_dev": (C.c_int, [C.c_void_p, blkp, dp]),
+        "vlct_compute_dev_part": (C.c_int, [C.c_void_p, blkp, dp, C.c_int,
+                                            C.c_int, C.c_int]),
+        "vlct_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "vlct_last_error": (C.c_char_p, [C.c_void_p]),
         "vlct_status_string": (C.c_char_p, [C.c_int]),
         "vlct_kernel_launches": (C.c_longlong, [C.c_void_p]),

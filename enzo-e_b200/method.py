@@ -157,6 +157,18 @@ class EnzoMethodMHDVlct:
                                                float(dt)))
         block.compute_done()
 
+    def compute_part(self, block, dt, part, z_lo, z_hi):
+        """One of the three parts of a step (vlct_compute_dev_part): the
+        interior first, then the lower / upper rest once the z ghost levels
+        have arrived. dt: one-element fp64 CUDA tensor. The caller calls
+        block.compute_done() after the last part."""
+        self._check(self._lib.vlct_compute_dev_part(
+            self._h, C.byref(block.c_block),
+            C.cast(dt.data_ptr(), C.POINTER(C.c_double)), part, z_lo, z_hi))
+
+    def set_option(self, key, value):
+        self._check(self._lib.vlct_set_option(self._h, key.encode(), int(value)))
+
     def timestep_dev(self, block, out=None):
         """timestep() without the host round trip: returns a one-element fp64
         CUDA tensor holding courant * min(...), filled asynchronously."""

@@ -184,6 +184,37 @@ int vlct_timestep_dev(vlct_handle *h, const vlct_block *block, double *dt_device
 int vlct_compute_dev(vlct_handle *h, const vlct_block *block,
                      const double *dt_device);
 
+/* One step in three parts, for drivers that overlap the ghost-zone exchange
+ * with the update (the reference overlaps the refresh messages of one block
+ * with other blocks' compute through Charm++'s message-driven scheduling,
+ * src/Cello/control_refresh.cpp:243-359; with one large block per GPU the
+ * overlap has to happen inside the block):
+ *   VLCT_PART_INTERIOR  everything that can be computed from the cell levels
+ *                       z_lo-4 .. z_hi+5 alone (z in ghost-including indices),
+ *                       i.e. without the z ghost levels when
+ *                       gz+4 <= z_lo < z_hi <= mz-gz-6;
+ *   VLCT_PART_LOWER / VLCT_PART_UPPER  the rest, below / above it; these read
+ *                       the z ghost levels and may be issued in either order
+ *                       once the exchange has delivered them.
+ * INTERIOR must be issued first (it also latches dt), all three with the same
+ * (z_lo, z_hi). Every kernel of the step is a pure function of its inputs at a
+ * given index and the parts tile each kernel's index box exactly once, so the
+ * three calls together leave bit-for-bit what vlct_compute_dev leaves
+ * (tests/test_gpu_parts.py). Two-stage "vl" scheme, DEVICE blocks only. */
+enum { VLCT_PART_INTERIOR = 0, VLCT_PART_LOWER = 1, VLCT_PART_UPPER = 2 };
+int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
+                          const double *dt_device, int part, int z_lo, int z_hi);
+
+/* Tuning knobs of a handle (none changes any result bit):
+ *   "host_pipeline_levels"   VLCT_MEM_HOST blocks are staged through the GPU
+ *        as a pipeline over z: the H2D copy of the next levels, the kernels on
+ *        the current ones and the D2H copy of the finished ones overlap.
+ *        -1 (default): ~mz/32 levels per pass for blocks of >= 32 MB per
+ *        field, one shot below that; 0: always one shot; n > 0: n levels.
+ *   "device_pipeline_levels" run VLCT_MEM_DEVICE steps in passes of n levels
+ *        too (0 = off, default; a test hook for the pass machinery). */
+int vlct_set_option(vlct_handle *h, const char *key, long long value);
+
 /* Message of the last failure on this handle (never NULL). */
 const char *vlct_last_error(const vlct_handle *h);
 const char *vlct_status_string(int status);
