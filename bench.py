@@ -127,7 +127,7 @@ def workload_config(size, world, grid):
             "riemann_solver": "hlld", "reconstruct_method": "plm",
             "courant": 0.3, "gamma": 5.0 / 3.0,
             "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} bricks",
-            "step": "timestep + dt min-reduce + ghost refresh + compute (dt device-resident: vlct_timestep_dev / vlct_compute_dev)",
+            "step": "timestep + dt min-reduce + ghost refresh + compute (dt device-resident: vlct_timestep_dev / vlct_compute_dev; with a z split the z ghost exchange overlaps the interior update)",
             "l2_policy": "inputs (>=1.1 GB per field) exceed the 126 MB L2"}
 
 
@@ -211,7 +211,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    grid = _grid(args.gpus)
+    grid = _grid(args.gpus, args.layout)
     t_all = time.perf_counter()
     samples = []
     for _ in range(args.warmup):
@@ -239,9 +239,9 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def _grid(world):
+def _grid(world, layout="slabs"):
     from enzo_e_b200.domain import proc_grid
-    return proc_grid(world)
+    return proc_grid(world, slabs=(layout == "slabs"))
 
 
 # Kernel families and their ALGORITHMIC bytes per processed unit (DESIGN.md
@@ -310,8 +310,14 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    domain = Domain(rank, world)
+        opts = None
+        try:   # NCCL's own stream above the compute stream: the ghost slabs
+            # move while the interior update runs
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    domain = Domain(rank, world, grid=_grid(world, args.layout))
     grid = domain.grid
     size = args.size
     n_local = (size, size, size)
@@ -332,8 +338,9 @@ def run_ours(args):
             # the cycles queue back to back, nothing waits for the host
             dt = method.timestep_dev(block, out=dt_dev)
             dt = domain.global_dt(dt, dev)
-            domain.refresh(method, block)
-            method.compute(block, dt)
+            # refresh + compute; with a z split the z exchange runs under the
+            # interior part of the update (Domain.step)
+            domain.step(method, block, dt, overlap=not args.no_overlap)
             return dt
 
         def sync_all():
@@ -511,6 +518,10 @@ def main():
                     help="cells per axis per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-block", type=int, default=48)
+    ap.add_argument("--layout", default="slabs", choices=["slabs", "bricks"],
+                    help="N > 1: z slabs (1x1xN, default) or bricks (2x2x2 at N=8)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: exchange ghosts before the update instead of under it")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -14,6 +14,13 @@ the min-reduction of the timestep (src/Cello/control_stopping.cpp:96-142).
   * slabs are packed/unpacked by CUDA kernels (csrc: k_slab_copy) and moved
     with NCCL send/recv (torch.distributed P2P) over NVLink
   * dt = all_reduce(MIN) of the per-block timestep
+  * `step()` overlaps the exchange along z (the last axis of the refresh) with
+    the update: the slabs are packed and handed to NCCL, the interior part of
+    the step (everything that does not read a z ghost level,
+    vlct_compute_dev_part) is queued behind them on the compute stream while
+    NCCL moves the slabs on its own stream, then the ghosts are unpacked and
+    the lower / upper rest of the step runs. Results are bit-identical to
+    refresh() + compute().
 """
 import torch
 
@@ -23,8 +30,12 @@ except Exception:  # pragma: no cover
     dist = None
 
 
-def proc_grid(world):
-    """(px, py, pz): split z first (contiguous slabs), then y, then x."""
+def proc_grid(world, slabs=False):
+    """(px, py, pz): split z first (contiguous slabs), then y, then x.
+    slabs=True: z slabs only (two neighbours per rank, the whole exchange can
+    be overlapped with the update)."""
+    if slabs:
+        return (1, 1, world)
     grid = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
     if world in grid:
         return grid[world]
@@ -64,12 +75,17 @@ class Domain:
 
     # -- refresh ---------------------------------------------------------------
     def refresh(self, method, block, buffers=None, pack=None, unpack=None,
-                wrap=None, alloc=None):
+                wrap=None, alloc=None, defer_z=False):
         """Fill all ghost zones of `block` (periodic domain).
 
         pack/unpack/wrap/alloc default to the CUDA kernels behind `method`;
         the gloo CPU tests pass host stand-ins to exercise the neighbour and
-        message-ordering logic without a GPU."""
+        message-ordering logic without a GPU.
+
+        defer_z=True: if the domain is split along z, the z exchange is only
+        started (slabs packed, sends / receives posted); the returned handle
+        goes to refresh_finish(), which waits for the messages and unpacks the
+        ghosts. Returns None when nothing was deferred."""
         pack = pack or method.halo_pack
         unpack = unpack or method.halo_unpack
         wrap = wrap or (lambda blk, axes: method.refresh_periodic(blk, axes))
@@ -101,12 +117,45 @@ class Domain:
                    dist.P2POp(dist.isend, send_hi, hi),
                    dist.P2POp(dist.irecv, recv_hi, hi),
                    dist.P2POp(dist.irecv, recv_lo, lo)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            if send_lo.is_cuda and not same_stream:
-                torch.cuda.current_stream().synchronize()
-            unpack(block, axis, 0, recv_lo)
-            unpack(block, axis, 1, recv_hi)
+            reqs = dist.batch_isend_irecv(ops)
+            pending = (reqs, axis, recv_lo, recv_hi, unpack, same_stream)
+            if defer_z and axis == 2:
+                # NCCL works on its own stream, ordered after the packs; the
+                # caller's stream only joins it in refresh_finish()
+                return pending
+            self.refresh_finish(method, block, pending)
+        return None
+
+    def refresh_finish(self, method, block, pending):
+        """Wait for a deferred exchange and unpack its ghost slabs."""
+        reqs, axis, recv_lo, recv_hi, unpack, same_stream = pending
+        for req in reqs:
+            req.wait()
+        if recv_lo.is_cuda and not same_stream:
+            torch.cuda.current_stream().synchronize()
+        unpack(block, axis, 0, recv_lo)
+        unpack(block, axis, 1, recv_hi)
+
+    def step(self, method, block, dt, overlap=True):
+        """refresh + compute of one cycle (dt: device-resident, already
+        reduced over ranks). With overlap the z exchange runs under the
+        interior part of the update."""
+        from . import abi
+        mz = block.n[2] + 2 * block.g[2]
+        z_lo = block.g[2] + abi.PART_REACH_BELOW
+        z_hi = mz - block.g[2] - abi.PART_REACH_ABOVE
+        can_split = (overlap and self.grid[2] > 1 and z_hi > z_lo
+                     and hasattr(dt, "data_ptr")
+                     and getattr(block, "stream_is_current", False))
+        pending = self.refresh(method, block, defer_z=can_split)
+        if pending is None:
+            method.compute(block, dt)
+            return
+        method.compute_part(block, dt, abi.PART_INTERIOR, z_lo, z_hi)
+        self.refresh_finish(method, block, pending)
+        method.compute_part(block, dt, abi.PART_LOWER, z_lo, z_hi)
+        method.compute_part(block, dt, abi.PART_UPPER, z_lo, z_hi)
+        block.compute_done()
 
     def global_dt(self, dt, device=None):
         if hasattr(dt, "data_ptr"):

@@ -22,35 +22,47 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=dev)
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    # "overlap": Domain.step with the z exchange under the interior part of
+    # the update (device-resident dt); "slabs": z slabs instead of bricks
+    mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
+    overlap = "overlap" in mode
     n_scalars = 1
     params = {"mhd_choice": "constrained_transport", "riemann_solver": "hlld",
               "reconstruct_method": "plm", "theta_limiter": 1.5,
               "courant": 0.3,
               "Physics:fluid_props:floors:density": 1e-200,
               "Physics:fluid_props:floors:pressure": 1e-200}
-    dom = Domain(rank, world)
+    from enzo_e_b200.domain import proc_grid
+    dom = Domain(rank, world, grid=proc_grid(world, slabs="slabs" in mode))
     g = (3, 3, 3)
     n_local = (24, 20, 16)
     N = tuple(n_local[a] * dom.grid[a] for a in range(3))
     width = tuple(1.0 / N[a] for a in range(3))
     passive = tuple(f"passive_{k}" for k in range(n_scalars))
 
-    def run(domain, n, lower):
+    def run(domain, n, lower, overlap=False):
         f = problems.orszag_tang(n, g, lower, width, device=dev,
                                  n_passive=n_scalars)
         m = EnzoMethodMHDVlct(params, n_passive=n_scalars)
         blk = Block(f, n, g, width, passive=passive)
         dts = []
         for _ in range(nsteps):
-            dt = domain.global_dt(m.timestep(blk), dev)
-            domain.refresh(m, blk)
-            m.compute(blk, dt)
-            dts.append(dt)
+            if overlap:
+                dt = domain.global_dt(m.timestep_dev(blk), dev)
+                domain.step(m, blk, dt)
+                dts.append(dt.clone())
+            else:
+                dt = domain.global_dt(m.timestep(blk), dev)
+                domain.refresh(m, blk)
+                m.compute(blk, dt)
+                dts.append(dt)
         m.synchronize()
+        torch.cuda.synchronize()
+        assert blk.compute_done_count == nsteps
         m.close()
-        return f, dts
+        return f, [float(t) for t in dts]
 
-    f, dts = run(dom, n_local, dom.lower_corner(n_local, width))
+    f, dts = run(dom, n_local, dom.lower_corner(n_local, width), overlap)
     ok = True
     names = sorted(f)
     # gather the active zones on rank 0
@@ -69,7 +81,7 @@ def main():
         for name in names:
             face = {"bfieldi_x": 0, "bfieldi_y": 1, "bfieldi_z": 2}.get(name, -1)
             for r in range(world):
-                c = Domain(r, world).coords
+                c = Domain(r, world, grid=dom.grid).coords
                 part = f[name][r]
                 sl_loc, sl_glob = [], []
                 for ax in (2, 1, 0):          # array axes z, y, x

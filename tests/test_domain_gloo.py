@@ -113,7 +113,7 @@ def make_block(coords, n, g, N, fill_ghosts):
     return HostBlock(f, n, g)
 
 
-def _worker(rank, world, port, grid, result_q):
+def _worker(rank, world, port, grid, result_q, defer=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -126,10 +126,16 @@ def _worker(rank, world, port, grid, result_q):
         blk = make_block(dom.coords, n, g, N, fill_ghosts=False)
         want = make_block(dom.coords, n, g, N, fill_ghosts=True)
         k = HostKernels()
-        dom.refresh(k, blk, pack=k.halo_pack, unpack=k.halo_unpack,
-                    wrap=k.wrap,
-                    alloc=lambda nbytes: torch.empty(nbytes // 8,
-                                                     dtype=torch.float64))
+        pending = dom.refresh(k, blk, pack=k.halo_pack, unpack=k.halo_unpack,
+                              wrap=k.wrap, defer_z=defer,
+                              alloc=lambda nbytes: torch.empty(
+                                  nbytes // 8, dtype=torch.float64))
+        # a deferred z exchange is handed back iff the domain is split along z
+        assert (pending is not None) == (defer and grid[2] > 1)
+        if pending is not None:
+            # x and y are complete, the z ghosts arrive with refresh_finish
+            assert np.all(blk.fields["density"][:g[2]] == -1.0)
+            dom.refresh_finish(k, blk, pending)
         bad = [name for name in FIELDS
                if not np.array_equal(blk.fields[name], want.fields[name])]
         dt = dom.global_dt(0.5 + rank, device="cpu")
@@ -146,13 +152,15 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("grid", [(1, 1, 2), (2, 1, 1), (1, 2, 1)])
-def test_refresh_two_ranks(grid):
+@pytest.mark.parametrize("grid,defer", [((1, 1, 2), False), ((2, 1, 1), False),
+                                        ((1, 2, 1), False), ((1, 1, 2), True),
+                                        ((1, 2, 1), True)])
+def test_refresh_two_ranks(grid, defer):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, q))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, q, defer))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -171,6 +179,7 @@ def test_proc_grid_and_neighbours():
     assert proc_grid(2) == (1, 1, 2)
     assert proc_grid(4) == (1, 2, 2)
     assert proc_grid(8) == (2, 2, 2)
+    assert proc_grid(8, slabs=True) == (1, 1, 8)
     for world in (2, 4, 8, 6, 12):
         g = proc_grid(world)
         assert g[0] * g[1] * g[2] == world

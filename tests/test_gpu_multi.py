@@ -10,15 +10,16 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+@pytest.mark.parametrize("mode", ["plain", "overlap", "overlap-slabs"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_bricks_match_single_block(world):
+def test_bricks_match_single_block(world, mode):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + world),
-           os.path.join(HERE, "multi_gpu_worker.py"), "3"]
+           os.path.join(HERE, "multi_gpu_worker.py"), "3", mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:]
