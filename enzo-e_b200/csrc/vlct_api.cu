@@ -457,6 +457,12 @@ int vlct_create(const vlct_config* cfg, vlct_handle** out)
   // (fluid-props/EnzoPhysicsFluidProps.cpp:234)
   const float ggm1 = (float) (cfg->gamma * (cfg->gamma - 1.));
   P.ggm1 = (double) ggm1;
+  {
+    // through volatiles so the host compiler cannot fold or reassociate it
+    volatile double gm1 = cfg->gamma - 1.0;
+    volatile double one = 1.0;
+    P.igm1 = one / gm1;
+  }
   P.nsc = cfg->n_passive;
   P.riemann = cfg->riemann_solver;
   P.recon = cfg->reconstruct_method;

@@ -131,7 +131,7 @@ solve_and_store(const Params& P, const double* wl_, const double* wr_,
     wr.bi = wr.bj = wr.bk = 0.;
   }
   Flux f;
-  riemann_solve<SOLVER, DE>(P.gamma, wl, wr, f);
+  riemann_solve<SOLVER, DE>(P.gamma, P.igm1, wl, wr, f);
 
   double* fm[3] = { F.mx_, F.my_, F.mz_ };
   F.rho[c] = f.rho;

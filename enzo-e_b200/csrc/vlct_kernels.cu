@@ -124,7 +124,11 @@ __device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
   A.edge[D][c] = 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
 }
 
+#ifdef VLCT_EDGE_MINBLOCKS   // tuning hook (A/B builds)
+__global__ void __launch_bounds__(kBlock, VLCT_EDGE_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(kBlock)
+#endif
 k_edge_efield(const Geom G, const EdgeArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(box, i, j, k);

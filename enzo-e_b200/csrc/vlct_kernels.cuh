@@ -46,6 +46,7 @@ struct Params {
   double density_floor, pressure_floor;
   double de_eta;
   double ggm1;          // (double)(float)(gamma*(gamma-1)), FluidProps.cpp:234
+  double igm1;          // 1. / (gamma - 1.), HLLD.hpp:66 (IEEE, host-side)
   int nsc;
   int mhd, de;
   int riemann, recon;
