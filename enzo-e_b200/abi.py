@@ -23,6 +23,7 @@ MHD_CHOICE = {"unset": -1, "no_bfield": 0, "constrained_transport": 1}
 TIME_SCHEME = {"vl": 0, "euler": 1}
 DUAL_ENERGY = {"disabled": 0, "modern": 1, "bryan95": 2}
 MEM_HOST, MEM_DEVICE = 0, 1
+BOUNDARY = {"outflow": 0, "reflecting": 1}
 PART_INTERIOR, PART_LOWER, PART_UPPER = 0, 1, 2
 # input levels an interior part reads below z_lo / beyond z_hi (vlct.h)
 PART_REACH_BELOW, PART_REACH_ABOVE = 4, 6

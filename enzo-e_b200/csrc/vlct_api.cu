@@ -891,6 +891,38 @@ int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
   return VLCT_OK;
 }
 
+int vlct_boundary(vlct_handle* h, const vlct_block* b, int axis, int side, int type)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_boundary needs a DEVICE block");
+  if (axis < 0 || axis > 2 || (side != 0 && side != 1) ||
+      (type != VLCT_BOUNDARY_OUTFLOW && type != VLCT_BOUNDARY_REFLECTING))
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "bad arguments to vlct_boundary");
+  const Geom G = geom_of(b);
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  if (type == VLCT_BOUNDARY_REFLECTING && n[axis] < g[axis])
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "reflecting boundary needs n >= ghost depth along the axis");
+  // the vector component along `axis` flips under reflection
+  // (has_vector_name_, EnzoBoundary.cpp:80-86)
+  double* const vec[3][3] = { { b->velocity_x, b->bfield_x, b->bfieldi_x },
+                              { b->velocity_y, b->bfield_y, b->bfieldi_y },
+                              { b->velocity_z, b->bfield_z, b->bfieldi_z } };
+  std::vector<RefreshField> fields;
+  collect_fields(h, b, G, fields);
+  for (const RefreshField& f : fields) {
+    double sign = 1.0;
+    for (int c = 0; c < 3; c++) if (f.p == vec[axis][c]) sign = -1.0;
+    launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
+                         f.n2, axis, n[axis], g[axis], f.face == axis ? 1 : 0,
+                         side, type, sign);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
 long long vlct_halo_bytes(const vlct_handle* h, const vlct_block* b, int axis)
 {
   if (h == nullptr || b == nullptr || axis < 0 || axis > 2) return -1;

@@ -439,6 +439,41 @@ k_wrap_axis(double* p, int n0, int n1, int n2, int axis, int n, int g, int cen)
   }
 }
 
+/// outflow / reflecting domain boundary of one field along one axis
+/// (enzo-core/EnzoBoundary.cpp:164-283 reflecting, :352-466 outflow): threads
+/// enumerate the g ghost layers of one side; the other two axes run over their
+/// full, ghost- and centering-including extent like the reference's loops.
+__global__ void __launch_bounds__(256)
+k_boundary_axis(double* p, int n0, int n1, int n2, int axis, int n, int g,
+                int cen, int side, int type, double sign)
+{
+  const int ext[3] = { n2, n1, n0 };
+  int sh[3] = { ext[0], ext[1], ext[2] };
+  sh[axis] = g;
+  const size_t total = (size_t) sh[0] * sh[1] * sh[2];
+  for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t) gridDim.x * blockDim.x) {
+    int idx[3];
+    idx[0] = (int) (t % sh[0]);
+    idx[1] = (int) ((t / sh[0]) % sh[1]);
+    idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
+    const int ig = idx[axis];
+    int src, dst;
+    if (type == VLCT_BOUNDARY_OUTFLOW) {
+      if (side == 0) { src = g;               dst = g - ig - 1; }
+      else           { src = n + g - 1 + cen; dst = src + ig + 1; }
+    } else {
+      if (side == 0) { src = g + cen + ig;    dst = g - ig - 1; }
+      else           { src = n + g - 1 - ig;  dst = n + g + ig + cen; }
+    }
+    idx[axis] = src;
+    const double v = p[((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0]];
+    idx[axis] = dst;
+    p[((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0]] =
+        (type == VLCT_BOUNDARY_OUTFLOW) ? v : sign * v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
             double* buffer, int pack)
@@ -659,6 +694,21 @@ void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
   if (blocks > 148 * 16) blocks = 148 * 16;
   ScopedLaunch sl(ctx, "k_wrap_axis");
   k_wrap_axis<<<blocks, 256, 0, st>>>(p, n0, n1, n2, axis, n, g, cen);
+}
+
+void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
+                          int axis, int n, int g, int cen, int side, int type,
+                          double sign)
+{
+  const int ext[3] = { n2, n1, n0 };
+  size_t total = (size_t) g;
+  for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
+  if (total == 0) return;
+  int blocks = (int) ((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ScopedLaunch sl(ctx, "k_boundary_axis");
+  k_boundary_axis<<<blocks, 256, 0, ctx.st>>>(p, n0, n1, n2, axis, n, g, cen, side,
+                                              type, sign);
 }
 
 void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,

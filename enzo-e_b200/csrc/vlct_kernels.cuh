@@ -141,6 +141,11 @@ void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
 void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
                       int axis, int n, int g, int cen);
 
+/// outflow / reflecting boundary of one field on one face of the domain
+void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
+                          int axis, int n, int g, int cen, int side, int type,
+                          double sign);
+
 /// halo slab pack / unpack of one field along one axis
 /// lo..lo+g: range along the axis; the slab spans the full other extents
 void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "vlct_synchronize",
     "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
     "vlct_profile_get", "vlct_selftest_fpops",
-    "vlct_refresh_periodic", "vlct_halo_bytes", "vlct_halo_pack",
+    "vlct_refresh_periodic", "vlct_boundary", "vlct_halo_bytes", "vlct_halo_pack",
     "vlct_halo_unpack",
 )
 
@@ -80,6 +80,7 @@ def load():
         "vlct_selftest_fpops": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_int,
                                           C.POINTER(C.c_longlong)]),
         "vlct_refresh_periodic": (C.c_int, [C.c_void_p, blkp, C.c_int]),
+        "vlct_boundary": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, C.c_int]),
         "vlct_halo_bytes": (C.c_longlong, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_pack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),
         "vlct_halo_unpack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),

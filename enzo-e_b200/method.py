@@ -193,6 +193,13 @@ class EnzoMethodMHDVlct:
         self._check(self._lib.vlct_refresh_periodic(
             self._h, C.byref(block.c_block), axes))
 
+    def boundary(self, block, axis, side, kind):
+        """EnzoBoundary::enforce on one face of the domain: kind "outflow" or
+        "reflecting", side 0 = lower / 1 = upper (apply after the periodic /
+        neighbour refresh of the other axes, like Block::update_boundary_)."""
+        self._check(self._lib.vlct_boundary(
+            self._h, C.byref(block.c_block), axis, side, abi.BOUNDARY[kind]))
+
     def halo_bytes(self, block, axis):
         return self._lib.vlct_halo_bytes(self._h, C.byref(block.c_block), axis)
 

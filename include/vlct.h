@@ -269,6 +269,21 @@ int vlct_selftest_fpops(long long n, unsigned long long seed, int mode,
  * that the shared face belongs to both sides. axes: bit 0/1/2 = x/y/z. */
 int vlct_refresh_periodic(vlct_handle *h, const vlct_block *block, int axes);
 
+/* Non-periodic domain boundaries: EnzoBoundary::enforce for one face of the
+ * domain (src/Enzo/enzo-core/EnzoBoundary.cpp:33-76), applied to every field
+ * of the block like Block::update_boundary_ does at the end of a refresh
+ * (src/Cello/mesh_Block.cpp:1057-1077, control_refresh.cpp:229-232 -- i.e.
+ * AFTER the periodic / neighbour ghost copies of the other axes).
+ *   outflow     ghost layers copy the outermost active cell (for a field that
+ *               is face-centred along `axis`: the boundary face)
+ *   reflecting  ghost layers mirror the active zone; the vector component
+ *               along `axis` (velocity_, bfield_, bfieldi_) changes sign
+ * The layers span the full ghost-including extent of the other two axes.
+ * Masks and "inflow" (Value-initialised, problem-specific) are not covered. */
+enum { VLCT_BOUNDARY_OUTFLOW = 0, VLCT_BOUNDARY_REFLECTING = 1 };
+int vlct_boundary(vlct_handle *h, const vlct_block *block, int axis, int side,
+                  int type);
+
 /* Pack / unpack the ghost-exchange slab of all fields along one axis
  * (axis 0,1,2 = x,y,z; side 0 = lower, 1 = upper) into / from a contiguous
  * device buffer: the payload of one MsgRefresh FieldFace

@@ -160,6 +160,9 @@ def _ic_lib():
         lib.vlct_oracle_refresh_periodic.restype = C.c_int
         lib.vlct_oracle_refresh_periodic.argtypes = [
             C.POINTER(abi.VlctBlock), C.c_int, C.c_int]
+        lib.vlct_oracle_boundary.restype = C.c_int
+        lib.vlct_oracle_boundary.argtypes = [
+            C.POINTER(abi.VlctBlock), C.c_int, C.c_int, C.c_int, C.c_int]
         lib._ic_ready = True
     return lib
 
@@ -193,3 +196,15 @@ def center_bfield(blk):
 def refresh_periodic(blk, n_passive=0, axes=7):
     """Ghost refresh of a single periodic block (host memory)."""
     _ic_lib().vlct_oracle_refresh_periodic(C.byref(blk), n_passive, axes)
+
+
+BOUNDARY_TYPES = {"outflow": 0, "reflecting": 1}
+
+
+def boundary(blk, axis, side, kind, n_passive=0):
+    """EnzoBoundary::enforce on one face of the domain (host memory);
+    kind: "outflow" | "reflecting"; side 0 = lower, 1 = upper."""
+    rc = _ic_lib().vlct_oracle_boundary(C.byref(blk), n_passive, axis, side,
+                                        BOUNDARY_TYPES[kind])
+    if rc != 0:
+        raise RuntimeError(f"vlct_oracle_boundary failed ({rc})")

@@ -537,3 +537,73 @@ int vlct_oracle_refresh_periodic(const vlct_block *b, int n_passive, int axes)
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* non-periodic domain boundaries of a single block                          */
+/* ------------------------------------------------------------------------ */
+
+/* EnzoBoundary::enforce_outflow_precision_ / enforce_reflecting_precision_
+ * (src/Enzo/enzo-core/EnzoBoundary.cpp:164-283, 352-466) for one field.
+ * n0,n1,n2: array extents (z,y,x) incl. ghosts and centering; n, g: active
+ * cells and ghost depth along `axis`; cen = 1 if the field is face-centred
+ * along `axis`; side 0 = lower, 1 = upper; type 0 = outflow, 1 = reflecting;
+ * sign: -1 for the vector component along `axis` (reflecting only). */
+static void boundary_axis(double *p, int n0, int n1, int n2, int axis, int n,
+                          int g, int cen, int side, int type, double sign)
+{
+  const int ext[3] = { n2, n1, n0 };
+  for (int ig = 0; ig < g; ig++) {
+    int src, dst;
+    if (type == 0) {                 /* outflow: copy the outermost active value */
+      if (side == 0) { src = g;               dst = g - ig - 1; }
+      else           { src = n + g - 1 + cen; dst = src + ig + 1; }
+    } else {                         /* reflecting: mirror image, signed */
+      if (side == 0) { src = g + cen + ig;    dst = g - ig - 1; }
+      else           { src = n + g - 1 - ig;  dst = n + g + ig + cen; }
+    }
+    int lim[3] = { ext[0], ext[1], ext[2] };
+    lim[axis] = 1;
+    for (int k = 0; k < lim[2]; k++)
+      for (int j = 0; j < lim[1]; j++)
+        for (int i = 0; i < lim[0]; i++) {
+          int is[3] = { i, j, k }, id[3] = { i, j, k };
+          is[axis] = src; id[axis] = dst;
+          const double v = p[((size_t) is[2] * n1 + is[1]) * n2 + is[0]];
+          p[((size_t) id[2] * n1 + id[1]) * n2 + id[0]] =
+            (type == 0) ? v : sign * v;
+        }
+  }
+}
+
+/* Block::update_boundary_ (src/Cello/mesh_Block.cpp:1057-1077) for one face of
+ * the domain: every permanent field of the block. type 0 = "outflow",
+ * 1 = "reflecting". */
+int vlct_oracle_boundary(const vlct_block *b, int n_passive, int axis, int side,
+                         int type)
+{
+  const int mx = b->nx + 2 * b->gx, my = b->ny + 2 * b->gy, mz = b->nz + 2 * b->gz;
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  if (axis < 0 || axis > 2 || (side != 0 && side != 1) || (type != 0 && type != 1))
+    return 1;
+  /* vector components: has_vector_name_ (EnzoBoundary.cpp:80-86) */
+  struct { double *p; int comp; } cell[] = {
+    { b->density, -1 }, { b->velocity_x, 0 }, { b->velocity_y, 1 },
+    { b->velocity_z, 2 }, { b->total_energy, -1 }, { b->internal_energy, -1 },
+    { b->bfield_x, 0 }, { b->bfield_y, 1 }, { b->bfield_z, 2 },
+    { b->pressure, -1 }, { b->acceleration_x, -1 }, { b->acceleration_y, -1 },
+    { b->acceleration_z, -1 } };
+  for (size_t c = 0; c < sizeof(cell) / sizeof(cell[0]); c++)
+    if (cell[c].p)
+      boundary_axis(cell[c].p, mz, my, mx, axis, n[axis], g[axis], 0, side, type,
+                    cell[c].comp == axis ? -1.0 : 1.0);
+  for (int s = 0; s < n_passive; s++)
+    boundary_axis(b->passive[s], mz, my, mx, axis, n[axis], g[axis], 0, side,
+                  type, 1.0);
+  double *face[3] = { b->bfieldi_x, b->bfieldi_y, b->bfieldi_z };
+  for (int f = 0; f < 3; f++)
+    if (face[f])
+      boundary_axis(face[f], mz + (f == 2), my + (f == 1), mx + (f == 0), axis,
+                    n[axis], g[axis], f == axis, side, type,
+                    f == axis ? -1.0 : 1.0);
+  return 0;
+}

@@ -156,3 +156,86 @@ def run_linear_wave(name, N, mhd=True, kind="oracle", positive_vel=True,
         method.close()
     fields = LINWAVE_FIELDS_MHD if mhd else LINWAVE_FIELDS_HD
     return l1_error_norm(s0, s1, fields, N), dts, f
+
+
+# ---------------------------------------------------------------------------
+# axis-aligned shock tubes (input/vlct/MHD_shock_tube/*.in,
+# input/vlct/run_MHD_shock_tube_test.py, tools/l1_error_norm.py "table" mode)
+# ---------------------------------------------------------------------------
+import os as _os
+
+GOLDEN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+# input/vlct/run_MHD_shock_tube_test.py:82-87 (x, y, z)
+GOLDEN_RJ2A = (0.012523489882320429, 0.012523489882320308, 0.012523489882320315)
+RJ2A_FIELDS = ["density", "velocity_x", "velocity_y", "velocity_z", "pressure",
+               "bfield_x", "bfield_y", "bfield_z"]
+
+
+def load_reference_table(name):
+    """tools/l1_error_norm.py:412-471: '#key = value' header lines, then a
+    CSV with a header row"""
+    path = _os.path.join(GOLDEN_DIR, name)
+    skip = 0
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith("#"):
+                skip += 1
+            else:
+                break
+    rec = np.genfromtxt(path, skip_header=skip, comments="#", delimiter=",",
+                        names=True, encoding="utf-8")
+    return {k: rec[k] for k in rec.dtype.names}
+
+
+def rj2a_setup(axis, ncells=256):
+    """method_vlct_{x,y,z}_rj2a_N256.in: 256x4x4 cells on the unit cube, one
+    block, outflow along the tube, periodic across it; vlct.incl parameters."""
+    cfg = make_config(riemann="hlld", recon="plm", theta=2.0, mhd=True,
+                      courant=0.4, gamma=1.6666666666666667, dfloor=1e-200,
+                      pfloor=1e-200)
+    n = [4, 4, 4]
+    n[axis] = ncells
+    n, g = tuple(n), (3, 3, 3)
+    d = tuple(1.0 / n[a] for a in range(3))
+    f = alloc_fields(cfg, n, g)
+    blk = oracle.numpy_block(f, n, g, d)
+    oracle.ic_shock_tube(blk, (0.0, 0.0, 0.0), cfg.gamma, "rj2a",
+                         aligned_ax=axis)
+    return cfg, f, blk, n, g, d, 0.2
+
+
+def table_l1_norm(snap, table, axis, fields):
+    """compare_to_1D_reference (tools/l1_error_norm.py:537-628) with --permute:
+    the table's vectors are rotated onto the tube's axis, the table is
+    broadcast across the tube, residuals are normalised by the cell count."""
+    names = "xyz"
+    ref = dict(table)
+    for pre in ("velocity", "bfield"):
+        if all(f"{pre}_{c}" in table for c in names):
+            comps = [table[f"{pre}_{c}"] for c in names]
+            for k in range(3):
+                ref[f"{pre}_{names[(axis + k) % 3]}"] = comps[k]
+    shape = [1, 1, 1]
+    shape[2 - axis] = -1
+    resid = [np.sum(np.abs(snap[k] - ref[k].reshape(shape))) / float(snap[k].size)
+             for k in fields]
+    return float(np.sqrt(np.sum(np.square(np.array(resid)))))
+
+
+def run_rj2a(axis, method=None, refresh=None, kind="oracle"):
+    cfg, f, blk, n, g, d, t_final = rj2a_setup(axis)
+    own = method is None
+    if own:
+        method = oracle.CpuMethod(cfg, g, kind=kind)
+    if refresh is None:
+        periodic_axes = 7 & ~(1 << axis)
+
+        def refresh(b):
+            # refresh, then Block::update_boundary_ (control_refresh.cpp:229-232)
+            oracle.refresh_periodic(b, 0, periodic_axes)
+            oracle.boundary(b, axis, 0, "outflow")
+            oracle.boundary(b, axis, 1, "outflow")
+    dts = evolve(method, blk, t_final, refresh, dump_times=(t_final,))
+    if own:
+        method.close()
+    return cfg, f, g, dts

@@ -85,3 +85,30 @@ def test_halo_pack_unpack_match_host(axis):
     for name in dev:
         assert torch.equal(dev[name], wrapped[name]), name
     method.close()
+
+
+@pytest.mark.parametrize("kind", ["outflow", "reflecting"])
+def test_boundary_kernels_match_oracle(kind):
+    """vlct_boundary against the oracle's restatement of EnzoBoundary, every
+    axis and side, all fields (cell- and face-centred, passive scalars)"""
+    from helpers import make_config, random_state, copy_state, bit_equal, oracle
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(riemann="hlld", recon="plm", mhd=True, dual_energy=True,
+                      n_passive=2, accel=True)
+    n, g, d = (9, 5, 7), (3, 3, 3), (0.1, 0.1, 0.1)
+    passive = [f"passive_{i}" for i in range(2)]
+    host = random_state(cfg, n, g, seed=41)
+    method = EnzoMethodMHDVlct(config=cfg)
+    for axis in range(3):
+        for side in (0, 1):
+            want = copy_state(host)
+            blk = oracle.numpy_block(want, n, g, d, passive)
+            oracle.boundary(blk, axis, side, kind, n_passive=2)
+            dev = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+            block = Block(dev, n, g, d, passive=passive)
+            method.boundary(block, axis, side, kind)
+            method.synchronize()
+            got = {k: v.cpu().numpy() for k, v in dev.items()}
+            eq = bit_equal(want, got)
+            assert all(eq.values()), (axis, side, [k for k, v in eq.items() if not v])
+    method.close()

@@ -243,3 +243,34 @@ def test_axis_permutation_invariance(kw):
         a = r_x[k][act]
         assert np.array_equal(a, np.broadcast_to(a[0:1, 0:1, :], a.shape)), k
     assert not np.array_equal(r_x["density"][act], s_x["density"][act])
+
+
+# ---------------------------------------------------------------------------
+# Ryu-Jones 2a MHD shock tube with outflow boundaries, all on the device
+# (input/vlct/run_MHD_shock_tube_test.py:62-87)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_rj2a_shock_tube_golden_on_device(axis):
+    cfg, f, blk, n, g, d, t_final = P.rj2a_setup(axis)
+    run = GpuRun(cfg, f, n, g, d)
+    periodic_axes = 7 & ~(1 << axis)
+
+    def refresh(_blk=None):
+        run.method.refresh_periodic(run.block, periodic_axes)
+        run.method.boundary(run.block, axis, 0, "outflow")
+        run.method.boundary(run.block, axis, 1, "outflow")
+    dts = P.evolve(run, blk, t_final, refresh, dump_times=(t_final,))
+    run.download(f)
+    run.close()
+    snap = P.snapshot(cfg, f, g)
+    table = P.load_reference_table("rj2a_shock_tube_t0.2_res256.csv")
+    norm = P.table_l1_norm(snap, table, axis, P.RJ2A_FIELDS)
+    assert P.golden_isclose(norm, P.GOLDEN_RJ2A[axis]), (norm, P.GOLDEN_RJ2A[axis])
+    for k, a in snap.items():       # zero variation across the tube
+        pencil = np.moveaxis(a, 2 - axis, 0)
+        assert np.array_equal(pencil, np.broadcast_to(pencil[:, :1, :1], pencil.shape)), k
+    if axis == 0:                   # and the whole run matches the oracle's bits
+        cfg2, f2, g2, dts2 = P.run_rj2a(0)
+        assert dts == dts2
+        eq = bit_equal(f2, f)
+        assert all(eq.values()), {k: v for k, v in eq.items() if not v}

@@ -115,3 +115,61 @@ def test_oracle_active_floors_really_trigger():
     act = got["density"][3:-3, 3:-3, 3:-3]
     assert np.min(act) >= 0.95
     assert np.any(act == 0.95)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_rj2a_shock_tube_golden(axis):
+    """Ryu-Jones 2a MHD shock tube along x / y / z with outflow boundaries:
+    the reference's golden L1 norms against its tabulated solution and exactly
+    zero variation across the tube (run_MHD_shock_tube_test.py:62-87)."""
+    cfg, f, g, dts = P.run_rj2a(axis)
+    snap = P.snapshot(cfg, f, g)
+    table = P.load_reference_table("rj2a_shock_tube_t0.2_res256.csv")
+    norm = P.table_l1_norm(snap, table, axis, P.RJ2A_FIELDS)
+    assert P.golden_isclose(norm, P.GOLDEN_RJ2A[axis]), (norm, P.GOLDEN_RJ2A[axis])
+    for k, a in snap.items():       # "standard deviation of the L1 norms == 0.0"
+        pencil = np.moveaxis(a, 2 - axis, 0)
+        assert np.array_equal(pencil, np.broadcast_to(pencil[:, :1, :1], pencil.shape)), k
+
+
+def test_boundary_conditions_follow_enzo_boundary():
+    """outflow / reflecting ghost fill against a direct numpy statement of
+    EnzoBoundary.cpp:164-283,352-466 (cell- and face-centred fields)"""
+    cfg = make_config(riemann="hlld", recon="plm", mhd=True)
+    n, g, d = (6, 5, 4), (3, 3, 3), (0.1, 0.1, 0.1)
+    for kind in ("outflow", "reflecting"):
+        for axis in range(3):
+            for side in (0, 1):
+                f = random_state(cfg, n, g, seed=31)
+                want = copy_state(f)
+                blk = oracle.numpy_block(f, n, g, d)
+                oracle.boundary(blk, axis, side, kind)
+                for name, a in want.items():
+                    cen = 1 if name == "bfieldi_" + "xyz"[axis] else 0
+                    sign = -1.0 if (kind == "reflecting" and name in (
+                        "velocity_" + "xyz"[axis], "bfield_" + "xyz"[axis],
+                        "bfieldi_" + "xyz"[axis])) else 1.0
+                    v = np.moveaxis(a, 2 - axis, 0)      # axis first (a view)
+                    na, ga = n[axis], g[axis]
+                    for ig in range(ga):
+                        if kind == "outflow":
+                            src = ga if side == 0 else na + ga - 1 + cen
+                            dst = ga - ig - 1 if side == 0 else src + ig + 1
+                        else:
+                            src = ga + cen + ig if side == 0 else na + ga - 1 - ig
+                            dst = ga - ig - 1 if side == 0 else na + ga + ig + cen
+                        v[dst] = sign * v[src]
+                assert all(bit_equal(want, f).values()), (kind, axis, side)
+
+
+def test_compiled_reference_reproduces_rj2a_golden():
+    """the reference's own compiled sources on the same shock tube"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    cfg, f, g, dts = P.run_rj2a(0, kind="ref")
+    cfg2, f2, g2, dts2 = P.run_rj2a(0, kind="oracle")
+    assert dts == dts2
+    assert all(bit_equal(f, f2).values())
+    table = P.load_reference_table("rj2a_shock_tube_t0.2_res256.csv")
+    norm = P.table_l1_norm(P.snapshot(cfg, f, g), table, 0, P.RJ2A_FIELDS)
+    assert P.golden_isclose(norm, P.GOLDEN_RJ2A[0])
