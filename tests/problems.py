@@ -239,3 +239,135 @@ def run_rj2a(axis, method=None, refresh=None, kind="oracle"):
     if own:
         method.close()
     return cfg, f, g, dts
+
+
+# ---------------------------------------------------------------------------
+# Sod shock tube with dual energy in a Mach-10 frame
+# (input/vlct/dual_energy_shock_tube/*.in, run_dual_energy_shock_tube_test.py)
+# ---------------------------------------------------------------------------
+GOLDEN_SOD_DE = 0.02605861216339738   # run_dual_energy_shock_tube_test.py:64
+SOD_FIELDS = ["density", "velocity_x", "velocity_y", "velocity_z"]
+SOD_BKG_VELOCITY, SOD_OFFSET = 11.875, 2.96875
+
+
+def sod_de_setup(axis, flipped=False):
+    """method_vlct_sod_{x,y,z}_de_M10[_reverse].in: 508x4x4 cells of width
+    1/128, MHD solver (hlld + CT) with B = 0, gamma 1.4, dual energy "modern"
+    with eta = 0.00769, the whole tube moving at 11.875 along its axis. (The
+    reference cuts the tube into 4 blocks; one block gives the same cells.)"""
+    cfg = make_config(riemann="hlld", recon="plm", theta=2.0, mhd=True,
+                      courant=0.4, gamma=1.4, dual_energy=True, eta=0.00769,
+                      dfloor=1e-200, pfloor=1e-200)
+    n = [4, 4, 4]
+    n[axis] = 508
+    n, g, d = tuple(n), (3, 3, 3), (0.0078125,) * 3
+    lower = [0.0, 0.0, 0.0]
+    if flipped:
+        lower[axis] = -SOD_OFFSET
+    f = alloc_fields(cfg, n, g)
+    blk = oracle.numpy_block(f, n, g, d)
+    oracle.ic_shock_tube(blk, tuple(lower), cfg.gamma, "sod", aligned_ax=axis,
+                         axis_velocity=SOD_BKG_VELOCITY, flipped=flipped)
+    return cfg, f, blk, n, g, d, 0.25
+
+
+def sod_de_l1_norm(snap, axis, flipped=False):
+    """compare_to_1D_reference with --permute, --bkg_velocity, --offset_soln
+    (and --reverse for the flipped tube): the 128-cell table covers the part
+    of the domain the tube has drifted into."""
+    table = load_reference_table("sod_shock_tube_t0.25_res128.csv")
+    names = "xyz"
+    ref = {k: v.copy() for k, v in table.items()}
+    for c in names:
+        ref.setdefault("velocity_" + c, np.zeros_like(table["density"]))
+    bkg = [SOD_BKG_VELOCITY, 0.0, 0.0]
+    if flipped:                       # reverse_1D_soln (l1_error_norm.py:519-535)
+        for k in ref:
+            if k != "x":
+                ref[k] = ref[k][::-1]
+        for c in names:
+            ref["velocity_" + c] = -1.0 * ref["velocity_" + c]
+        bkg[0] = -SOD_BKG_VELOCITY
+    comps = [ref["velocity_" + c] for c in names]
+    for k in range(3):
+        ref["velocity_" + names[(axis + k) % 3]] = comps[k]
+    if axis == 1:                     # testing_utils.py:219-231
+        bkg = bkg[2:] + bkg[:2]
+    elif axis == 2:
+        bkg = bkg[1:] + bkg[:1]
+    for i, c in enumerate(names):
+        ref["velocity_" + c] = ref["velocity_" + c] + bkg[i]
+    sl = [slice(None)] * 3
+    sl[2 - axis] = slice(0, 128) if flipped else slice(380, 508)
+    shape = [1, 1, 1]
+    shape[2 - axis] = 128
+    resid = []
+    for k in SOD_FIELDS:
+        a = snap[k][tuple(sl)]
+        resid.append(np.sum(np.abs(a - ref[k].reshape(shape))) / float(a.size))
+    return float(np.sqrt(np.sum(np.square(np.array(resid)))))
+
+
+def outflow_refresh(axis, refresh_periodic, boundary):
+    """refresh of a tube: periodic across it, then outflow at its two ends"""
+    periodic_axes = 7 & ~(1 << axis)
+
+    def refresh(b):
+        refresh_periodic(b, periodic_axes)
+        boundary(b, axis, 0, "outflow")
+        boundary(b, axis, 1, "outflow")
+    return refresh
+
+
+def run_sod_de(axis, flipped=False, kind="oracle"):
+    cfg, f, blk, n, g, d, t_final = sod_de_setup(axis, flipped)
+    method = oracle.CpuMethod(cfg, g, kind=kind)
+    refresh = outflow_refresh(axis, lambda b, ax: oracle.refresh_periodic(b, 0, ax),
+                              oracle.boundary)
+    dts = evolve(method, blk, t_final, refresh, dump_times=(t_final,))
+    method.close()
+    return cfg, f, g, dts
+
+
+# ---------------------------------------------------------------------------
+# passive scalar carried by a sound wave
+# (input/vlct/passive_advect_sound_wave/*.in, run_passive_advect_sound_test.py)
+# ---------------------------------------------------------------------------
+GOLDEN_PASSIVE_SOUND = 6.918011605252798e-08
+PASSIVE_FIELDS = ["density", "velocity_x", "velocity_y", "velocity_z",
+                  "total_energy", "bfield_x", "bfield_y", "bfield_z", "red"]
+
+
+def passive_sound_setup(axis):
+    """16x4x4 cells, MHD solver with B = 0, one "color" field "red" whose mass
+    fraction is a sine a quarter wavelength out of phase with the wave."""
+    cfg = make_config(riemann="hlld", recon="plm", theta=2.0, mhd=True,
+                      courant=0.4, gamma=1.6666666666666667, n_passive=1,
+                      dfloor=1e-200, pfloor=1e-200)
+    n = [4, 4, 4]
+    n[axis] = 16
+    n, g, d = tuple(n), (3, 3, 3), (1.0 / 16,) * 3
+    f = alloc_fields(cfg, n, g, passive=("red",))
+    blk = oracle.numpy_block(f, n, g, d, ("red",))
+    x = (np.arange(n[axis] + 2 * g[axis]) - g[axis] + 0.5) * d[axis]
+    shape = [1, 1, 1]
+    shape[2 - axis] = -1
+    X = x.reshape(shape) * np.ones(f["density"].shape)
+    s = np.sin(2.0 * np.pi * X)
+    f["density"][...] = 1.0 + 1.e-6 * s
+    f["velocity_" + "xyz"[axis]][...] = -1.e-6 * s
+    f["total_energy"][...] = 1.5 * (0.6 + 1.e-6 * s) / (1.0 + 1.e-6 * s)
+    f["red"][...] = ((0.1 + 1.e-7 * np.sin(2.0 * np.pi * (X - 0.25)))
+                     * (1.0 + 1.e-6 * s))
+    return cfg, f, blk, n, g, d, 1.0
+
+
+def passive_snapshot(f, g):
+    gx, gy, gz = g
+    return {k: f[k][gz:-gz, gy:-gy, gx:-gx].copy() for k in PASSIVE_FIELDS}
+
+
+def passive_l1_norm(s0, s1):
+    resid = [np.sum(np.abs(s0[k] - s1[k])) / float(s0[k].size)
+             for k in PASSIVE_FIELDS]
+    return float(np.sqrt(np.sum(np.square(np.array(resid)))))

@@ -274,3 +274,43 @@ def test_rj2a_shock_tube_golden_on_device(axis):
         assert dts == dts2
         eq = bit_equal(f2, f)
         assert all(eq.values()), {k: v for k, v in eq.items() if not v}
+
+
+@pytest.mark.parametrize("axis,flipped", [(0, False), (0, True), (1, False),
+                                          (2, False)])
+def test_sod_dual_energy_shock_tube_golden_on_device(axis, flipped):
+    """run_dual_energy_shock_tube_test.py:64-78 (x, x reversed, y, z)"""
+    cfg, f, blk, n, g, d, t_final = P.sod_de_setup(axis, flipped)
+    run = GpuRun(cfg, f, n, g, d)
+    refresh = P.outflow_refresh(
+        axis, lambda b, ax: run.method.refresh_periodic(run.block, ax),
+        lambda b, ax, side, kind: run.method.boundary(run.block, ax, side, kind))
+    P.evolve(run, blk, t_final, refresh, dump_times=(t_final,))
+    run.download(f)
+    run.close()
+    snap = P.snapshot(cfg, f, g)
+    norm = P.sod_de_l1_norm(snap, axis, flipped)
+    assert P.golden_isclose(norm, P.GOLDEN_SOD_DE), (norm, P.GOLDEN_SOD_DE)
+    for k, a in snap.items():
+        pencil = np.moveaxis(a, 2 - axis, 0)
+        assert np.array_equal(pencil, np.broadcast_to(pencil[:, :1, :1], pencil.shape)), k
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_passive_scalar_sound_wave_golden_on_device(axis):
+    """run_passive_advect_sound_test.py:66-70, and bit-identical to the oracle"""
+    cfg, f, blk, n, g, d, t_final = P.passive_sound_setup(axis)
+    run = GpuRun(cfg, f, n, g, d, passive=("red",))
+    s0 = P.passive_snapshot(f, g)
+    dts = P.evolve(run, blk, t_final, run.refresh, dump_times=(0.0, t_final))
+    run.download(f)
+    run.close()
+    norm = P.passive_l1_norm(s0, P.passive_snapshot(f, g))
+    assert P.golden_isclose(norm, P.GOLDEN_PASSIVE_SOUND), norm
+    cfg2, f2, blk2, *_ = P.passive_sound_setup(axis)
+    m = oracle.CpuMethod(cfg2, g)
+    dts2 = P.evolve(m, blk2, t_final, lambda b: oracle.refresh_periodic(b, 1),
+                    dump_times=(0.0, t_final))
+    m.close()
+    assert dts == dts2
+    assert all(bit_equal(f2, f).values())

@@ -173,3 +173,24 @@ def test_compiled_reference_reproduces_rj2a_golden():
     table = P.load_reference_table("rj2a_shock_tube_t0.2_res256.csv")
     norm = P.table_l1_norm(P.snapshot(cfg, f, g), table, 0, P.RJ2A_FIELDS)
     assert P.golden_isclose(norm, P.GOLDEN_RJ2A[0])
+
+
+def test_sod_dual_energy_shock_tube_golden():
+    """Sod tube in a Mach-10 frame with the dual-energy formalism (MHD solver,
+    B = 0): golden norm of run_dual_energy_shock_tube_test.py:64-78"""
+    cfg, f, g, dts = P.run_sod_de(0)
+    norm = P.sod_de_l1_norm(P.snapshot(cfg, f, g), 0)
+    assert P.golden_isclose(norm, P.GOLDEN_SOD_DE), (norm, P.GOLDEN_SOD_DE)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_passive_scalar_sound_wave_golden(axis):
+    """run_passive_advect_sound_test.py:66-70"""
+    cfg, f, blk, n, g, d, t_final = P.passive_sound_setup(axis)
+    m = oracle.CpuMethod(cfg, g)
+    s0 = P.passive_snapshot(f, g)
+    P.evolve(m, blk, t_final, lambda b: oracle.refresh_periodic(b, 1),
+             dump_times=(0.0, t_final))
+    m.close()
+    norm = P.passive_l1_norm(s0, P.passive_snapshot(f, g))
+    assert P.golden_isclose(norm, P.GOLDEN_PASSIVE_SOUND), norm
