@@ -44,6 +44,17 @@ struct vlct_handle {
   bool have_mirror = false;
   vlct_block mirror;
   std::vector<void*> mirror_allocs;
+  // stacked device copy of a batch of blocks (vlct_compute_batch)
+  vlct_block arena;
+  int arena_capacity = 0;                 // blocks the arena / scratch can hold
+  std::vector<void*> arena_allocs;
+  double** d_ptr_table = nullptr;         // device: [field][block] user pointers
+  double** h_ptr_table = nullptr;         // pinned staging of the same
+  bool ptr_table_valid = false;           // device table == staging, for ptr_table_nb
+  int ptr_table_nb = 0;
+  size_t ptr_table_count = 0;
+  size_t scratch_levels = 0;              // z levels the scratch arrays hold
+  long long batch_max_blocks = 1024;
   long long launches = 0;
   long long copied_bytes[2] = { 0, 0 };   // H2D, D2H staged for HOST blocks
   Profiler prof;
@@ -71,21 +82,28 @@ int fail(vlct_handle* h, int code, const char* fmt, ...)
                   cudaGetErrorString(err__), __FILE__, __LINE__);            \
   } while (0)
 
-int dev_alloc(vlct_handle* h, double** out, size_t count, bool scratch = true)
+enum Pool { POOL_SCRATCH = 1, POOL_MIRROR = 0, POOL_ARENA = 2 };
+
+int dev_alloc(vlct_handle* h, double** out, size_t count, int pool = POOL_SCRATCH)
 {
   void* p = nullptr;
   CUDA_TRY(h, cudaMalloc(&p, count * sizeof(double)));
   CUDA_TRY(h, cudaMemset(p, 0, count * sizeof(double)));
-  (scratch ? h->allocations : h->mirror_allocs).push_back(p);
-  if (scratch) h->scratch_bytes += (long long) (count * sizeof(double));
+  (pool == POOL_SCRATCH ? h->allocations
+   : pool == POOL_MIRROR ? h->mirror_allocs : h->arena_allocs).push_back(p);
+  if (pool == POOL_SCRATCH) h->scratch_bytes += (long long) (count * sizeof(double));
   *out = (double*) p;
   return VLCT_OK;
 }
 
+/// elements of a (possibly stacked, Geom::levels) cell- / face-centred array
+size_t cell_count(const Geom& G)
+{ return (size_t) G.mx * (size_t) G.my * G.levels(); }
+
 size_t face_count(const Geom& G, int d)
 {
   return (size_t) (G.mx + (d == 0)) * (size_t) (G.my + (d == 1)) *
-         (size_t) (G.mz + (d == 2));
+         (G.levels() + (d == 2));
 }
 
 /// EnzoVlctScratchSpace (hydro-mhd/EnzoMethodMHDVlct.hpp:217-312) +
@@ -94,7 +112,8 @@ size_t face_count(const Geom& G, int d)
 int alloc_scratch(vlct_handle* h, const Geom& G)
 {
   h->G = G;
-  const size_t n = G.cells();
+  h->scratch_levels = G.levels();
+  const size_t n = cell_count(G);
   const Params& P = h->P;
   Scratch& S = h->S;
   memset(&S, 0, sizeof(S));
@@ -130,6 +149,27 @@ int alloc_scratch(vlct_handle* h, const Geom& G)
   // non-blocking stream that does not order against it
   CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
   return VLCT_OK;
+}
+
+/// The reference sizes its scratch from the first block and reuses it for
+/// every later one (EnzoMethodMHDVlct.cpp:236-246): one shape per handle. A
+/// batch of stacked blocks needs more z levels of the same shape; the scratch
+/// then grows (it never shrinks).
+int ensure_scratch(vlct_handle* h, const Geom& G)
+{
+  if (h->G.mx != 0 && (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz))
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "all blocks handled by one handle must share one shape "
+                "(first block was %dx%dx%d incl. ghosts, got %dx%dx%d)",
+                h->G.mx, h->G.my, h->G.mz, G.mx, G.my, G.mz);
+  if (h->G.mx != 0 && G.levels() <= h->scratch_levels) return VLCT_OK;
+  if (h->G.mx != 0) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (void* p : h->allocations) cudaFree(p);
+    h->allocations.clear();
+    h->scratch_bytes = 0;
+  }
+  return alloc_scratch(h, G);
 }
 
 int check_block(vlct_handle* h, const vlct_block* b, bool for_timestep)
@@ -212,7 +252,7 @@ const FieldRef kFields[] = {
 constexpr int kNumFields = (int) (sizeof(kFields) / sizeof(kFields[0]));
 
 size_t field_count(const Geom& G, int face)
-{ return face < 0 ? G.cells() : face_count(G, face); }
+{ return face < 0 ? cell_count(G) : face_count(G, face); }
 
 int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
 {
@@ -224,7 +264,7 @@ int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
     h->mirror.*(kFields[f].member) = nullptr;
     if (b->*(kFields[f].member) == nullptr) continue;
     double* p;
-    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), false)) != VLCT_OK)
+    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), POOL_MIRROR)) != VLCT_OK)
       return rc;
     h->mirror.*(kFields[f].member) = p;
   }
@@ -232,7 +272,7 @@ int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
     h->mirror.passive[s] = nullptr;
     if (s < h->P.nsc) {
       double* p;
-      if ((rc = dev_alloc(h, &p, G.cells(), false)) != VLCT_OK) return rc;
+      if ((rc = dev_alloc(h, &p, G.cells(), POOL_MIRROR)) != VLCT_OK) return rc;
       h->mirror.passive[s] = p;
     }
   }
@@ -484,6 +524,9 @@ void vlct_destroy(vlct_handle* h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void* p : h->allocations) cudaFree(p);
     for (void* p : h->mirror_allocs) cudaFree(p);
+    for (void* p : h->arena_allocs) cudaFree(p);
+    if (h->d_ptr_table) cudaFree(h->d_ptr_table);
+    if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
     if (h->d_dt_bits) cudaFree(h->d_dt_bits);
     if (h->d_step) cudaFree(h->d_step);
     if (h->h_dt_bits) cudaFreeHost(h->h_dt_bits);
@@ -571,15 +614,7 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
   int rc = check_block(h, b, false);
   if (rc != VLCT_OK) return rc;
   const Geom G = geom_of(b);
-  if (h->G.mx == 0) {
-    if ((rc = alloc_scratch(h, G)) != VLCT_OK) return rc;
-  } else if (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz) {
-    // the reference sizes its scratch from the first block and reuses it
-    return fail(h, VLCT_ERR_INVALID_BLOCK,
-                "all blocks handled by one handle must share one shape "
-                "(first block was %dx%dx%d incl. ghosts, got %dx%dx%d)",
-                h->G.mx, h->G.my, h->G.mz, G.mx, G.my, G.mz);
-  }
+  if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
   if (b->mem_space == VLCT_MEM_DEVICE) {
     cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
     if (h->device_pipeline_levels > 0 && h->cfg.time_scheme != VLCT_TIME_EULER)
@@ -739,12 +774,268 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   return VLCT_OK;
 }
 
+// ---- batches of equally shaped blocks ---------------------------------------
+}  // extern "C"
+
+namespace {
+
+/// every block of a batch must look like the first one
+int check_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
+                bool for_timestep)
+{
+  if (blocks == nullptr || nblocks <= 0)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "empty batch");
+  int rc;
+  const vlct_block& b0 = blocks[0];
+  for (int n = 0; n < nblocks; n++) {
+    const vlct_block& b = blocks[n];
+    if ((rc = check_block(h, &b, for_timestep)) != VLCT_OK) return rc;
+    if (b.nx != b0.nx || b.ny != b0.ny || b.nz != b0.nz || b.gx != b0.gx ||
+        b.gy != b0.gy || b.gz != b0.gz || b.dx != b0.dx || b.dy != b0.dy ||
+        b.dz != b0.dz || b.mem_space != b0.mem_space || b.stream != b0.stream)
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "block %d of the batch differs from block 0 in shape, cell "
+                  "width, mem_space or stream", n);
+    for (int f = 0; f < kNumFields; f++)
+      if ((b.*(kFields[f].member) == nullptr) != (b0.*(kFields[f].member) == nullptr))
+        return fail(h, VLCT_ERR_INVALID_BLOCK,
+                    "block %d of the batch does not have the same fields as block 0", n);
+  }
+  return VLCT_OK;
+}
+
+/// stacked device arrays for `nrep` blocks shaped like b0 (grow-only)
+int ensure_arena(vlct_handle* h, const vlct_block& b0, const Geom& G)
+{
+  bool enough = (h->arena_capacity >= G.nrep);
+  for (int f = 0; enough && f < kNumFields; f++)
+    if (b0.*(kFields[f].member) != nullptr && h->arena.*(kFields[f].member) == nullptr)
+      enough = false;     // a field the arena was not built with
+  if (enough) {
+    // shape is fixed per handle; cell widths may change from batch to batch
+    h->arena.dx = b0.dx; h->arena.dy = b0.dy; h->arena.dz = b0.dz;
+    return VLCT_OK;
+  }
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  h->ptr_table_valid = false;
+  for (void* p : h->arena_allocs) cudaFree(p);
+  h->arena_allocs.clear();
+  h->arena = b0;
+  h->arena.mem_space = VLCT_MEM_DEVICE;
+  int rc;
+  for (int f = 0; f < kNumFields; f++) {
+    h->arena.*(kFields[f].member) = nullptr;
+    if (b0.*(kFields[f].member) == nullptr) continue;
+    double* p;
+    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), POOL_ARENA)) != VLCT_OK)
+      return rc;
+    h->arena.*(kFields[f].member) = p;
+  }
+  for (int s = 0; s < VLCT_MAX_PASSIVE; s++) {
+    h->arena.passive[s] = nullptr;
+    if (s < h->P.nsc) {
+      double* p;
+      if ((rc = dev_alloc(h, &p, cell_count(G), POOL_ARENA)) != VLCT_OK) return rc;
+      h->arena.passive[s] = p;
+    }
+  }
+  const size_t need = (size_t) (kNumFields + VLCT_MAX_PASSIVE) * (size_t) G.nrep;
+  if (need > h->ptr_table_count) {
+    if (h->d_ptr_table) cudaFree(h->d_ptr_table);
+    if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
+    CUDA_TRY(h, cudaMalloc((void**) &h->d_ptr_table, need * sizeof(double*)));
+    CUDA_TRY(h, cudaMallocHost((void**) &h->h_ptr_table, need * sizeof(double*)));
+    h->ptr_table_count = need;
+    h->ptr_table_valid = false;
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
+  h->arena_capacity = G.nrep;
+  return VLCT_OK;
+}
+
+/// Move a set of fields between the blocks of a batch and the stacked arena:
+/// HOST blocks by one cudaMemcpyAsync per (block, field), DEVICE blocks by one
+/// gather / scatter kernel per field over a device table of the blocks' pointers.
+int batch_copy(vlct_handle* h, const vlct_block* blocks, int nb, const Geom& G,
+               cudaStream_t st, bool to_arena, CopySet set)
+{
+  const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
+  const Geom one{ G.mx, G.my, G.mz, 1, 0 };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  // pointer table (DEVICE blocks): row = field slot, column = block
+  if (!host) {
+    auto entry = [&](int slot, int n) -> double* {
+      return slot < kNumFields ? blocks[n].*(kFields[slot].member)
+                               : blocks[n].passive[slot - kNumFields];
+    };
+    const int nslots = kNumFields + h->P.nsc;
+    bool same = h->ptr_table_valid && h->ptr_table_nb == nb;
+    for (int f = 0; same && f < nslots; f++)
+      for (int n = 0; same && n < nb; n++)
+        if (h->h_ptr_table[(size_t) f * nb + n] != entry(f, n)) same = false;
+    if (!same) {
+      // the staging buffer may still be the source of an upload in flight
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      for (int f = 0; f < nslots; f++)
+        for (int n = 0; n < nb; n++)
+          h->h_ptr_table[(size_t) f * nb + n] = entry(f, n);
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_ptr_table, h->h_ptr_table,
+                                  (size_t) nslots * nb * sizeof(double*),
+                                  cudaMemcpyHostToDevice, st));
+      h->ptr_table_valid = true;
+      h->ptr_table_nb = nb;
+    }
+  }
+  auto move = [&](int slot, double* stacked, int face,
+                  double* vlct_block::*member, int passive) -> int {
+    const size_t count = field_count(one, face);
+    const size_t plane = (size_t) (G.mx + (face == 0)) * (size_t) (G.my + (face == 1));
+    const size_t stride = plane * (size_t) G.zper;
+    if (!host) {
+      launch_batch_copy(ctx, stacked, h->d_ptr_table + (size_t) slot * nb, nb, count,
+                        stride, to_arena);
+      return VLCT_OK;
+    }
+    for (int n = 0; n < nb; n++) {
+      double* hp = passive >= 0 ? blocks[n].passive[passive] : blocks[n].*member;
+      double* dp = stacked + (size_t) n * stride;
+      CUDA_TRY(h, cudaMemcpyAsync(to_arena ? (void*) dp : (void*) hp,
+                                  to_arena ? (void*) hp : (void*) dp,
+                                  count * sizeof(double),
+                                  to_arena ? cudaMemcpyHostToDevice
+                                           : cudaMemcpyDeviceToHost, st));
+      h->copied_bytes[to_arena ? 0 : 1] += (long long) (count * sizeof(double));
+    }
+    return VLCT_OK;
+  };
+  int rc;
+  for (int f = 0; f < kNumFields; f++) {
+    double* stacked = h->arena.*(kFields[f].member);
+    if (stacked == nullptr || blocks[0].*(kFields[f].member) == nullptr) continue;
+    if (!in_copy_set(h, kFields[f].member, set)) continue;
+    if ((rc = move(f, stacked, kFields[f].face, kFields[f].member, -1)) != VLCT_OK)
+      return rc;
+  }
+  for (int s = 0; s < h->P.nsc; s++)
+    if ((rc = move(kNumFields + s, h->arena.passive[s], -1, nullptr, s)) != VLCT_OK)
+      return rc;
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
+/// sub-batch size: gridDim.y carries (z levels) x (blocks)
+int batch_chunk(const vlct_handle* h, const Geom& G)
+{
+  long long cap = 65535 / (G.mz + 1);
+  if (cap > h->batch_max_blocks) cap = h->batch_max_blocks;
+  return cap < 1 ? 1 : (int) cap;
+}
+
+Geom stacked_geom(const vlct_block& b0, int nrep)
+{
+  Geom G = geom_of(&b0);
+  G.nrep = nrep;
+  G.zper = G.mz + 1;
+  return G;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  int rc = check_batch(h, blocks, nblocks, false);
+  if (rc != VLCT_OK) return rc;
+  const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
+  cudaStream_t st = (!host && blocks[0].stream) ? (cudaStream_t) blocks[0].stream
+                                                 : h->own_stream;
+  const int chunk = batch_chunk(h, geom_of(&blocks[0]));
+  for (int first = 0; first < nblocks; first += chunk) {
+    const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
+    const Geom G = stacked_geom(blocks[0], nb);
+    if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
+    if ((rc = ensure_arena(h, blocks[0], G)) != VLCT_OK) return rc;
+    if ((rc = batch_copy(h, blocks + first, nb, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK)
+      return rc;
+    if ((rc = compute_on_device(h, &h->arena, G, dt, nullptr, st)) != VLCT_OK) return rc;
+    if ((rc = batch_copy(h, blocks + first, nb, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK)
+      return rc;
+    // the pointer table and the arena are reused by the next sub-batch
+    if (host || first + chunk < nblocks) CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  return VLCT_OK;
+}
+
+int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
+                        double* dt_out)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
+  if (dt_out == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_out is NULL");
+  int rc = check_batch(h, blocks, nblocks, true);
+  if (rc != VLCT_OK) return rc;
+  const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
+  cudaStream_t st = (!host && blocks[0].stream) ? (cudaStream_t) blocks[0].stream
+                                                 : h->own_stream;
+  const int chunk = batch_chunk(h, geom_of(&blocks[0]));
+  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  for (int first = 0; first < nblocks; first += chunk) {
+    const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
+    const Geom G = stacked_geom(blocks[0], nb);
+    if ((rc = ensure_arena(h, blocks[0], G)) != VLCT_OK) return rc;
+    if ((rc = batch_copy(h, blocks + first, nb, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK)
+      return rc;
+    // the minimum accumulates over the sub-batches
+    if ((rc = timestep_launch(h, &h->arena, G, st, kNoClip, first == 0)) != VLCT_OK)
+      return rc;
+    // timestep writes "pressure" and (dual energy) total / internal energy
+    {
+      const vlct_block* bb = blocks + first;
+      const size_t stride = (size_t) G.mx * G.my * (size_t) G.zper;
+      const size_t count = (size_t) G.mx * G.my * (size_t) G.mz;
+      double* vlct_block::* const outs[3] = { &vlct_block::pressure,
+                                              &vlct_block::total_energy,
+                                              &vlct_block::internal_energy };
+      const int nout = h->P.de ? 3 : 1;
+      for (int o = 0; o < nout; o++) {
+        if (host) {
+          for (int n = 0; n < nb; n++) {
+            CUDA_TRY(h, cudaMemcpyAsync(bb[n].*(outs[o]),
+                                        h->arena.*(outs[o]) + (size_t) n * stride,
+                                        count * sizeof(double), cudaMemcpyDeviceToHost, st));
+            h->copied_bytes[1] += (long long) (count * sizeof(double));
+          }
+        } else {
+          int slot = 0;
+          for (int f = 0; f < kNumFields; f++) if (kFields[f].member == outs[o]) slot = f;
+          launch_batch_copy(ctx, h->arena.*(outs[o]), h->d_ptr_table + (size_t) slot * nb,
+                            nb, count, stride, false);
+        }
+      }
+    }
+    if (first + chunk < nblocks) CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  double dt_min;
+  memcpy(&dt_min, h->h_dt_bits, sizeof(double));
+  *dt_out = dt_min * h->cfg.courant;
+  return VLCT_OK;
+}
+
 int vlct_set_option(vlct_handle* h, const char* key, long long value)
 {
   if (h == nullptr || key == nullptr) return VLCT_ERR_INVALID_CONFIG;
   if (strcmp(key, "host_pipeline_levels") == 0) {
     if (value < -1) return fail(h, VLCT_ERR_INVALID_CONFIG, "host_pipeline_levels >= -1");
     h->host_pipeline_levels = value;
+  } else if (strcmp(key, "batch_max_blocks") == 0) {
+    if (value < 1) return fail(h, VLCT_ERR_INVALID_CONFIG, "batch_max_blocks >= 1");
+    h->batch_max_blocks = value;
   } else if (strcmp(key, "device_pipeline_levels") == 0) {
     if (value < 0) return fail(h, VLCT_ERR_INVALID_CONFIG, "device_pipeline_levels >= 0");
     h->device_pipeline_levels = value;
@@ -775,12 +1066,7 @@ int vlct_compute_dev_part(vlct_handle* h, const vlct_block* b,
     return fail(h, VLCT_ERR_INVALID_BLOCK,
                 "interior range [%d,%d) must satisfy gz+%d <= z_lo < z_hi <= mz-gz-%d",
                 z_lo, z_hi, kStartReach, kEndReach);
-  if (h->G.mx == 0) {
-    if ((rc = alloc_scratch(h, G)) != VLCT_OK) return rc;
-  } else if (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz) {
-    return fail(h, VLCT_ERR_INVALID_BLOCK,
-                "all blocks handled by one handle must share one shape");
-  }
+  if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
   cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
   const ZCut none{ CUT_NONE, 0 }, start{ CUT_START, z_lo }, end{ CUT_END, z_hi };
   switch (part) {

@@ -37,6 +37,21 @@ inline bool clip_z(Box& b, const ZClip& zc)
   return !empty(b);
 }
 
+/// z levels a launch covers over all stacked blocks
+inline unsigned stacked_nz(const Geom& G, const Box& b)
+{ return (unsigned) (b.hi[2] - b.lo[2]) * (unsigned) G.nrep; }
+
+/// stacked level number kk in [0, nz * nrep) -> the level inside its block
+/// (for index-box tests) and the level in the stacked arrays (for indexing)
+__device__ __forceinline__ void unstack(const Geom& G, const Box& b, unsigned kk,
+                                        int& k_local, int& k_global)
+{
+  const unsigned nz = (unsigned) (b.hi[2] - b.lo[2]);
+  const unsigned r = kk / nz;
+  k_local = b.lo[2] + (int) (kk - r * nz);
+  k_global = k_local + (int) r * G.zper;
+}
+
 __device__ __forceinline__ size_t cidx(const Geom& G, int k, int j, int i)
 { return ((size_t) k * (size_t) G.my + (size_t) j) * (size_t) G.mx + (size_t) i; }
 

@@ -186,9 +186,11 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nfx = box.hi[0] - box.lo[0];
   const int wpr = (nfx + FPW - 1) / FPW;  // warps per row
-  const int nyb = box.hi[1] - box.lo[1], nzb = box.hi[2] - box.lo[2];
+  const int nyb = box.hi[1] - box.lo[1];
+  // rows of all stacked blocks (G.nrep = 1 for a single block)
+  const unsigned nzs = (unsigned) (box.hi[2] - box.lo[2]) * (unsigned) G.nrep;
   // (32-bit index arithmetic: the launcher checks that the counts fit)
-  const unsigned nrows = (unsigned) nyb * (unsigned) nzb;
+  const unsigned nrows = (unsigned) nyb * nzs;
   const unsigned ngroups = (nrows + kXRows - 1) / kXRows;
   const unsigned gw = blockIdx.x * kXWarps + w;
   if (gw >= (unsigned) wpr * ngroups) return;
@@ -208,14 +210,18 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   } else if (lane == 0) { ecell = f0 + 32; epos = 32; }
   if (ecell >= G.mx) ecell = -1;
 
-  // (j,k) of the current row, advanced incrementally
+  // (j,k) of the current and of the next row (k: level in the stacked arrays)
   int j = box.lo[1] + (int) (row0 % (unsigned) nyb);
-  int k = box.lo[2] + (int) (row0 / (unsigned) nyb);
+  int kl, k;
+  unstack(G, box, row0 / (unsigned) nyb, kl, k);
 #pragma unroll 1
   for (unsigned row = row0; row < row1; row++) {
     const size_t rowbase = cidx(G, k, j, 0);
     const int jc = j, kc = k;
-    if (++j == box.hi[1]) { j = box.lo[1]; k++; }
+    if (++j == box.hi[1]) {
+      j = box.lo[1];
+      unstack(G, box, (row + 1) / (unsigned) nyb, kl, k);
+    }
     if (row + 1 < row1 && i < G.mx) {
       prefetch_cell<MHD, DE>(u, cidx(G, k, j, i));
       if (MHD) prefetch_l1(bi + fidx(G, 0, k, j, i + 1));
@@ -288,14 +294,29 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   constexpr bool PLM = (RECON != RECON_NN);
   constexpr int OD = (DIM == 1) ? 2 : 1;   // the non-x, non-sweep axis
 
+  // Stacked blocks (G.nrep > 1) repeat the box along z: for the y sweep z is
+  // the column axis `o`, for the z sweep it is the march axis.
   const int nxb = box.hi[0] - box.lo[0];
-  const int nob = box.hi[OD] - box.lo[OD];
+  const unsigned nob = (unsigned) (box.hi[OD] - box.lo[OD]) *
+                       (DIM == 1 ? (unsigned) G.nrep : 1u);
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (unsigned) nxb * (unsigned) nob) return;
+  if (t >= (unsigned) nxb * nob) return;
   const int i = box.lo[0] + (int) (t % (unsigned) nxb);
-  const int o = box.lo[OD] + (int) (t / (unsigned) nxb);
-  const int f0 = box.lo[DIM] + (int) blockIdx.y * chunk;
-  const int f1 = min(f0 + chunk, box.hi[DIM]);
+  int o, zshift = 0;
+  if (DIM == 1) {
+    int ol;
+    unstack(G, box, t / (unsigned) nxb, ol, o);
+  } else {
+    o = box.lo[OD] + (int) (t / (unsigned) nxb);
+    // blockIdx.y = (block of the batch) * chunks_per_block + chunk
+    const unsigned cpb = gridDim.y / (unsigned) G.nrep;
+    zshift = (int) (blockIdx.y / cpb) * G.zper;
+  }
+  const int cy = (DIM == 1) ? (int) blockIdx.y
+                            : (int) (blockIdx.y % (gridDim.y / (unsigned) G.nrep));
+  const int fl0 = box.lo[DIM] + cy * chunk;          // inside the block
+  const int f0 = fl0 + zshift;                       // in the stacked arrays
+  const int f1 = min(fl0 + chunk, box.hi[DIM]) + zshift;
   const int j = (DIM == 1) ? f0 : o, k = (DIM == 1) ? o : f0;
   // cell stride along the sweep; the face-centred array of component DIM has
   // the same stride along DIM, and face f sits at index f+1
@@ -319,7 +340,7 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
     load_cell<DIM, MHD, DE>(P, u, c, Wc);
   }
 
-  const int mdim = (DIM == 1) ? G.my : G.mz;
+  const int mdim = (DIM == 1) ? G.my : (int) G.levels();
   constexpr int kAhead = 2;                 // prefetch distance, in faces
 #pragma unroll 1
   for (int f = f0; f < f1; f++, c += sd, fb += sd) {
@@ -370,7 +391,8 @@ void flux_go(const FluxLaunch& L)
   if constexpr (DIM == 0) {
     constexpr int fpw = (RECON != RECON_NN) ? 31 : 32;   // k_flux_x: FPW
     const long long wpr = (b.hi[0] - b.lo[0] + fpw - 1) / fpw;
-    const long long rows = (long long) (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    const long long rows = (long long) (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]) *
+                           L.G.nrep;
     const long long warps = wpr * ((rows + kXRows - 1) / kXRows);
     const unsigned grid = (unsigned) ((warps + kXWarps - 1) / kXWarps);
     k_flux_x<RECON, SOLVER, DE><<<grid, kXWarps * 32, 0, L.st>>>(
@@ -378,14 +400,16 @@ void flux_go(const FluxLaunch& L)
   } else {
     constexpr int D = DIM;
     const int od = (D == 1) ? 2 : 1;
-    const long long cols = (long long) (b.hi[0] - b.lo[0]) * (b.hi[od] - b.lo[od]);
+    const long long cols = (long long) (b.hi[0] - b.lo[0]) * (b.hi[od] - b.lo[od]) *
+                           (D == 1 ? L.G.nrep : 1);
     const int nf = b.hi[D] - b.lo[D];
     // chunks along the march: enough blocks for many waves, long enough that
     // the 2-3 warm-up cells per chunk stay a small overhead
     int chunk = 64;
     if (nf < 2 * chunk) chunk = nf;
     const unsigned gx = (unsigned) ((cols + kMarchThreads - 1) / kMarchThreads);
-    const unsigned gy = (unsigned) ((nf + chunk - 1) / chunk);
+    const unsigned gy = (unsigned) ((nf + chunk - 1) / chunk) *
+                        (D == 2 ? (unsigned) L.G.nrep : 1u);
     k_flux_march<D, RECON, SOLVER, DE><<<dim3(gx, gy), kMarchThreads, 0, L.st>>>(
         L.P, L.G, L.cur, L.spec, L.bi, L.F, b, chunk);
   }

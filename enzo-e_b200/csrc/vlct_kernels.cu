@@ -33,19 +33,22 @@ namespace {
 // boxes would otherwise waste 10-20 % of the threads), blockIdx.y is z.
 constexpr int kBlock = 256;
 
-inline dim3 grid_for(const Box& b)
+inline dim3 grid_for(const Geom& G, const Box& b)
 {
-  const unsigned nx = b.hi[0] - b.lo[0], ny = b.hi[1] - b.lo[1], nz = b.hi[2] - b.lo[2];
-  return dim3((nx * ny + kBlock - 1) / kBlock, nz, 1);
+  const unsigned nx = b.hi[0] - b.lo[0], ny = b.hi[1] - b.lo[1];
+  return dim3((nx * ny + kBlock - 1) / kBlock, stacked_nz(G, b), 1);
 }
 
-#define VLCT_THREAD_IN_BOX(box, i, j, k)                                       \
+// i, j: x / y index; kl: z level inside the block (what index boxes are tested
+// against); k: z level in the (possibly stacked) arrays
+#define VLCT_THREAD_IN_BOX(G, box, i, j, kl, k)                                \
   const unsigned nxb__ = (box).hi[0] - (box).lo[0];                            \
   const unsigned t__ = blockIdx.x * kBlock + threadIdx.x;                      \
   if (t__ >= nxb__ * (unsigned) ((box).hi[1] - (box).lo[1])) return;           \
   const int i = (box).lo[0] + (int) (t__ % nxb__);                             \
   const int j = (box).lo[1] + (int) (t__ / nxb__);                             \
-  const int k = (box).lo[2] + (int) blockIdx.y;
+  int kl, k;                                                                   \
+  unstack((G), (box), blockIdx.y, kl, k);
 
 // ---------------------------------------------------------------------------
 // specific passive scalars: EnzoPhysicsFluidProps::primitive_from_integration
@@ -56,7 +59,8 @@ __global__ void __launch_bounds__(kBlock)
 k_specific_scalars(const int nsc, const Geom G, const State u,
                    const ScalarPtrs spec, const Box box)
 {
-  VLCT_THREAD_IN_BOX(box, i, j, k);
+  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
+  (void) kl;
   const size_t c = cidx(G, k, j, i);
   const double rho = __ldg(u.rho + c);
   for (int s = 0; s < nsc; s++)
@@ -86,12 +90,12 @@ __device__ __forceinline__ double upwind_weight(double dflux)
 
 template <int D>
 __device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
-                                               int k, int j, int i)
+                                               int kl, int k, int j, int i)
 {
   constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
   const Box& bx = A.box[D];
   if (i < bx.lo[0] || i >= bx.hi[0] || j < bx.lo[1] || j >= bx.hi[1] ||
-      k < bx.lo[2] || k >= bx.hi[2]) return;
+      kl < bx.lo[2] || kl >= bx.hi[2]) return;
   const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
   const ptrdiff_t sj = st[JD], sk = st[KD];
   const size_t c = cidx(G, k, j, i);
@@ -131,10 +135,10 @@ __global__ void __launch_bounds__(kBlock)
 #endif
 k_edge_efield(const Geom G, const EdgeArgs A, const Box box)
 {
-  VLCT_THREAD_IN_BOX(box, i, j, k);
-  edge_component<0>(G, A, k, j, i);
-  edge_component<1>(G, A, k, j, i);
-  edge_component<2>(G, A, k, j, i);
+  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
+  edge_component<0>(G, A, kl, k, j, i);
+  edge_component<1>(G, A, kl, k, j, i);
+  edge_component<2>(G, A, kl, k, j, i);
 }
 
 struct FaceArgs {
@@ -147,12 +151,12 @@ struct FaceArgs {
 
 template <int D>
 __device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
-                                               int k, int j, int i)
+                                               int kl, int k, int j, int i)
 {
   constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
   const Box& bx = A.box[D];
   if (i < bx.lo[0] || i >= bx.hi[0] || j < bx.lo[1] || j >= bx.hi[1] ||
-      k < bx.lo[2] || k >= bx.hi[2]) return;
+      kl < bx.lo[2] || kl >= bx.hi[2]) return;
   const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
   // face f along D is edge index f-1 along D
   const size_t e = cidx(G, k - (D == 2), j - (D == 1), i - (D == 0));
@@ -167,10 +171,10 @@ __device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
 __global__ void __launch_bounds__(kBlock)
 k_face_bfield(const Geom G, const FaceArgs A, const Box box)
 {
-  VLCT_THREAD_IN_BOX(box, i, j, k);
-  face_component<0>(G, A, k, j, i);
-  face_component<1>(G, A, k, j, i);
-  face_component<2>(G, A, k, j, i);
+  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
+  face_component<0>(G, A, kl, k, j, i);
+  face_component<1>(G, A, kl, k, j, i);
+  face_component<2>(G, A, kl, k, j, i);
 }
 
 // ---------------------------------------------------------------------------
@@ -230,7 +234,7 @@ template <bool MHD, bool DE>
 __global__ void __launch_bounds__(kBlock)
 k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
 {
-  VLCT_THREAD_IN_BOX(box, i, j, k);
+  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
   const size_t c = cidx(G, k, j, i);
   const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
 
@@ -249,7 +253,7 @@ k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
 
   const Box& in = A.inner;
   if (i < in.lo[0] || i >= in.hi[0] || j < in.lo[1] || j >= in.hi[1] ||
-      k < in.lo[2] || k >= in.hi[2]) return;
+      kl < in.lo[2] || kl >= in.hi[2]) return;
 
   const double dtd[3] = { __ldg(A.sp), __ldg(A.sp + 1), __ldg(A.sp + 2) };
   // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
@@ -329,12 +333,14 @@ template <bool MHD, bool DE>
 __global__ void __launch_bounds__(256)
 k_timestep(const Params P, const Geom G, const State u, double* pressure,
            double dx, double dy, double dz, unsigned long long* dt_bits,
-           const size_t c_begin, const size_t c_end)
+           const size_t c_begin, const size_t c_end, const size_t rep_stride)
 {
-  const size_t n = c_end;
+  // blockIdx.y = block of a stacked batch (cells [c_begin, c_end) of each)
+  const size_t shift = (size_t) blockIdx.y * rep_stride;
+  const size_t n = c_end + shift;
   double local_min = DBL_MAX;
-  for (size_t c = c_begin + (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < n;
-       c += (size_t) gridDim.x * blockDim.x) {
+  for (size_t c = c_begin + shift + (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+       c < n; c += (size_t) gridDim.x * blockDim.x) {
     const double rho = u.rho[c];
     const double vx = u.vx[c], vy = u.vy[c], vz = u.vz[c];
     double bx = 0., by = 0., bz = 0.;
@@ -474,6 +480,22 @@ k_boundary_axis(double* p, int n0, int n1, int n2, int axis, int n, int g,
   }
 }
 
+/// gather the blocks of a batch into their stacked array, or scatter them back:
+/// blockIdx.y = block; ptrs[block] = that block's own (device) array of `count`
+/// elements, stacked at stride `stride`
+__global__ void __launch_bounds__(256)
+k_batch_copy(double* __restrict__ stacked, double* const* __restrict__ ptrs,
+             size_t count, size_t stride, int to_stacked)
+{
+  double* p = ptrs[blockIdx.y];
+  double* q = stacked + (size_t) blockIdx.y * stride;
+  for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < count;
+       t += (size_t) gridDim.x * blockDim.x) {
+    if (to_stacked) q[t] = p[t];
+    else            p[t] = q[t];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
             double* buffer, int pack)
@@ -548,7 +570,7 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
   Box box = full_box(G, stale);
   if (!clip_z(box, zc)) return;
   ScopedLaunch sl(ctx, "k_specific_scalars");
-  k_specific_scalars<<<grid_for(box), kBlock, 0, ctx.st>>>(
+  k_specific_scalars<<<grid_for(G, box), kBlock, 0, ctx.st>>>(
       P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
 }
 
@@ -580,7 +602,7 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     // clips all three)
     if (clip_z(box, z_edge)) {
       ScopedLaunch sl(ctx, "k_edge_efield");
-      k_edge_efield<<<grid_for(box), block, 0, st>>>(G, A, box);
+      k_edge_efield<<<grid_for(G, box), block, 0, st>>>(G, A, box);
     }
   }
   {
@@ -600,7 +622,7 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
     if (clip_z(box, z_face)) {
       ScopedLaunch sl(ctx, "k_face_bfield");
-      k_face_bfield<<<grid_for(box), block, 0, st>>>(G, A, box);
+      k_face_bfield<<<grid_for(G, box), block, 0, st>>>(G, A, box);
     }
   }
 }
@@ -627,7 +649,7 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   // with CT the centred B is rewritten on the whole [s, m-s)^3 region
   Box box = P.mhd ? full_box(G, s) : A.inner;
   if (!clip_z(box, zc)) return;
-  const int block = kBlock; const dim3 grid = grid_for(box);
+  const int block = kBlock; const dim3 grid = grid_for(G, box);
   ScopedLaunch sl(ctx, "k_update");
   if (P.mhd) {
     if (P.de) k_update<true, true><<<grid, block, 0, st>>>(P, G, A, box);
@@ -654,16 +676,18 @@ void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
   const size_t plane = (size_t) G.mx * (size_t) G.my;
   const size_t c0 = plane * (size_t) zlo, c1 = plane * (size_t) zhi;
   const size_t n = c1 - c0;
-  int blocks = (int) ((n + 255) / 256);
-  const int max_blocks = 148 * 16;
-  if (blocks > max_blocks) blocks = max_blocks;
+  int blocks_x = (int) ((n + 255) / 256);
+  const int max_blocks = (148 * 16 + G.nrep - 1) / G.nrep;
+  if (blocks_x > max_blocks) blocks_x = max_blocks;
+  const dim3 blocks(blocks_x, G.nrep, 1);
+  const size_t rep_stride = plane * (size_t) G.zper;
   ScopedLaunch sl(ctx, "k_timestep");
   if (P.mhd) {
-    if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
-    else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
+    if (P.de) k_timestep<true, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1, rep_stride);
+    else      k_timestep<true, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1, rep_stride);
   } else {
-    if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
-    else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1);
+    if (P.de) k_timestep<false, true><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1, rep_stride);
+    else      k_timestep<false, false><<<blocks, 256, 0, st>>>(P, G, u, pressure, width[0], width[1], width[2], dt_bits, c0, c1, rep_stride);
   }
 }
 
@@ -709,6 +733,18 @@ void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n
   ScopedLaunch sl(ctx, "k_boundary_axis");
   k_boundary_axis<<<blocks, 256, 0, ctx.st>>>(p, n0, n1, n2, axis, n, g, cen, side,
                                               type, sign);
+}
+
+void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,
+                       int nblocks, size_t count, size_t stride, bool to_stacked)
+{
+  if (count == 0 || nblocks == 0) return;
+  int bx = (int) ((count + 255) / 256);
+  const int cap = (148 * 16 + nblocks - 1) / nblocks;
+  if (bx > cap) bx = cap;
+  ScopedLaunch sl(ctx, to_stacked ? "k_batch_gather" : "k_batch_scatter");
+  k_batch_copy<<<dim3(bx, nblocks), 256, 0, ctx.st>>>(stacked, ptrs, count, stride,
+                                                      to_stacked ? 1 : 0);
 }
 
 void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,

@@ -13,11 +13,21 @@ namespace vlct {
 
 constexpr int kMaxPassive = VLCT_MAX_PASSIVE;
 
-/// extents of a cell-centred array including ghost zones
+/// extents of a cell-centred array including ghost zones. A batch of `nrep`
+/// equally shaped blocks may be stacked along z (vlct_compute_batch): block r
+/// occupies the levels [r*zper, r*zper + mz) of every array (zper = mz + 1, so
+/// that the z-face-centred arrays with their mz + 1 levels stack at the same
+/// period). Index boxes are always those of ONE block; a launch repeats them
+/// nrep times. Stencils never leave a block's own levels, so stacked blocks
+/// cannot see each other.
 struct Geom {
   int mx, my, mz;
+  int nrep = 1, zper = 0;
   __host__ __device__ size_t cells() const
   { return (size_t) mx * (size_t) my * (size_t) mz; }
+  /// levels of a stacked cell-centred array
+  __host__ __device__ size_t levels() const
+  { return nrep > 1 ? (size_t) nrep * (size_t) zper : (size_t) mz; }
 };
 
 /// the integration quantities of one state (all cell-centred, shape mz,my,mx)
@@ -145,6 +155,11 @@ void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
 void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
                           int axis, int n, int g, int cen, int side, int type,
                           double sign);
+
+/// batch of blocks <-> their stacked array (ptrs: device table of nblocks
+/// device pointers, `count` elements each, stacked `stride` elements apart)
+void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,
+                       int nblocks, size_t count, size_t stride, bool to_stacked);
 
 /// halo slab pack / unpack of one field along one axis
 /// lo..lo+g: range along the axis; the slab spans the full other extents

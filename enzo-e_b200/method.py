@@ -166,6 +166,31 @@ class EnzoMethodMHDVlct:
             self._h, C.byref(block.c_block),
             C.cast(dt.data_ptr(), C.POINTER(C.c_double)), part, z_lo, z_hi))
 
+    # -- many blocks per launch ------------------------------------------------
+    @staticmethod
+    def _block_array(blocks):
+        arr = (abi.VlctBlock * len(blocks))()
+        for i, b in enumerate(blocks):
+            arr[i] = b.c_block
+        return arr
+
+    def compute_batch(self, blocks, dt):
+        """compute() for a list of equally shaped blocks in one set of kernel
+        launches (vlct_compute_batch)."""
+        arr = self._block_array(blocks)
+        self._check(self._lib.vlct_compute_batch(self._h, arr, len(blocks),
+                                                 float(dt)))
+        for b in blocks:
+            b.compute_done()
+
+    def timestep_batch(self, blocks):
+        """min over the blocks of timestep(block); fills every "pressure"."""
+        arr = self._block_array(blocks)
+        out = C.c_double(0.0)
+        self._check(self._lib.vlct_timestep_batch(self._h, arr, len(blocks),
+                                                  C.byref(out)))
+        return out.value
+
     def set_option(self, key, value):
         self._check(self._lib.vlct_set_option(self._h, key.encode(), int(value)))
 

@@ -205,7 +205,29 @@ enum { VLCT_PART_INTERIOR = 0, VLCT_PART_LOWER = 1, VLCT_PART_UPPER = 2 };
 int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
                           const double *dt_device, int part, int z_lo, int z_hi);
 
+/* Many blocks of one shape in ONE set of kernel launches.
+ * The reference calls compute(Block*) once per block
+ * (src/Cello/control_compute.cpp:42-124), typically for 16^3..32^3-cell blocks;
+ * one launch sequence per such block would leave a B200 idle. Here the blocks
+ * (all with the same active size, ghost depth, cell widths, fields, mem_space
+ * and stream -- e.g. all leaf blocks of one refinement level on this PE) are
+ * stacked along z in device memory and every kernel of the step covers all of
+ * them at once; stencils never leave a block's own levels, so each block gets
+ * bit for bit what vlct_compute / vlct_timestep give it alone
+ * (tests/test_gpu_batch.py). vlct_timestep_batch returns the minimum over the
+ * blocks (the reference min-reduces the per-block values anyway,
+ * src/Cello/control_stopping.cpp:96-142) and fills every block's "pressure".
+ * `blocks` is an array of nblocks structs. HOST blocks are staged by one copy
+ * per (block, field); DEVICE blocks are gathered / scattered by one kernel per
+ * field. Batches larger than "batch_max_blocks" run in sub-batches. */
+int vlct_compute_batch(vlct_handle *h, const vlct_block *blocks, int nblocks,
+                       double dt);
+int vlct_timestep_batch(vlct_handle *h, const vlct_block *blocks, int nblocks,
+                        double *dt_out);
+
 /* Tuning knobs of a handle (none changes any result bit):
+ *   "batch_max_blocks"  blocks stacked per launch set by the *_batch entry
+ *        points (default 1024; also limited by 65535 / (mz + 1)).
  *   "host_pipeline_levels"   VLCT_MEM_HOST blocks are staged through the GPU
  *        as a pipeline over z: the H2D copy of the next levels, the kernels on
  *        the current ones and the D2H copy of the finished ones overlap.
