@@ -19,9 +19,14 @@ def _coords(n_local, g, lower, width, device):
     out = []
     for ax in range(3):
         m = n_local[ax] + 2 * g[ax]
-        idx = torch.arange(m + 1, dtype=torch.float64, device=device) - g[ax]
-        face = lower[ax] + width[ax] * idx
-        cen = lower[ax] + width[ax] * (0.5 + idx[:-1])
+        # positions are formed from the GLOBAL cell index (the block's lower
+        # corner is a whole number of cells from the origin), so that a brick
+        # of a decomposed domain gets bit for bit the values the undivided
+        # domain has there
+        off = round(lower[ax] / width[ax])
+        idx = torch.arange(m + 1, dtype=torch.float64, device=device) - g[ax] + off
+        face = width[ax] * idx
+        cen = width[ax] * (0.5 + idx[:-1])
         out.append((cen, face))
     return out
 

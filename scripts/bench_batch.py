@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Throughput of many small blocks (Enzo-E's usual operating point): one
+launch sequence per block (vlct_timestep + vlct_compute in a loop) against
+the batched entry points (vlct_timestep_batch + vlct_compute_batch), device
+resident, MHD PLM + HLLD + CT. usage: bench_batch.py [block_size nblocks]..."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(size, nb, steps=3):
+    import torch
+    from bench import PARAMS, GHOST
+    from enzo_e_b200 import problems
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    dev = torch.device("cuda", 0)
+    per_axis = round(nb ** (1 / 3))
+    width = (1.0 / (size * per_axis),) * 3
+    n = (size,) * 3
+    blocks, keep = [], []
+    for b in range(nb):
+        c = (b % per_axis, (b // per_axis) % per_axis, b // per_axis ** 2)
+        lower = tuple(c[a] * size * width[a] for a in range(3))
+        f = problems.orszag_tang(n, GHOST, lower, width, device=dev)
+        keep.append(f)
+        blocks.append(Block(f, n, GHOST, width))
+    method = EnzoMethodMHDVlct(PARAMS)
+    out = {"block": size, "nblocks": nb, "cells": nb * size ** 3}
+
+    def loop_step():
+        dt = min(method.timestep(b) for b in blocks)
+        for b in blocks:
+            method.compute(b, dt)
+
+    def batch_step():
+        dt = method.timestep_batch(blocks)
+        method.compute_batch(blocks, dt)
+
+    for name, step in (("batch", batch_step), ("loop", loop_step)):
+        step()
+        torch.cuda.synchronize()
+        l0 = method.kernel_launches()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        el = (time.perf_counter() - t0) / steps
+        out[name] = {"ms_per_step": 1e3 * el,
+                     "cell_updates_per_s": nb * size ** 3 / el,
+                     "launches_per_step": (method.kernel_launches() - l0) / steps}
+    out["speedup"] = out["loop"]["ms_per_step"] / out["batch"]["ms_per_step"]
+    method.close()
+    return out
+
+
+if __name__ == "__main__":
+    args = [int(a) for a in sys.argv[1:]] or [32, 512, 16, 4096]
+    for size, nb in zip(args[::2], args[1::2]):
+        print(json.dumps(run(size, nb)), flush=True)
