@@ -71,6 +71,19 @@ class VlctBlock(C.Structure):
     )
 
 
+VLCT_FLUX_FIELDS = 6 + VLCT_MAX_PASSIVE
+
+
+class VlctFaceFluxes(C.Structure):
+    _fields_ = [("face", ((_DP * VLCT_FLUX_FIELDS) * 2) * 3),
+                ("mem_space", C.c_int)]
+
+
+def face_flux_shape(dim, nx, ny, nz):
+    """(slower, faster) shape of one face array of vlct_face_fluxes"""
+    return {0: (nz, ny), 1: (nz, nx), 2: (ny, nx)}[dim]
+
+
 def default_config():
     """The defaults vlct_config_init() produces (reference defaults)."""
     return VlctConfig(

@@ -54,6 +54,9 @@ struct vlct_handle {
   int ptr_table_nb = 0;
   size_t ptr_table_count = 0;
   size_t scratch_levels = 0;              // z levels the scratch arrays hold
+  bool stepped = false;                   // a compute has filled the flux arrays
+  double* d_face_stage = nullptr;         // device staging of vlct_save_face_fluxes
+  size_t face_stage_count = 0;
   long long batch_max_blocks = 1024;
   long long launches = 0;
   long long copied_bytes[2] = { 0, 0 };   // H2D, D2H staged for HOST blocks
@@ -450,6 +453,7 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
+  h->stepped = (G.nrep == 1);   // face fluxes of a single block can be read back
   return VLCT_OK;
 }
 
@@ -525,6 +529,7 @@ void vlct_destroy(vlct_handle* h)
     for (void* p : h->allocations) cudaFree(p);
     for (void* p : h->mirror_allocs) cudaFree(p);
     for (void* p : h->arena_allocs) cudaFree(p);
+    if (h->d_face_stage) cudaFree(h->d_face_stage);
     if (h->d_ptr_table) cudaFree(h->d_ptr_table);
     if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
     if (h->d_dt_bits) cudaFree(h->d_dt_bits);
@@ -841,6 +846,7 @@ int ensure_arena(vlct_handle* h, const vlct_block& b0, const Geom& G)
   }
   const size_t need = (size_t) (kNumFields + VLCT_MAX_PASSIVE) * (size_t) G.nrep;
   if (need > h->ptr_table_count) {
+    if (h->d_face_stage) cudaFree(h->d_face_stage);
     if (h->d_ptr_table) cudaFree(h->d_ptr_table);
     if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
     CUDA_TRY(h, cudaMalloc((void**) &h->d_ptr_table, need * sizeof(double*)));
@@ -942,6 +948,71 @@ Geom stacked_geom(const vlct_block& b0, int nrep)
 }  // namespace
 
 extern "C" {
+
+int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
+                          const vlct_face_fluxes* out)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (b == nullptr || out == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "NULL argument to vlct_save_face_fluxes");
+  if (h->P.mhd)   // EnzoMethodMHDVlct.cpp:137-141
+    return fail(h, VLCT_ERR_INVALID_CONFIG,
+                "Flux corrections are currently only supported in hydro-mode");
+  const Geom G = geom_of(b);
+  if (h->G.mx == 0 || !h->stepped)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_save_face_fluxes needs a preceding vlct_compute");
+  if (G.mx != h->G.mx || G.my != h->G.my || G.mz != h->G.mz)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "block shape differs from the last compute");
+  const bool host = (out->mem_space == VLCT_MEM_HOST);
+  cudaStream_t st = (b->mem_space == VLCT_MEM_DEVICE && b->stream)
+                        ? (cudaStream_t) b->stream : h->own_stream;
+  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  const int m[3] = { G.mx, G.my, G.mz };
+  const int nstages = (h->cfg.time_scheme == VLCT_TIME_EULER) ? 1 : 2;
+  const double* sp = h->d_step + 4 * (nstages - 1);   // dt/dx, dt/dy, dt/dz of the final stage
+  // device staging for HOST output: the largest face of one field at a time
+  size_t max_face = 0;
+  for (int d = 0; d < 3; d++) {
+    const int a0 = (d == 0) ? 1 : 0, a1 = (d == 2) ? 1 : 2;
+    const size_t cnt = (size_t) n[a0] * n[a1];
+    if (cnt > max_face) max_face = cnt;
+  }
+  if (host && h->face_stage_count < 2 * max_face) {
+    if (h->d_face_stage) cudaFree(h->d_face_stage);
+    CUDA_TRY(h, cudaMalloc((void**) &h->d_face_stage, 2 * max_face * sizeof(double)));
+    h->face_stage_count = 2 * max_face;
+  }
+  for (int d = 0; d < 3; d++) {
+    const FluxSet& F = h->S.flux[d];
+    const double* arrays[VLCT_FLUX_FIELDS] = { F.rho, F.mx_, F.my_, F.mz_, F.e,
+                                               h->P.de ? F.eint : nullptr };
+    for (int s = 0; s < h->P.nsc; s++) arrays[6 + s] = F.sc[s];
+    const int a0 = (d == 0) ? 1 : 0, a1 = (d == 2) ? 1 : 2;
+    const size_t cnt = (size_t) n[a0] * n[a1];
+    for (int f = 0; f < 6 + h->P.nsc; f++) {
+      if (arrays[f] == nullptr) continue;
+      for (int side = 0; side < 2; side++) {
+        double* dst = out->face[d][side][f];
+        if (dst == nullptr) continue;
+        const int at = side ? m[d] - g[d] - 1 : g[d] - 1;
+        double* ddst = host ? h->d_face_stage + (size_t) side * max_face : dst;
+        launch_face_flux(ctx, G, arrays[f], sp + d, ddst, d, at, n[a0], n[a1],
+                         g[a0], g[a1]);
+        if (host) {
+          CUDA_TRY(h, cudaMemcpyAsync(dst, ddst, cnt * sizeof(double),
+                                      cudaMemcpyDeviceToHost, st));
+          h->copied_bytes[1] += (long long) (cnt * sizeof(double));
+        }
+      }
+      // the staging buffer is reused by the next field
+      if (host) CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
 
 int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt)
 {

@@ -480,6 +480,24 @@ k_boundary_axis(double* p, int n0, int n1, int n2, int axis, int n, int g,
   }
 }
 
+/// dt/dx * flux through one face of the block, over the active transverse
+/// extent (EnzoMethodMHDVlct.cpp:250-330). flux: cell-strided array, entry at
+/// index `at` along `dim`; out: packed (n1, n0), slower axis first.
+__global__ void __launch_bounds__(256)
+k_face_flux(const double* __restrict__ flux, const double* __restrict__ dtdx,
+            double* __restrict__ out, int mx, int my, int dim, int at, int n0,
+            int n1, int g0, int g1)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned) n0 * (unsigned) n1) return;
+  const int i0 = (int) (t % (unsigned) n0), i1 = (int) (t / (unsigned) n0);
+  const int a0 = (dim == 0) ? 1 : 0, a1 = (dim == 2) ? 1 : 2;
+  int idx[3];
+  idx[dim] = at; idx[a0] = g0 + i0; idx[a1] = g1 + i1;
+  const size_t c = ((size_t) idx[2] * my + idx[1]) * mx + idx[0];
+  out[t] = __ldg(dtdx) * __ldg(flux + c);
+}
+
 /// gather the blocks of a batch into their stacked array, or scatter them back:
 /// blockIdx.y = block; ptrs[block] = that block's own (device) array of `count`
 /// elements, stacked at stride `stride`
@@ -733,6 +751,17 @@ void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n
   ScopedLaunch sl(ctx, "k_boundary_axis");
   k_boundary_axis<<<blocks, 256, 0, ctx.st>>>(p, n0, n1, n2, axis, n, g, cen, side,
                                               type, sign);
+}
+
+void launch_face_flux(const LaunchCtx& ctx, const Geom& G, const double* flux,
+                      const double* dtdx, double* out, int dim, int at, int n0,
+                      int n1, int g0, int g1)
+{
+  const unsigned total = (unsigned) n0 * (unsigned) n1;
+  if (total == 0) return;
+  ScopedLaunch sl(ctx, "k_face_flux");
+  k_face_flux<<<(total + 255) / 256, 256, 0, ctx.st>>>(flux, dtdx, out, G.mx, G.my,
+                                                       dim, at, n0, n1, g0, g1);
 }
 
 void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,

@@ -156,6 +156,13 @@ void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n
                           int axis, int n, int g, int cen, int side, int type,
                           double sign);
 
+/// out[(i1, i0)] = *dtdx * flux[.. at ..]: one face of the block for the
+/// flux-correction output (dim: normal axis; n0/g0, n1/g1: active size and
+/// ghost depth of the faster / slower transverse axis)
+void launch_face_flux(const LaunchCtx& ctx, const Geom& G, const double* flux,
+                      const double* dtdx, double* out, int dim, int at, int n0,
+                      int n1, int g0, int g1);
+
 /// batch of blocks <-> their stacked array (ptrs: device table of nblocks
 /// device pointers, `count` elements each, stacked `stride` elements apart)
 void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,

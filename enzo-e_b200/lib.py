@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
     "vlct_compute_dev_part", "vlct_set_option",
-    "vlct_compute_batch", "vlct_timestep_batch",
+    "vlct_compute_batch", "vlct_timestep_batch", "vlct_save_face_fluxes",
     "vlct_last_error", "vlct_status_string",
     "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_staged_bytes",
     "vlct_synchronize",
@@ -69,6 +69,8 @@ def load():
         "vlct_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "vlct_compute_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_double]),
         "vlct_timestep_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, dp]),
+        "vlct_save_face_fluxes": (C.c_int, [C.c_void_p, blkp,
+                                            C.POINTER(abi.VlctFaceFluxes)]),
         "vlct_last_error": (C.c_char_p, [C.c_void_p]),
         "vlct_status_string": (C.c_char_p, [C.c_int]),
         "vlct_kernel_launches": (C.c_longlong, [C.c_void_p]),

@@ -166,6 +166,37 @@ class EnzoMethodMHDVlct:
             self._h, C.byref(block.c_block),
             C.cast(dt.data_ptr(), C.POINTER(C.c_double)), part, z_lo, z_hi))
 
+    # -- flux corrections -------------------------------------------------------
+    def save_face_fluxes(self, block, n_fields=None, device=None):
+        """dt/dx * final-stage fluxes through the block's six faces, as the
+        reference stores them for Method "flux_correct"
+        (EnzoMethodMHDVlct::save_fluxes_for_corrections_). Returns
+        {(dim, side, field): 2-D array}; numpy arrays, or CUDA tensors when
+        `device` is given. field: 0 density, 1..3 momentum x..z, 4 total
+        energy, 5 internal energy (dual energy), 6+s passive scalar s."""
+        nf = 6 + self.config.n_passive if n_fields is None else n_fields
+        ff = abi.VlctFaceFluxes()
+        ff.mem_space = abi.MEM_HOST if device is None else abi.MEM_DEVICE
+        out = {}
+        for dim in range(3):
+            shape = abi.face_flux_shape(dim, *block.n)
+            for side in range(2):
+                for f in range(nf):
+                    if f == 5 and not self.config.dual_energy:
+                        continue
+                    if device is None:
+                        a = np.zeros(shape)
+                        ptr = a.ctypes.data_as(C.POINTER(C.c_double))
+                    else:
+                        import torch
+                        a = torch.zeros(shape, dtype=torch.float64, device=device)
+                        ptr = C.cast(a.data_ptr(), C.POINTER(C.c_double))
+                    out[(dim, side, f)] = a
+                    ff.face[dim][side][f] = ptr
+        self._check(self._lib.vlct_save_face_fluxes(
+            self._h, C.byref(block.c_block), C.byref(ff)))
+        return out
+
     # -- many blocks per launch ------------------------------------------------
     @staticmethod
     def _block_array(blocks):

@@ -205,6 +205,31 @@ enum { VLCT_PART_INTERIOR = 0, VLCT_PART_LOWER = 1, VLCT_PART_UPPER = 2 };
 int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
                           const double *dt_device, int part, int z_lo, int z_hi);
 
+/* Flux-correction output:
+ * EnzoMethodMHDVlct::save_fluxes_for_corrections_
+ * (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:250-330, called for the final
+ * stage at :480-490). After vlct_compute / vlct_compute_dev of a block,
+ * vlct_save_face_fluxes writes dt/dx * (final-stage flux) through the block's
+ * two faces along every dimension -- what the reference deposits in the
+ * block's FluxData for Method "flux_correct" -- over the active transverse
+ * extent:
+ *   face[dim][side][field]  packed 2-D array, slower axis first:
+ *        dim 0: (nz, ny)   dim 1: (nz, nx)   dim 2: (ny, nx);
+ *        side 0 = lower face (flux index g-1), 1 = upper face (index m-g-1);
+ *        field 0 density, 1..3 velocity_x..z (momentum fluxes), 4 total_energy,
+ *        5 internal_energy (dual energy only), 6+s passive scalar s.
+ * NULL entries are skipped. Like the reference (cpp:137-141) this is
+ * supported in pure-hydro mode only (mhd_choice = "no_bfield"). The fluxes are
+ * those of the LAST compute call on this handle; mem_space says where the
+ * output arrays live. */
+#define VLCT_FLUX_FIELDS (6 + VLCT_MAX_PASSIVE)
+typedef struct vlct_face_fluxes {
+  double *face[3][2][VLCT_FLUX_FIELDS];
+  int mem_space;
+} vlct_face_fluxes;
+int vlct_save_face_fluxes(vlct_handle *h, const vlct_block *block,
+                          const vlct_face_fluxes *out);
+
 /* Many blocks of one shape in ONE set of kernel launches.
  * The reference calls compute(Block*) once per block
  * (src/Cello/control_compute.cpp:42-124), typically for 16^3..32^3-cell blocks;

@@ -129,6 +129,33 @@ class CpuMethod:
         if rc != 0:
             raise RuntimeError(f"{self.kind}: compute failed ({rc})")
 
+    def face_fluxes(self, blk, dt, n, n_fields):
+        """save_fluxes_for_corrections_ on the fluxes of the last compute
+        (oracle restatement only): {(dim, side, field): 2-D numpy array}"""
+        assert self.kind == "oracle"
+        import numpy as np
+        nslots = 6 + abi.VLCT_MAX_PASSIVE
+        dp = C.POINTER(C.c_double)
+        table = (((dp * nslots) * 2) * 3)()
+        out = {}
+        for dim in range(3):
+            shape = abi.face_flux_shape(dim, *n)
+            for side in range(2):
+                for f in range(n_fields):
+                    if f == 5 and not self.cfg.dual_energy:
+                        continue
+                    a = np.zeros(shape)
+                    out[(dim, side, f)] = a
+                    table[dim][side][f] = a.ctypes.data_as(dp)
+        fn = self._lib.vlct_oracle_face_fluxes
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_double,
+                       C.c_void_p]
+        rc = fn(self._h, C.byref(blk), float(dt), C.byref(table))
+        if rc != 0:
+            raise RuntimeError(f"vlct_oracle_face_fluxes failed ({rc})")
+        return out
+
     def timestep(self, blk):
         out = C.c_double(0.0)
         rc = self._timestep(self._h, C.byref(blk), C.byref(out))

@@ -1175,6 +1175,47 @@ int vlct_oracle_compute(vlct_oracle *o, const vlct_block *b, double dt)
   return 0;
 }
 
+/* EnzoMethodMHDVlct::save_fluxes_for_corrections_
+ * (hydro-mhd/EnzoMethodMHDVlct.cpp:250-330): dt/dx times the final-stage flux
+ * through the block's two faces along every dimension, over the active
+ * transverse extent, for the "conserved" fields. Uses the flux arrays the last
+ * vlct_oracle_compute left behind. out[dim][side][field]: packed 2-D arrays,
+ * slower axis first -- (z,y) for dim 0, (z,x) for dim 1, (y,x) for dim 2;
+ * field slots as in vlct_face_fluxes (include/vlct.h); NULL = skip. */
+int vlct_oracle_face_fluxes(const vlct_oracle *o, const vlct_block *b, double dt,
+                            double *const out[3][2][6 + VLCT_MAX_PASSIVE])
+{
+  if (o->mx == 0) return 2;
+  const int slot_q[6] = { Q_RHO, Q_VX, Q_VY, Q_VZ, Q_EN, Q_EINT };
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  const int m[3] = { o->mx, o->my, o->mz };
+  const double width[3] = { b->dx, b->dy, b->dz };
+  for (int dim = 0; dim < 3; dim++) {
+    const double dt_dxi = dt / width[dim];
+    const int left = g[dim] - 1, right = m[dim] - g[dim] - 1;
+    for (int f = 0; f < 6 + o->nsc; f++) {
+      const int q = (f < 6) ? slot_q[f] : Q_SC0 + (f - 6);
+      if (q == Q_EINT && !o->de) continue;
+      const arr3 F = o->flux[dim][q];
+      for (int side = 0; side < 2; side++) {
+        double *dst = out[dim][side][f];
+        if (dst == NULL) continue;
+        const int at = side ? right : left;
+        /* transverse axes: (a1 slower, a0 faster) */
+        const int a0 = (dim == 0) ? 1 : 0, a1 = (dim == 2) ? 1 : 2;
+        for (int i1 = 0; i1 < n[a1]; i1++)
+          for (int i0 = 0; i0 < n[a0]; i0++) {
+            int idx[3];
+            idx[dim] = at; idx[a0] = g[a0] + i0; idx[a1] = g[a1] + i1;
+            dst[(size_t) i1 * n[a0] + i0] =
+              dt_dxi * F.p[((size_t) idx[2] * F.n1 + idx[1]) * F.n2 + idx[0]];
+          }
+      }
+    }
+  }
+  return 0;
+}
+
 /* EnzoMethodMHDVlct::timestep (hydro-mhd/EnzoMethodMHDVlct.cpp:551-588) and
  * EnzoMHDIntegratorStageCommands::timestep (StageCommands.cpp:299-366) */
 int vlct_oracle_timestep(vlct_oracle *o, const vlct_block *b, double *dt_out)
