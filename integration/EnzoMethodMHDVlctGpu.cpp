@@ -29,7 +29,8 @@ static void set_key_(vlct_config* cfg, const char* key, const std::string& val)
 
 EnzoMethodMHDVlctGpu::EnzoMethodMHDVlctGpu(ParameterGroup p,
                                            bool store_fluxes_for_corrections)
-  : Method(), handle_(nullptr), passive_names_()
+  : Method(), handle_(nullptr), passive_names_(),
+    store_fluxes_for_corrections_(store_fluxes_for_corrections)
 {
   vlct_config_init(&config_);
 
@@ -80,9 +81,11 @@ EnzoMethodMHDVlctGpu::EnzoMethodMHDVlctGpu(ParameterGroup p,
   // gravity source terms only when the acceleration fields exist (cpp:219-232)
   config_.has_acceleration = field_descr->is_field("acceleration_x") ? 1 : 0;
 
-  ASSERT("EnzoMethodMHDVlctGpu",
-         "Flux corrections are not supported by the GPU path yet",
-         !store_fluxes_for_corrections);
+  if (store_fluxes_for_corrections) {       // cpp:137-141
+    ASSERT("EnzoMethodMHDVlctGpu",
+           "Flux corrections are currently only supported in hydro-mode",
+           config_.mhd_choice == VLCT_MHD_NO_BFIELD);
+  }
   ASSERT("EnzoMethodMHDVlctGpu", "\"pressure\" must be a permanent field",
          field_descr->is_field("pressure"));
 
@@ -120,6 +123,7 @@ void EnzoMethodMHDVlctGpu::pup(PUP::er& p)
   // vlct_config is plain data; scratch space is never serialised (cpp:170-197)
   PUParray(p, reinterpret_cast<char*>(&config_), sizeof(vlct_config));
   p | passive_names_;
+  p | store_fluxes_for_corrections_;
   if (p.isUnpacking()) create_handle_();
 }
 
@@ -163,13 +167,84 @@ void EnzoMethodMHDVlctGpu::bind_block_(Block* block, vlct_block* out) noexcept
 
 //----------------------------------------------------------------------
 
+/// allocate_FC_flux_buffer_ (cpp:332-352): one single-flux-array FluxData
+/// entry per field of the "conserved" group, every cycle
+static void allocate_FC_flux_buffer_(Block* block) throw()
+{
+  Field field = block->data()->field();
+  auto field_names = field.groups()->group_list("conserved");
+  const int nf = (int) field_names.size();
+  std::vector<int> field_list(nf);
+  for (int i = 0; i < nf; i++) field_list[i] = field.field_id(field_names[i]);
+  int nx, ny, nz;
+  field.size(&nx, &ny, &nz);
+  block->data()->flux_data()->allocate(nx, ny, nz, field_list, true);
+}
+
+//----------------------------------------------------------------------
+
+/// save_fluxes_for_corrections_ (cpp:250-330): the library returns
+/// dt/dx * (final-stage flux) on the block's six faces as packed arrays whose
+/// layout is FaceFluxes' own (ix + mx*(iy + my*iz) with the normal extent 1)
+void EnzoMethodMHDVlctGpu::save_fluxes_for_corrections_(Block* block,
+                                                        const vlct_block& b) noexcept
+{
+  Field field = block->data()->field();
+  FluxData* flux_data = block->data()->flux_data();
+  const int nf = flux_data->num_fields();
+
+  vlct_face_fluxes ff;
+  memset(&ff, 0, sizeof(ff));
+  ff.mem_space = VLCT_MEM_HOST;
+  struct Target { FaceFluxes* face; std::vector<double> staging; };
+  std::vector<Target> targets;
+  targets.reserve((std::size_t) nf * 6);       // pointers into it stay valid
+
+  for (int i_f = 0; i_f < nf; i_f++) {
+    const std::string field_name = field.field_name(flux_data->index_field(i_f));
+    int slot = -1;
+    if (field_name == "density") slot = 0;
+    else if (field_name == "velocity_x") slot = 1;
+    else if (field_name == "velocity_y") slot = 2;
+    else if (field_name == "velocity_z") slot = 3;
+    else if (field_name == "total_energy") slot = 4;
+    else if (field_name == "internal_energy") slot = 5;
+    for (std::size_t k = 0; k < passive_names_.size(); k++)
+      if (field_name == passive_names_[k]) slot = 6 + (int) k;
+    if (slot < 0) {
+      ERROR1("EnzoMethodMHDVlctGpu::save_fluxes_for_corrections_",
+             "no flux is computed for the conserved field \"%s\"",
+             field_name.c_str());
+    }
+    for (int dim = 0; dim < 3; dim++) {
+      for (int side = 0; side < 2; side++) {
+        FaceFluxes* face = flux_data->block_fluxes(dim, side, i_f);
+        int mx, my, mz;
+        face->get_size(&mx, &my, &mz);
+        targets.push_back(Target{ face, std::vector<double>((std::size_t) mx * my * mz) });
+        ff.face[dim][side][slot] = targets.back().staging.data();
+      }
+    }
+  }
+  const int rc = vlct_save_face_fluxes(handle_, &b, &ff);
+  check_status_(rc, handle_, "EnzoMethodMHDVlctGpu::save_fluxes_for_corrections_");
+  for (Target& t : targets) {
+    enzo_float* dest = t.face->flux_array();
+    for (std::size_t i = 0; i < t.staging.size(); i++) dest[i] = (enzo_float) t.staging[i];
+  }
+}
+
+//----------------------------------------------------------------------
+
 void EnzoMethodMHDVlctGpu::compute(Block* block) throw()
 {
+  if (store_fluxes_for_corrections_) allocate_FC_flux_buffer_(block);   // cpp:362
   if (block->is_leaf()) {           // cpp:364
     vlct_block b;
     bind_block_(block, &b);
     const int rc = vlct_compute(handle_, &b, block->dt());
     check_status_(rc, handle_, "EnzoMethodMHDVlctGpu::compute");
+    if (store_fluxes_for_corrections_) save_fluxes_for_corrections_(block, b);  // cpp:480-490
   }
   block->compute_done();            // cpp:499
 }

@@ -34,7 +34,8 @@ public:
   /// like EnzoMethodMHDVlct::pup, EnzoMethodMHDVlct.cpp:170-197)
   PUPable_decl(EnzoMethodMHDVlctGpu);
   EnzoMethodMHDVlctGpu(CkMigrateMessage* m)
-    : Method(m), handle_(nullptr), passive_names_() {}
+    : Method(m), handle_(nullptr), passive_names_(),
+      store_fluxes_for_corrections_(false) {}
   void pup(PUP::er& p);
 
   virtual ~EnzoMethodMHDVlctGpu();
@@ -48,10 +49,13 @@ protected:
   void create_handle_();
   /// fills a vlct_block with the pointers Field::values() returns
   void bind_block_(Block* block, vlct_block* out) noexcept;
+  /// deposits dt/dx * face fluxes in the block's FluxData (for "flux_correct")
+  void save_fluxes_for_corrections_(Block* block, const vlct_block& b) noexcept;
 
   vlct_config config_;
   vlct_handle* handle_;
   std::vector<std::string> passive_names_;
+  bool store_fluxes_for_corrections_;
 };
 
 #endif /* ENZO_ENZO_METHOD_MHD_VLCT_GPU_HPP */

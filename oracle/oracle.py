@@ -104,11 +104,19 @@ def numpy_block(fields, n, g, d, passive=()):
 class CpuMethod:
     """A CPU `EnzoMethodMHDVlct` (oracle restatement or compiled reference)."""
 
-    def __init__(self, cfg, ghost=(3, 3, 3), kind="oracle"):
+    def __init__(self, cfg, ghost=(3, 3, 3), kind="oracle", store_fluxes=False):
+        """store_fluxes: construct the reference Method ("ref" / "adapter")
+        with store_fluxes_for_corrections = true (the oracle restatement
+        always keeps its flux arrays)"""
         self.kind = kind
         self.cfg = cfg
         (self._lib, create, self._destroy, self._compute,
          self._timestep) = _load(kind)
+        if store_fluxes and kind != "oracle":
+            pfx = {"ref": "vlct_ref", "adapter": "vlct_adapter"}[kind]
+            create = getattr(self._lib, pfx + "_create_fc")
+            create.restype = C.c_void_p
+            create.argtypes = [C.POINTER(abi.VlctConfig), C.c_int, C.c_int, C.c_int]
         self._h = create(C.byref(cfg), *ghost)
         if not self._h:
             raise RuntimeError(f"{kind}: create failed")
@@ -130,9 +138,10 @@ class CpuMethod:
             raise RuntimeError(f"{self.kind}: compute failed ({rc})")
 
     def face_fluxes(self, blk, dt, n, n_fields):
-        """save_fluxes_for_corrections_ on the fluxes of the last compute
-        (oracle restatement only): {(dim, side, field): 2-D numpy array}"""
-        assert self.kind == "oracle"
+        """save_fluxes_for_corrections_ of the last compute:
+        {(dim, side, field): 2-D numpy array}. For "ref" / "adapter" (created
+        with store_fluxes=True) this is what the Method itself deposited in
+        the block's FluxData."""
         import numpy as np
         nslots = 6 + abi.VLCT_MAX_PASSIVE
         dp = C.POINTER(C.c_double)
@@ -147,11 +156,18 @@ class CpuMethod:
                     a = np.zeros(shape)
                     out[(dim, side, f)] = a
                     table[dim][side][f] = a.ctypes.data_as(dp)
-        fn = self._lib.vlct_oracle_face_fluxes
-        fn.restype = C.c_int
-        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_double,
-                       C.c_void_p]
-        rc = fn(self._h, C.byref(blk), float(dt), C.byref(table))
+        if self.kind == "oracle":
+            fn = self._lib.vlct_oracle_face_fluxes
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_double,
+                           C.c_void_p]
+            rc = fn(self._h, C.byref(blk), float(dt), C.byref(table))
+        else:
+            pfx = {"ref": "vlct_ref", "adapter": "vlct_adapter"}[self.kind]
+            fn = getattr(self._lib, pfx + "_face_fluxes")
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p]
+            rc = fn(self._h, C.byref(table))
         if rc != 0:
             raise RuntimeError(f"vlct_oracle_face_fluxes failed ({rc})")
         return out

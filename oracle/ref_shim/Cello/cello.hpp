@@ -206,17 +206,48 @@ private:
 
 //----------------------------------------------------------------------
 
+/// Minimal stand-ins for Cello's flux-correction containers
+/// (src/Cello/data_FaceFluxes.hpp, data_FluxData.hpp): one array per
+/// (field, axis, side); indexing ix + mx*(iy + my*iz), with extent 1 along the
+/// face's normal (data_FaceFluxes.hpp:98-122).
 class FaceFluxes {
 public:
-  void get_size(int*, int*, int*) const {}
-  double* flux_array(int*, int*, int*) { return nullptr; }
+  FaceFluxes(int mx = 1, int my = 1, int mz = 1)
+    : mx_(mx), my_(my), mz_(mz), fluxes_((std::size_t) mx * my * mz, 0.0) {}
+  int get_size(int* pmx = nullptr, int* pmy = nullptr, int* pmz = nullptr) const {
+    if (pmx) *pmx = mx_;
+    if (pmy) *pmy = my_;
+    if (pmz) *pmz = mz_;
+    return mx_ * my_ * mz_;
+  }
+  double* flux_array(int* dx = nullptr, int* dy = nullptr, int* dz = nullptr) {
+    if (dx) *dx = 1;
+    if (dy) *dy = mx_;
+    if (dz) *dz = mx_ * my_;
+    return fluxes_.data();
+  }
+private:
+  int mx_, my_, mz_;
+  std::vector<double> fluxes_;
 };
 class FluxData {
 public:
-  int num_fields() const { return 0; }
-  int index_field(int) const { return 0; }
-  FaceFluxes* block_fluxes(int, int, int) { return nullptr; }
-  void allocate(int, int, int, std::vector<int>, bool) {}
+  int num_fields() const { return (int) field_list_.size(); }
+  int index_field(int i_f) const { return field_list_.at(i_f); }
+  FaceFluxes* block_fluxes(int axis, int face, int i_f)
+  { return &fluxes_.at(((std::size_t) i_f * 3 + axis) * 2 + face); }
+  void allocate(int nx, int ny, int nz, std::vector<int> field_list, bool) {
+    field_list_ = field_list;
+    fluxes_.clear();
+    for (std::size_t i_f = 0; i_f < field_list.size(); i_f++)
+      for (int axis = 0; axis < 3; axis++)
+        for (int face = 0; face < 2; face++)
+          fluxes_.push_back(FaceFluxes(axis == 0 ? 1 : nx, axis == 1 ? 1 : ny,
+                                       axis == 2 ? 1 : nz));
+  }
+private:
+  std::vector<int> field_list_;
+  std::vector<FaceFluxes> fluxes_;
 };
 
 class Data {

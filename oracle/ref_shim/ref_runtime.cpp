@@ -103,6 +103,9 @@ struct RefContext {
 struct RefHandle {
   RefContext* ctx;
   ShimMethod* method;
+  // flux-correction output of the last compute: [field slot][axis][face]
+  bool store_fluxes = false;
+  std::vector<double> saved[6 + VLCT_MAX_PASSIVE][3][2];
 };
 
 std::vector<RefContext*> g_contexts;
@@ -178,7 +181,8 @@ void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
 
 extern "C" {
 
-void* SHIM_FN(create)(const vlct_config* cfg, int gx, int gy, int gz)
+static void* create_(const vlct_config* cfg, int gx, int gy, int gz,
+                     bool store_fluxes)
 {
   std::lock_guard<std::mutex> lock(g_mutex);
   RefContext* c = nullptr;
@@ -221,6 +225,16 @@ void* SHIM_FN(create)(const vlct_config* cfg, int gx, int gy, int gz)
       c->descr.insert(name, 0,0,0);
       c->descr.groups()->add(name, "color");
     }
+    // what an input file lists in Group "conserved" for a VL+CT run with
+    // Method "flux_correct" (only looked at when fluxes are stored)
+    c->descr.groups()->add("density", "conserved");
+    c->descr.groups()->add("velocity_x", "conserved");
+    c->descr.groups()->add("velocity_y", "conserved");
+    c->descr.groups()->add("velocity_z", "conserved");
+    c->descr.groups()->add("total_energy", "conserved");
+    if (de) c->descr.groups()->add("internal_energy", "conserved");
+    for (const std::string& name : c->passive_names)
+      c->descr.groups()->add(name, "conserved");
     EnzoDualEnergyConfig de_config = EnzoDualEnergyConfig::build_disabled();
     if (cfg->dual_energy == VLCT_DE_MODERN) {
       de_config = EnzoDualEnergyConfig::build_modern_formulation
@@ -250,9 +264,17 @@ void* SHIM_FN(create)(const vlct_config* cfg, int gx, int gy, int gz)
     p.set("mhd_choice", mhd ? "constrained_transport" : "no_bfield");
   if (cfg->courant >= 0) p.set("courant", fmt_double(cfg->courant));
 
-  h->method = new ShimMethod(p, false);
+  h->store_fluxes = store_fluxes;
+  h->method = new ShimMethod(p, store_fluxes);
   return h;
 }
+
+void* SHIM_FN(create)(const vlct_config* cfg, int gx, int gy, int gz)
+{ return create_(cfg, gx, gy, gz, false); }
+
+/// the same Method constructed with store_fluxes_for_corrections = true
+void* SHIM_FN(create_fc)(const vlct_config* cfg, int gx, int gy, int gz)
+{ return create_(cfg, gx, gy, gz, true); }
 
 void SHIM_FN(destroy)(void* handle)
 {
@@ -281,7 +303,46 @@ int SHIM_FN(compute)(void* handle, const vlct_block* b, double dt)
   bind_block(h, blk, b);
   blk.set_dt(dt);
   h->method->compute(&blk);
+  if (h->store_fluxes) {
+    // keep what save_fluxes_for_corrections_ deposited in the block's FluxData
+    FluxData* fd = blk.data()->flux_data();
+    Field field = blk.data()->field();
+    for (int i_f = 0; i_f < fd->num_fields(); i_f++) {
+      const std::string name = field.field_name(fd->index_field(i_f));
+      int slot = -1;
+      const char* fixed[6] = { "density", "velocity_x", "velocity_y", "velocity_z",
+                               "total_energy", "internal_energy" };
+      for (int k = 0; k < 6; k++) if (name == fixed[k]) slot = k;
+      for (std::size_t k = 0; k < h->ctx->passive_names.size(); k++)
+        if (name == h->ctx->passive_names[k]) slot = 6 + (int) k;
+      if (slot < 0) continue;
+      for (int axis = 0; axis < 3; axis++)
+        for (int face = 0; face < 2; face++) {
+          FaceFluxes* ff = fd->block_fluxes(axis, face, i_f);
+          const int m = ff->get_size();
+          double* p = ff->flux_array();
+          h->saved[slot][axis][face].assign(p, p + m);
+        }
+    }
+  }
   return (blk.compute_done_count == 1) ? 0 : 1;
+}
+
+/// out[axis][face][slot] (NULL = skip) <- the face fluxes of the last compute
+int SHIM_FN(face_fluxes)(void* handle, double* const out[3][2][6 + VLCT_MAX_PASSIVE])
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  if (!h->store_fluxes) return 1;
+  for (int axis = 0; axis < 3; axis++)
+    for (int face = 0; face < 2; face++)
+      for (int slot = 0; slot < 6 + VLCT_MAX_PASSIVE; slot++) {
+        double* dst = out[axis][face][slot];
+        if (dst == nullptr) continue;
+        const std::vector<double>& src = h->saved[slot][axis][face];
+        if (src.empty()) return 2;
+        memcpy(dst, src.data(), src.size() * sizeof(double));
+      }
+  return 0;
 }
 
 int SHIM_FN(timestep)(void* handle, const vlct_block* b, double* dt_out)

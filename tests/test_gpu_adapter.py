@@ -44,3 +44,31 @@ def test_cxx_method_adapter_matches_reference(kw):
     eq = bit_equal(want, got)
     bad = {k: max_abs_diff(want, got)[k] for k, ok in eq.items() if not ok}
     assert not bad, bad
+
+
+def test_cxx_method_adapter_stores_fluxes_for_corrections():
+    """constructed with store_fluxes_for_corrections = true, the C++ adapter
+    deposits in the block's FluxData exactly what the reference's own Method
+    deposits (EnzoMethodMHDVlct.cpp:250-330, 480-490)"""
+    import numpy as np
+    if not (oracle.have_adapter() and oracle.have_ref()):
+        pytest.skip("oracle/_ref libraries not available")
+    cfg = make_config(riemann="hllc", recon="plm", mhd=False, dual_energy=True,
+                      gamma=1.4, n_passive=2)
+    n, g, d = (14, 9, 8), (3, 3, 3), (0.1, 0.12, 0.09)
+    nf = 6 + cfg.n_passive
+    host = random_state(cfg, n, g, seed=19)
+    out = {}
+    for kind in ("ref", "adapter"):
+        f = copy_state(host)
+        blk = oracle.numpy_block(f, n, g, d, passive_names(cfg))
+        m = oracle.CpuMethod(cfg, g, kind=kind, store_fluxes=True)
+        dt = m.timestep(blk)
+        m.compute(blk, dt)
+        out[kind] = (m.face_fluxes(blk, dt, n, nf), f, dt)
+        m.close()
+    assert out["ref"][2] == out["adapter"][2]
+    assert all(bit_equal(out["ref"][1], out["adapter"][1]).values())
+    a, b = out["ref"][0], out["adapter"][0]
+    for key in a:
+        assert np.array_equal(a[key].view(np.uint64), b[key].view(np.uint64)), key

@@ -194,3 +194,34 @@ def test_passive_scalar_sound_wave_golden(axis):
     m.close()
     norm = P.passive_l1_norm(s0, P.passive_snapshot(f, g))
     assert P.golden_isclose(norm, P.GOLDEN_PASSIVE_SOUND), norm
+
+
+@pytest.mark.parametrize("kw", [dict(riemann="hllc", recon="plm", mhd=False),
+                                dict(riemann="hllc", recon="plm", mhd=False,
+                                     dual_energy=True, gamma=1.4, n_passive=2),
+                                dict(riemann="hllc", recon="plm_athena", mhd=False,
+                                     time_scheme="euler", courant=0.5)])
+def test_face_fluxes_match_compiled_reference(kw):
+    """flux-correction output: the restatement of save_fluxes_for_corrections_
+    against what the reference's own Method deposits in FluxData"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    cfg = make_config(**kw)
+    n, g, d = (11, 8, 6), (3, 3, 3), (0.1, 0.12, 0.09)
+    nf = 6 + cfg.n_passive
+    host = random_state(cfg, n, g, seed=61)
+    out = {}
+    for kind in ("oracle", "ref"):
+        f = copy_state(host)
+        blk = oracle.numpy_block(f, n, g, d, passive_names(cfg))
+        m = oracle.CpuMethod(cfg, g, kind=kind, store_fluxes=True)
+        dt = m.timestep(blk)
+        m.compute(blk, dt)
+        out[kind] = (m.face_fluxes(blk, dt, n, nf), f)
+        m.close()
+    assert all(bit_equal(out["oracle"][1], out["ref"][1]).values())
+    a, b = out["oracle"][0], out["ref"][0]
+    assert set(a) == set(b)
+    for key in a:
+        assert np.array_equal(a[key].view(np.uint64), b[key].view(np.uint64)), key
+        assert np.any(a[key] != 0.0), key
