@@ -41,6 +41,9 @@ inline dim3 grid_for(const Geom& G, const Box& b)
 
 // i, j: x / y index; kl: z level inside the block (what index boxes are tested
 // against); k: z level in the (possibly stacked) arrays
+// (kernels are instantiated for a single block, STACKED = false: kl == k, one
+// register and one division less -- k_edge_efield is sensitive to both -- and
+// for a stacked batch)
 #define VLCT_THREAD_IN_BOX(G, box, i, j, kl, k)                                \
   const unsigned nxb__ = (box).hi[0] - (box).lo[0];                            \
   const unsigned t__ = blockIdx.x * kBlock + threadIdx.x;                      \
@@ -48,15 +51,17 @@ inline dim3 grid_for(const Geom& G, const Box& b)
   const int i = (box).lo[0] + (int) (t__ % nxb__);                             \
   const int j = (box).lo[1] + (int) (t__ / nxb__);                             \
   int kl, k;                                                                   \
-  unstack((G), (box), blockIdx.y, kl, k);
+  if constexpr (STACKED) unstack((G), (box), blockIdx.y, kl, k);               \
+  else kl = k = (box).lo[2] + (int) blockIdx.y;
 
 // ---------------------------------------------------------------------------
 // specific passive scalars: EnzoPhysicsFluidProps::primitive_from_integration
 // (fluid-props/EnzoPhysicsFluidProps.cpp:64-138). The pressure part of that
 // routine is evaluated on the fly inside the flux kernels (vlct_flux.cu).
 // ---------------------------------------------------------------------------
+template <bool STACKED>
 __global__ void __launch_bounds__(kBlock)
-k_specific_scalars(const int nsc, const Geom G, const State u,
+k_specific_scalars(const int nsc, const typename GeomFor<STACKED>::type G, const State u,
                    const ScalarPtrs spec, const Box box)
 {
   VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
@@ -88,8 +93,8 @@ __device__ __forceinline__ double upwind_weight(double dflux)
   return 0.5;
 }
 
-template <int D>
-__device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
+template <int D, class GEOM>
+__device__ __forceinline__ void edge_component(const GEOM& G, const EdgeArgs& A,
                                                int kl, int k, int j, int i)
 {
   constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
@@ -128,12 +133,11 @@ __device__ __forceinline__ void edge_component(const Geom& G, const EdgeArgs& A,
   A.edge[D][c] = 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
 }
 
-#ifdef VLCT_EDGE_MINBLOCKS   // tuning hook (A/B builds)
-__global__ void __launch_bounds__(kBlock, VLCT_EDGE_MINBLOCKS)
-#else
+// (40 registers = 6 blocks of 256 threads per SM; measured faster than 5 blocks
+// at 42-44 registers, 4.4 vs 5.1 ms at 512^3, and than 8 blocks at 32)
+template <bool STACKED>
 __global__ void __launch_bounds__(kBlock)
-#endif
-k_edge_efield(const Geom G, const EdgeArgs A, const Box box)
+k_edge_efield(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
   edge_component<0>(G, A, kl, k, j, i);
@@ -149,8 +153,8 @@ struct FaceArgs {
   Box box[3];
 };
 
-template <int D>
-__device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
+template <int D, class GEOM>
+__device__ __forceinline__ void face_component(const GEOM& G, const FaceArgs& A,
                                                int kl, int k, int j, int i)
 {
   constexpr int JD = (D + 1) % 3, KD = (D + 2) % 3;
@@ -168,8 +172,9 @@ __device__ __forceinline__ void face_component(const Geom& G, const FaceArgs& A,
   A.bi_out[D][f] = __ldg(A.bi0[D] + f) - E_k_term + E_j_term;
 }
 
+template <bool STACKED>
 __global__ void __launch_bounds__(kBlock)
-k_face_bfield(const Geom G, const FaceArgs A, const Box box)
+k_face_bfield(const typename GeomFor<STACKED>::type G, const FaceArgs A, const Box box)
 {
   VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
   face_component<0>(G, A, kl, k, j, i);
@@ -230,9 +235,10 @@ floor_energy_and_sync(const Params& P, double rho, double vx, double vy,
   }
 }
 
-template <bool MHD, bool DE>
+template <bool MHD, bool DE, bool STACKED>
 __global__ void __launch_bounds__(kBlock)
-k_update(const Params P, const Geom G, const UpdateArgs A, const Box box)
+k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateArgs A,
+         const Box box)
 {
   VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
   const size_t c = cidx(G, k, j, i);
@@ -588,8 +594,12 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
   Box box = full_box(G, stale);
   if (!clip_z(box, zc)) return;
   ScopedLaunch sl(ctx, "k_specific_scalars");
-  k_specific_scalars<<<grid_for(G, box), kBlock, 0, ctx.st>>>(
-      P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
+  if (G.nrep > 1)
+    k_specific_scalars<true><<<grid_for(G, box), kBlock, 0, ctx.st>>>(
+        P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
+  else
+    k_specific_scalars<false><<<grid_for(G, box), kBlock, 0, ctx.st>>>(
+        P.nsc, lite(G), cur, scalar_ptrs(S.prim_sc, P.nsc), box);
 }
 
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
@@ -620,7 +630,8 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     // clips all three)
     if (clip_z(box, z_edge)) {
       ScopedLaunch sl(ctx, "k_edge_efield");
-      k_edge_efield<<<grid_for(G, box), block, 0, st>>>(G, A, box);
+      if (G.nrep > 1) k_edge_efield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
+      else            k_edge_efield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
     }
   }
   {
@@ -640,7 +651,8 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
     if (clip_z(box, z_face)) {
       ScopedLaunch sl(ctx, "k_face_bfield");
-      k_face_bfield<<<grid_for(G, box), block, 0, st>>>(G, A, box);
+      if (G.nrep > 1) k_face_bfield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
+      else            k_face_bfield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
     }
   }
 }
@@ -669,13 +681,19 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   if (!clip_z(box, zc)) return;
   const int block = kBlock; const dim3 grid = grid_for(G, box);
   ScopedLaunch sl(ctx, "k_update");
+#define VLCT_UPDATE(MHD_, DE_)                                                   \
+  do {                                                                          \
+    if (G.nrep > 1) k_update<MHD_, DE_, true><<<grid, block, 0, st>>>(P, G, A, box);  \
+    else            k_update<MHD_, DE_, false><<<grid, block, 0, st>>>(P, lite(G), A, box); \
+  } while (0)
   if (P.mhd) {
-    if (P.de) k_update<true, true><<<grid, block, 0, st>>>(P, G, A, box);
-    else      k_update<true, false><<<grid, block, 0, st>>>(P, G, A, box);
+    if (P.de) VLCT_UPDATE(true, true);
+    else      VLCT_UPDATE(true, false);
   } else {
-    if (P.de) k_update<false, true><<<grid, block, 0, st>>>(P, G, A, box);
-    else      k_update<false, false><<<grid, block, 0, st>>>(P, G, A, box);
+    if (P.de) VLCT_UPDATE(false, true);
+    else      VLCT_UPDATE(false, false);
   }
+#undef VLCT_UPDATE
 }
 
 void launch_timestep_reset(const LaunchCtx& ctx, unsigned long long* dt_bits)
