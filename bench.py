@@ -482,30 +482,43 @@ def run_e2e(args, method, fields, n_local, width, world, dev):
     m2 = EnzoMethodMHDVlct(PARAMS)
     hb = Block(host_np, n_local, GHOST, width)
     steps = max(2, min(args.steps, 4))
-    for _ in range(1):
-        dt = m2.timestep(hb)
-        m2.compute(hb, dt)
-    if world > 1:
-        dist.barrier()
-    h2d0, d2h0 = m2.staged_bytes()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        dt = m2.timestep(hb)
-        m2.compute(hb, dt)
-    elapsed = time.perf_counter() - t0
-    h2d1, d2h1 = m2.staged_bytes()
-    h2d, d2h = (h2d1 - h2d0) // steps, (d2h1 - d2h0) // steps
-    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
-    m2.close()
     cells = n_local[0] * n_local[1] * n_local[2] * world * steps
-    return {"value": cells / elapsed, "unit": UNIT,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": 1e3 * elapsed / steps,
-            "path": "vlct_timestep + vlct_compute with mem_space=HOST "
-                    "(pinned host arrays, copies inside the calls)"}
+
+    def timed(reuse):
+        m2.set_option("host_mirror_reuse", reuse)
+        for _ in range(1):
+            dt = m2.timestep(hb)
+            m2.compute(hb, dt)
+        if world > 1:
+            dist.barrier()
+        h2d0, d2h0 = m2.staged_bytes()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dt = m2.timestep(hb)
+            m2.compute(hb, dt)
+        elapsed = time.perf_counter() - t0
+        h2d1, d2h1 = m2.staged_bytes()
+        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+        return {"value": cells / elapsed, "unit": UNIT,
+                "h2d_bytes_per_step": (h2d1 - h2d0) // steps,
+                "d2h_bytes_per_step": (d2h1 - d2h0) // steps,
+                "steps": steps, "ms_per_step": 1e3 * elapsed / steps}
+
+    out = timed(0)
+    out["path"] = ("vlct_timestep + vlct_compute with mem_space=HOST (pinned host "
+                   "arrays; every call uploads its inputs and downloads its "
+                   "outputs, as a z-pass pipeline of H2D / kernels / D2H)")
+    # informational: the same loop with the caller's promise that nobody writes
+    # the fields between compute and the next timestep (Enzo-E's cycle order),
+    # so that timestep reuses the device copy compute left behind
+    reuse = timed(1)
+    reuse["path"] = "as e2e, option host_mirror_reuse = 1 (include/vlct.h)"
+    out["with_host_mirror_reuse"] = reuse
+    m2.close()
+    return out
 
 
 def main():

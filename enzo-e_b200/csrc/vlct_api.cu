@@ -43,6 +43,12 @@ struct vlct_handle {
   // device mirror of a HOST block (mem_space == VLCT_MEM_HOST)
   bool have_mirror = false;
   vlct_block mirror;
+  // option "host_mirror_reuse": after vlct_compute of a HOST block the mirror
+  // holds exactly what was copied back; a vlct_timestep of the same block that
+  // follows immediately may use it instead of uploading the fields again
+  long long host_mirror_reuse = 0;
+  bool mirror_is_current = false;
+  vlct_block mirror_of;          // the host block the mirror is a copy of
   std::vector<void*> mirror_allocs;
   // stacked device copy of a batch of blocks (vlct_compute_batch)
   vlct_block arena;
@@ -633,13 +639,35 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
   // HOST: stage through the device mirror; synchronous
   cudaStream_t st = h->own_stream;
   if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
-  if (const int levels = host_levels(h, G))
-    return compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels);
-  if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
-  if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
-  if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
-  CUDA_TRY(h, cudaStreamSynchronize(st));
-  return VLCT_OK;
+  h->mirror_is_current = false;
+  if (const int levels = host_levels(h, G)) {
+    rc = compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels);
+  } else {
+    if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
+    if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
+    if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  if (rc == VLCT_OK) {
+    // every field timestep() reads was uploaded and/or written by this call
+    h->mirror_is_current = true;
+    h->mirror_of = *b;
+  }
+  return rc;
+}
+
+/// may vlct_timestep(b) read the device mirror instead of uploading b's fields?
+bool mirror_serves(const vlct_handle* h, const vlct_block* b)
+{
+  if (!h->host_mirror_reuse || !h->mirror_is_current) return false;
+  const vlct_block& m = h->mirror_of;
+  if (b->nx != m.nx || b->ny != m.ny || b->nz != m.nz || b->gx != m.gx ||
+      b->gy != m.gy || b->gz != m.gz) return false;
+  for (int f = 0; f < kNumFields; f++)
+    if (b->*(kFields[f].member) != m.*(kFields[f].member)) return false;
+  for (int s = 0; s < h->P.nsc; s++)
+    if (b->passive[s] != m.passive[s]) return false;
+  return true;
 }
 
 /// launches DE sync + pressure + CFL minimum on the block's stream
@@ -744,7 +772,9 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
   } else {
     st = h->own_stream;
     if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
-    int levels = host_levels(h, G);
+    const bool reuse = mirror_serves(h, b);
+    h->mirror_is_current = false;   // one timestep per compute; DE sync rewrites energies
+    int levels = reuse ? 0 : host_levels(h, G);
     if (h->cfg.time_scheme == VLCT_TIME_EULER && h->host_pipeline_levels > 0)
       levels = (int) h->host_pipeline_levels;   // no stage coupling in timestep
     if (levels > 0) {
@@ -754,7 +784,8 @@ int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
       *dt_out = dt_min * h->cfg.courant;
       return VLCT_OK;
     }
-    if ((rc = mirror_copy(h, b, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
+    if (!reuse &&
+        (rc = mirror_copy(h, b, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
     db = &h->mirror;
   }
   if ((rc = timestep_launch(h, db, G, st)) != VLCT_OK) return rc;
@@ -1104,6 +1135,9 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
   if (strcmp(key, "host_pipeline_levels") == 0) {
     if (value < -1) return fail(h, VLCT_ERR_INVALID_CONFIG, "host_pipeline_levels >= -1");
     h->host_pipeline_levels = value;
+  } else if (strcmp(key, "host_mirror_reuse") == 0) {
+    h->host_mirror_reuse = (value != 0);
+    h->mirror_is_current = false;
   } else if (strcmp(key, "batch_max_blocks") == 0) {
     if (value < 1) return fail(h, VLCT_ERR_INVALID_CONFIG, "batch_max_blocks >= 1");
     h->batch_max_blocks = value;

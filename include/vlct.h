@@ -251,6 +251,16 @@ int vlct_timestep_batch(vlct_handle *h, const vlct_block *blocks, int nblocks,
                         double *dt_out);
 
 /* Tuning knobs of a handle (none changes any result bit):
+ *   "host_mirror_reuse"  (0 = off, default) A PROMISE BY THE CALLER: between
+ *        vlct_compute of a VLCT_MEM_HOST block and the vlct_timestep of the
+ *        same block that follows it, nobody writes the block's fields. That is
+ *        the order of Enzo-E's cycle on a unigrid when "mhd_vlct" is the last
+ *        Method that touches them: compute, then the stopping phase's
+ *        timestep, and only then the next refresh
+ *        (src/Cello/control_charm.cpp:111-150, control_stopping.cpp:44-142).
+ *        With the option on, that timestep reads the device copy the compute
+ *        call left behind instead of uploading eight fields again. Any other
+ *        call order falls back to uploading.
  *   "batch_max_blocks"  blocks stacked per launch set by the *_batch entry
  *        points (default 1024; also limited by 65535 / (mz + 1)).
  *   "host_pipeline_levels"   VLCT_MEM_HOST blocks are staged through the GPU

@@ -183,3 +183,46 @@ def test_part_arguments_are_validated():
     with pytest.raises(VlctError):
         method.set_option("no_such_option", 1)
     method.close()
+
+
+@pytest.mark.parametrize("name", ["mhd_hlld_plm", "mhd_hlld_athena_de",
+                                  "hd_hllc_plm_de_scalars"])
+@pytest.mark.parametrize("levels", [0, 4])
+def test_host_mirror_reuse_bit_exact(name, levels):
+    """option host_mirror_reuse: the timestep that follows a compute of the
+    same HOST block reads the device copy instead of uploading again -- same
+    bits, fewer bytes; another block in between falls back to uploading"""
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**CASES[name])
+    host = random_state(cfg, N, G, seed=27)
+    other = random_state(cfg, N, G, seed=28)
+    want, dts_want = run_cpu(cfg, host, N, G, D, 3)
+    want_other, dts_other = run_cpu(cfg, other, N, G, D, 1)
+    runs = {}
+    for reuse in (0, 1):
+        f, fo = copy_state(host), copy_state(other)
+        method = EnzoMethodMHDVlct(config=cfg)
+        method.set_option("host_pipeline_levels", levels)
+        method.set_option("host_mirror_reuse", reuse)
+        block = Block(f, N, G, D, passive=passive_names(cfg))
+        block_o = Block(fo, N, G, D, passive=passive_names(cfg))
+        dts = []
+        for step in range(3):
+            dt = method.timestep(block)
+            method.compute(block, dt)
+            dts.append(dt)
+            if step == 1:
+                # a different block right after a compute: must not be served
+                # from the mirror of `block`
+                dto = method.timestep(block_o)
+                method.compute(block_o, dto)
+                assert dto == dts_other[0]
+        runs[reuse] = method.staged_bytes()
+        method.close()
+        assert dts == dts_want
+        check(want, f)
+        check(want_other, fo)
+    # with reuse one of the three timesteps of `block` (the one after its own
+    # compute, step 0 -> 1) skips its upload
+    assert runs[1][0] < runs[0][0]
+    assert runs[1][1] == runs[0][1]
