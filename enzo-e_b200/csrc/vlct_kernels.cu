@@ -61,15 +61,24 @@ inline dim3 grid_for(const Geom& G, const Box& b)
 // ---------------------------------------------------------------------------
 template <bool STACKED>
 __global__ void __launch_bounds__(kBlock)
-k_specific_scalars(const int nsc, const typename GeomFor<STACKED>::type G, const State u,
-                   const ScalarPtrs spec, const Box box)
+k_specific_scalars(const int nsc, const typename GeomFor<STACKED>::type G,
+                   const __grid_constant__ State u,
+                   const __grid_constant__ ScalarPtrs spec, const Box box)
 {
   VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
   (void) kl;
   const size_t c = cidx(G, k, j, i);
   const double rho = __ldg(u.rho + c);
+  // all quotients share one reciprocal chain of rho (vlct_fpops.cuh: the same
+  // bits as the built-in division wherever its range guard passes; otherwise
+  // the cell is redone with the built-in operator)
+  FastOps op;
+  const double r = op.prep(rho);
   for (int s = 0; s < nsc; s++)
-    spec.p[s][c] = __ldg(u.sc[s] + c) / rho;
+    spec.p[s][c] = op.quotz(__ldg(u.sc[s] + c), rho, r);
+  if (op.bad)
+    for (int s = 0; s < nsc; s++)
+      spec.p[s][c] = __ldg(u.sc[s] + c) / rho;
 }
 
 // ---------------------------------------------------------------------------

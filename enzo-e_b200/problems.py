@@ -105,3 +105,48 @@ def mhd_blast(n_local, g, lower, width, device="cuda", gamma=5.0 / 3.0,
 
 def field_bytes(fields):
     return sum(v.numel() * v.element_size() for v in fields.values())
+
+
+def hydro_sod(n_local, g, lower, width, device="cuda", gamma=1.4,
+              dual_energy=True, split=0.5):
+    """3-D Sod problem (BASELINE configs[1]a): the shock-tube states of
+    src/Enzo/initial/EnzoInitialShockTube.cpp:37-80 (rho, p = 1, 1 | 0.125,
+    0.1, v = 0) split at x = `split`."""
+    (xc, _), (yc, _), (zc, _) = _coords(n_local, g, lower, width, device)
+    mz, my, mx = zc.numel(), yc.numel(), xc.numel()
+    shape = (mz, my, mx)
+    left = (xc.view(1, 1, mx) < split).expand(shape)
+    one = torch.ones(shape, dtype=torch.float64, device=device)
+    f = {"density": torch.where(left, 1.0 * one, 0.125 * one)}
+    p = torch.where(left, 1.0 * one, 0.1 * one)
+    for k in "xyz":
+        f["velocity_" + k] = torch.zeros(shape, dtype=torch.float64, device=device)
+    eint = p / ((gamma - 1.0) * f["density"])
+    f["total_energy"] = eint.clone()
+    if dual_energy:
+        f["internal_energy"] = eint.clone()
+    f["pressure"] = torch.zeros(shape, dtype=torch.float64, device=device)
+    return {k: v.contiguous() for k, v in f.items()}
+
+
+def hydro_blast(n_local, g, lower, width, device="cuda", gamma=5.0 / 3.0,
+                dual_energy=True, center=(0.5, 0.5, 0.5), radius_cells=3.5,
+                p_in=1.0e2, p_out=1.0e-5):
+    """Sedov-like blast (BASELINE configs[1]b): rho = 1, p = 1e-5 with p = 1e2
+    inside 3.5 cells of the centre."""
+    (xc, _), (yc, _), (zc, _) = _coords(n_local, g, lower, width, device)
+    mz, my, mx = zc.numel(), yc.numel(), xc.numel()
+    shape = (mz, my, mx)
+    r2 = ((xc.view(1, 1, mx) - center[0]) ** 2 + (yc.view(1, my, 1) - center[1]) ** 2
+          + (zc.view(mz, 1, 1) - center[2]) ** 2).expand(shape)
+    one = torch.ones(shape, dtype=torch.float64, device=device)
+    f = {"density": one.clone()}
+    p = torch.where(r2 < (radius_cells * width[0]) ** 2, p_in * one, p_out * one)
+    for k in "xyz":
+        f["velocity_" + k] = torch.zeros(shape, dtype=torch.float64, device=device)
+    eint = p / ((gamma - 1.0) * f["density"])
+    f["total_energy"] = eint.clone()
+    if dual_energy:
+        f["internal_energy"] = eint.clone()
+    f["pressure"] = torch.zeros(shape, dtype=torch.float64, device=device)
+    return {k: v.contiguous() for k, v in f.items()}
