@@ -145,6 +145,7 @@ class Domain:
         z_lo = block.g[2] + abi.PART_REACH_BELOW
         z_hi = mz - block.g[2] - abi.PART_REACH_ABOVE
         can_split = (overlap and self.grid[2] > 1 and z_hi > z_lo
+                     and method.config.time_scheme == abi.TIME_SCHEME["vl"]
                      and hasattr(dt, "data_ptr")
                      and getattr(block, "stream_is_current", False))
         pending = self.refresh(method, block, defer_z=can_split)
