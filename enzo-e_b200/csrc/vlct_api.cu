@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -51,13 +52,25 @@ struct vlct_handle {
   vlct_block mirror_of;          // the host block the mirror is a copy of
   std::vector<void*> mirror_allocs;
   // stacked device copy of a batch of blocks (vlct_compute_batch)
-  vlct_block arena;
-  int arena_capacity = 0;                 // blocks the arena / scratch can hold
-  std::vector<void*> arena_allocs;
+  // (two of them: HOST batches are double-buffered so that the copies of one
+  // sub-batch overlap the kernels of another)
+  vlct_block arena[2];
+  int arena_capacity[2] = { 0, 0 };       // blocks each arena can hold
+  std::vector<void*> arena_allocs[2];
+  long long host_batch_blocks = 0;        // option: HOST sub-batch size, 0 = auto
+  // option: how HOST batches cross PCIe. 0 = one cudaMemcpyBatchAsync per
+  // field set (copy engines), 1 = gather / scatter kernels on pinned memory
+  // (zero-copy), 2 = one cudaMemcpyAsync per (block, field)
+  long long host_batch_copy_mode = 0;
+  bool batch_memcpy_works = true;         // cudaMemcpyBatchAsync (CUDA >= 12.8)
   double** d_ptr_table = nullptr;         // device: [field][block] user pointers
   double** h_ptr_table = nullptr;         // pinned staging of the same
   bool ptr_table_valid = false;           // device table == staging, for ptr_table_nb
   int ptr_table_nb = 0;
+  bool ptr_table_usable = false;          // every pointer is device-accessible
+  // host pointers known to be pinned / registered -> their device alias
+  std::unordered_map<const void*, double*> mapped_host;
+  std::unordered_map<void*, size_t> registered;   // vlct_host_register ranges
   size_t ptr_table_count = 0;
   size_t scratch_levels = 0;              // z levels the scratch arrays hold
   bool stepped = false;                   // a compute has filled the flux arrays
@@ -91,7 +104,7 @@ int fail(vlct_handle* h, int code, const char* fmt, ...)
                   cudaGetErrorString(err__), __FILE__, __LINE__);            \
   } while (0)
 
-enum Pool { POOL_SCRATCH = 1, POOL_MIRROR = 0, POOL_ARENA = 2 };
+enum Pool { POOL_SCRATCH = 1, POOL_MIRROR = 0, POOL_ARENA = 2 /* + arena index */ };
 
 int dev_alloc(vlct_handle* h, double** out, size_t count, int pool = POOL_SCRATCH)
 {
@@ -99,7 +112,8 @@ int dev_alloc(vlct_handle* h, double** out, size_t count, int pool = POOL_SCRATC
   CUDA_TRY(h, cudaMalloc(&p, count * sizeof(double)));
   CUDA_TRY(h, cudaMemset(p, 0, count * sizeof(double)));
   (pool == POOL_SCRATCH ? h->allocations
-   : pool == POOL_MIRROR ? h->mirror_allocs : h->arena_allocs).push_back(p);
+   : pool == POOL_MIRROR ? h->mirror_allocs
+   : h->arena_allocs[pool - POOL_ARENA]).push_back(p);
   if (pool == POOL_SCRATCH) h->scratch_bytes += (long long) (count * sizeof(double));
   *out = (double*) p;
   return VLCT_OK;
@@ -534,13 +548,15 @@ void vlct_destroy(vlct_handle* h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void* p : h->allocations) cudaFree(p);
     for (void* p : h->mirror_allocs) cudaFree(p);
-    for (void* p : h->arena_allocs) cudaFree(p);
+    for (int a = 0; a < 2; a++)
+      for (void* p : h->arena_allocs[a]) cudaFree(p);
     if (h->d_face_stage) cudaFree(h->d_face_stage);
     if (h->d_ptr_table) cudaFree(h->d_ptr_table);
     if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
     if (h->d_dt_bits) cudaFree(h->d_dt_bits);
     if (h->d_step) cudaFree(h->d_step);
     if (h->h_dt_bits) cudaFreeHost(h->h_dt_bits);
+    for (auto& r : h->registered) cudaHostUnregister(r.first);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
     if (h->out_stream) cudaStreamDestroy(h->out_stream);
@@ -840,44 +856,79 @@ int check_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
   return VLCT_OK;
 }
 
-/// stacked device arrays for `nrep` blocks shaped like b0 (grow-only)
-int ensure_arena(vlct_handle* h, const vlct_block& b0, const Geom& G)
+/// stacked device arrays (arena `a`) for `nrep` blocks shaped like b0 (grow-only)
+int ensure_arena(vlct_handle* h, int a, const vlct_block& b0, const Geom& G)
 {
-  bool enough = (h->arena_capacity >= G.nrep);
+  vlct_block& arena = h->arena[a];
+  bool enough = (h->arena_capacity[a] >= G.nrep);
   for (int f = 0; enough && f < kNumFields; f++)
-    if (b0.*(kFields[f].member) != nullptr && h->arena.*(kFields[f].member) == nullptr)
+    if (b0.*(kFields[f].member) != nullptr && arena.*(kFields[f].member) == nullptr)
       enough = false;     // a field the arena was not built with
   if (enough) {
     // shape is fixed per handle; cell widths may change from batch to batch
-    h->arena.dx = b0.dx; h->arena.dy = b0.dy; h->arena.dz = b0.dz;
+    arena.dx = b0.dx; arena.dy = b0.dy; arena.dz = b0.dz;
     return VLCT_OK;
   }
   CUDA_TRY(h, cudaDeviceSynchronize());
   h->ptr_table_valid = false;
-  for (void* p : h->arena_allocs) cudaFree(p);
-  h->arena_allocs.clear();
-  h->arena = b0;
-  h->arena.mem_space = VLCT_MEM_DEVICE;
+  for (void* p : h->arena_allocs[a]) cudaFree(p);
+  h->arena_allocs[a].clear();
+  h->arena_capacity[a] = 0;
+  arena = b0;
+  arena.mem_space = VLCT_MEM_DEVICE;
   int rc;
   for (int f = 0; f < kNumFields; f++) {
-    h->arena.*(kFields[f].member) = nullptr;
+    arena.*(kFields[f].member) = nullptr;
     if (b0.*(kFields[f].member) == nullptr) continue;
     double* p;
-    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), POOL_ARENA)) != VLCT_OK)
+    if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), POOL_ARENA + a)) != VLCT_OK)
       return rc;
-    h->arena.*(kFields[f].member) = p;
+    arena.*(kFields[f].member) = p;
   }
   for (int s = 0; s < VLCT_MAX_PASSIVE; s++) {
-    h->arena.passive[s] = nullptr;
+    arena.passive[s] = nullptr;
     if (s < h->P.nsc) {
       double* p;
-      if ((rc = dev_alloc(h, &p, cell_count(G), POOL_ARENA)) != VLCT_OK) return rc;
-      h->arena.passive[s] = p;
+      if ((rc = dev_alloc(h, &p, cell_count(G), POOL_ARENA + a)) != VLCT_OK) return rc;
+      arena.passive[s] = p;
     }
   }
-  const size_t need = (size_t) (kNumFields + VLCT_MAX_PASSIVE) * (size_t) G.nrep;
+  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
+  h->arena_capacity[a] = G.nrep;
+  return VLCT_OK;
+}
+
+/// A pointer the device can dereference for p: p itself for device memory, the
+/// device alias for pinned / registered host memory (zero-copy over PCIe),
+/// nullptr for pageable host memory.
+double* device_alias(vlct_handle* h, double* p, bool host)
+{
+  if (!host || p == nullptr) return p;
+  auto it = h->mapped_host.find(p);
+  if (it != h->mapped_host.end()) return it->second;
+  cudaPointerAttributes attr;
+  double* alias = nullptr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
+      alias = (double*) attr.devicePointer;
+  } else {
+    cudaGetLastError();   // pageable memory on older drivers: not an error for us
+  }
+  if (alias != nullptr) h->mapped_host[p] = alias;   // (pageable: looked up again next time)
+  return alias;
+}
+
+/// Device table of every block's field pointers, row = field slot, column =
+/// block (all nblocks of the batch): what the gather / scatter kernels index.
+/// For HOST blocks it exists only if every array is pinned or registered
+/// (ptr_table_usable); pageable arrays go through cudaMemcpyAsync instead.
+int prepare_ptr_table(vlct_handle* h, const vlct_block* blocks, int nblocks)
+{
+  const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
+  const int nslots = kNumFields + h->P.nsc;
+  const size_t need = (size_t) (kNumFields + VLCT_MAX_PASSIVE) * (size_t) nblocks;
   if (need > h->ptr_table_count) {
-    if (h->d_face_stage) cudaFree(h->d_face_stage);
+    CUDA_TRY(h, cudaDeviceSynchronize());
     if (h->d_ptr_table) cudaFree(h->d_ptr_table);
     if (h->h_ptr_table) cudaFreeHost(h->h_ptr_table);
     CUDA_TRY(h, cudaMalloc((void**) &h->d_ptr_table, need * sizeof(double*)));
@@ -885,77 +936,110 @@ int ensure_arena(vlct_handle* h, const vlct_block& b0, const Geom& G)
     h->ptr_table_count = need;
     h->ptr_table_valid = false;
   }
-  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
-  h->arena_capacity = G.nrep;
+  bool same = h->ptr_table_valid && h->ptr_table_nb == nblocks;
+  bool usable = true;
+  std::vector<double*> fresh;
+  fresh.reserve((size_t) nslots * nblocks);
+  for (int f = 0; f < nslots; f++)
+    for (int n = 0; n < nblocks; n++) {
+      double* raw = f < kNumFields ? blocks[n].*(kFields[f].member)
+                                   : blocks[n].passive[f - kNumFields];
+      double* p = device_alias(h, raw, host);
+      if (raw != nullptr && p == nullptr) usable = false;
+      fresh.push_back(p);
+      if (same && h->h_ptr_table[(size_t) f * nblocks + n] != p) same = false;
+    }
+  h->ptr_table_usable = usable;
+  if (!usable) { h->ptr_table_valid = false; return VLCT_OK; }
+  if (!same) {
+    // the staging buffer may still be the source of an upload in flight
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    memcpy(h->h_ptr_table, fresh.data(), fresh.size() * sizeof(double*));
+    CUDA_TRY(h, cudaMemcpy(h->d_ptr_table, h->h_ptr_table,
+                           fresh.size() * sizeof(double*), cudaMemcpyHostToDevice));
+    h->ptr_table_valid = true;
+    h->ptr_table_nb = nblocks;
+  }
   return VLCT_OK;
 }
 
-/// Move a set of fields between the blocks of a batch and the stacked arena:
-/// HOST blocks by one cudaMemcpyAsync per (block, field), DEVICE blocks by one
-/// gather / scatter kernel per field over a device table of the blocks' pointers.
-int batch_copy(vlct_handle* h, const vlct_block* blocks, int nb, const Geom& G,
-               cudaStream_t st, bool to_arena, CopySet set)
+/// Move a set of fields between nb blocks of a batch (starting at block `first`
+/// of the nblocks the pointer table was prepared for) and the stacked arena:
+/// one gather / scatter kernel per field over the device table of the blocks'
+/// pointers -- device memory, or pinned / registered host memory read and
+/// written in place over PCIe --, or one cudaMemcpyAsync per (block, field) for
+/// pageable host arrays.
+int batch_copy(vlct_handle* h, int a, const vlct_block* blocks, int first, int nb,
+               int nblocks, const Geom& G, cudaStream_t st, bool to_arena, CopySet set)
 {
+  const vlct_block& arena = h->arena[a];
   const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
   const Geom one{ G.mx, G.my, G.mz, 1, 0 };
   const LaunchCtx ctx{ st, &h->launches, &h->prof };
-  // pointer table (DEVICE blocks): row = field slot, column = block
-  if (!host) {
-    auto entry = [&](int slot, int n) -> double* {
-      return slot < kNumFields ? blocks[n].*(kFields[slot].member)
-                               : blocks[n].passive[slot - kNumFields];
-    };
-    const int nslots = kNumFields + h->P.nsc;
-    bool same = h->ptr_table_valid && h->ptr_table_nb == nb;
-    for (int f = 0; same && f < nslots; f++)
-      for (int n = 0; same && n < nb; n++)
-        if (h->h_ptr_table[(size_t) f * nb + n] != entry(f, n)) same = false;
-    if (!same) {
-      // the staging buffer may still be the source of an upload in flight
-      CUDA_TRY(h, cudaStreamSynchronize(st));
-      for (int f = 0; f < nslots; f++)
-        for (int n = 0; n < nb; n++)
-          h->h_ptr_table[(size_t) f * nb + n] = entry(f, n);
-      CUDA_TRY(h, cudaMemcpyAsync(h->d_ptr_table, h->h_ptr_table,
-                                  (size_t) nslots * nb * sizeof(double*),
-                                  cudaMemcpyHostToDevice, st));
-      h->ptr_table_valid = true;
-      h->ptr_table_nb = nb;
-    }
-  }
+  // DEVICE blocks: gather / scatter kernels. HOST blocks: see host_batch_copy_mode.
+  const bool use_kernels = h->ptr_table_usable && (!host || h->host_batch_copy_mode == 1);
+  const bool use_batch_memcpy = host && !use_kernels && h->host_batch_copy_mode != 2 &&
+                                h->batch_memcpy_works;
+  std::vector<void*> dsts, srcs;
+  std::vector<size_t> sizes;
   auto move = [&](int slot, double* stacked, int face,
                   double* vlct_block::*member, int passive) -> int {
     const size_t count = field_count(one, face);
     const size_t plane = (size_t) (G.mx + (face == 0)) * (size_t) (G.my + (face == 1));
     const size_t stride = plane * (size_t) G.zper;
-    if (!host) {
-      launch_batch_copy(ctx, stacked, h->d_ptr_table + (size_t) slot * nb, nb, count,
-                        stride, to_arena);
+    if (use_kernels) {
+      launch_batch_copy(ctx, stacked, h->d_ptr_table + (size_t) slot * nblocks + first,
+                        nb, count, stride, to_arena, host);
+      if (host) h->copied_bytes[to_arena ? 0 : 1] += (long long) (nb * count * sizeof(double));
       return VLCT_OK;
     }
     for (int n = 0; n < nb; n++) {
-      double* hp = passive >= 0 ? blocks[n].passive[passive] : blocks[n].*member;
+      const vlct_block& b = blocks[first + n];
+      double* hp = passive >= 0 ? b.passive[passive] : b.*member;
       double* dp = stacked + (size_t) n * stride;
-      CUDA_TRY(h, cudaMemcpyAsync(to_arena ? (void*) dp : (void*) hp,
-                                  to_arena ? (void*) hp : (void*) dp,
-                                  count * sizeof(double),
-                                  to_arena ? cudaMemcpyHostToDevice
-                                           : cudaMemcpyDeviceToHost, st));
+      if (use_batch_memcpy) {
+        dsts.push_back(to_arena ? (void*) dp : (void*) hp);
+        srcs.push_back(to_arena ? (void*) hp : (void*) dp);
+        sizes.push_back(count * sizeof(double));
+      } else {
+        CUDA_TRY(h, cudaMemcpyAsync(to_arena ? (void*) dp : (void*) hp,
+                                    to_arena ? (void*) hp : (void*) dp,
+                                    count * sizeof(double),
+                                    to_arena ? cudaMemcpyHostToDevice
+                                             : cudaMemcpyDeviceToHost, st));
+      }
       h->copied_bytes[to_arena ? 0 : 1] += (long long) (count * sizeof(double));
     }
     return VLCT_OK;
   };
   int rc;
   for (int f = 0; f < kNumFields; f++) {
-    double* stacked = h->arena.*(kFields[f].member);
+    double* stacked = arena.*(kFields[f].member);
     if (stacked == nullptr || blocks[0].*(kFields[f].member) == nullptr) continue;
     if (!in_copy_set(h, kFields[f].member, set)) continue;
     if ((rc = move(f, stacked, kFields[f].face, kFields[f].member, -1)) != VLCT_OK)
       return rc;
   }
   for (int s = 0; s < h->P.nsc; s++)
-    if ((rc = move(kNumFields + s, h->arena.passive[s], -1, nullptr, s)) != VLCT_OK)
+    if ((rc = move(kNumFields + s, arena.passive[s], -1, nullptr, s)) != VLCT_OK)
       return rc;
+  if (use_batch_memcpy && !dsts.empty()) {
+    // all (block, field) copies of this set in ONE call, executed by the copy
+    // engines: no per-copy launch cost, no SM time, H2D and D2H truly overlap
+    cudaMemcpyAttributes attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t attr_idx = 0, fail_idx = 0;
+    cudaError_t err = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(),
+                                           dsts.size(), &attr, &attr_idx, 1, &fail_idx, st);
+    if (err != cudaSuccess) {
+      // older driver: remember, and do these copies one by one
+      cudaGetLastError();
+      h->batch_memcpy_works = false;
+      for (size_t i = 0; i < dsts.size(); i++)
+        CUDA_TRY(h, cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
+    }
+  }
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
 }
@@ -1054,20 +1138,65 @@ int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, do
   const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
   cudaStream_t st = (!host && blocks[0].stream) ? (cudaStream_t) blocks[0].stream
                                                  : h->own_stream;
-  const int chunk = batch_chunk(h, geom_of(&blocks[0]));
-  for (int first = 0; first < nblocks; first += chunk) {
-    const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
-    const Geom G = stacked_geom(blocks[0], nb);
-    if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
-    if ((rc = ensure_arena(h, blocks[0], G)) != VLCT_OK) return rc;
-    if ((rc = batch_copy(h, blocks + first, nb, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK)
-      return rc;
-    if ((rc = compute_on_device(h, &h->arena, G, dt, nullptr, st)) != VLCT_OK) return rc;
-    if ((rc = batch_copy(h, blocks + first, nb, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK)
-      return rc;
-    // the pointer table and the arena are reused by the next sub-batch
-    if (host || first + chunk < nblocks) CUDA_TRY(h, cudaStreamSynchronize(st));
+  int chunk = batch_chunk(h, geom_of(&blocks[0]));
+  if ((rc = prepare_ptr_table(h, blocks, nblocks)) != VLCT_OK) return rc;
+  if (!host) {
+    for (int first = 0; first < nblocks; first += chunk) {
+      const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
+      const Geom G = stacked_geom(blocks[0], nb);
+      if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
+      if ((rc = ensure_arena(h, 0, blocks[0], G)) != VLCT_OK) return rc;
+      if ((rc = batch_copy(h, 0, blocks, first, nb, nblocks, G, st, true,
+                           COPY_COMPUTE_IN)) != VLCT_OK) return rc;
+      if ((rc = compute_on_device(h, &h->arena[0], G, dt, nullptr, st)) != VLCT_OK) return rc;
+      if ((rc = batch_copy(h, 0, blocks, first, nb, nblocks, G, st, false,
+                           COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+      // (stream order protects the arena between consecutive sub-batches)
+    }
+    return VLCT_OK;
   }
+  // HOST blocks: a pipeline over sub-batches with two arenas -- the H2D copies
+  // of sub-batch s+1 (in_stream), the kernels of sub-batch s (st) and the D2H
+  // copies of sub-batch s-1 (out_stream) overlap; the kernels of consecutive
+  // sub-batches share the scratch arrays and run one after the other on st.
+  if (h->host_batch_blocks > 0) {
+    if (h->host_batch_blocks < chunk) chunk = (int) h->host_batch_blocks;
+  } else if (nblocks > 4) {
+    // auto: at least ~4 sub-batches, each of at least ~16 MB per field
+    const size_t per_block = geom_of(&blocks[0]).cells() * sizeof(double);
+    int want = (nblocks + 3) / 4;
+    const int min_blocks = (int) (((size_t) 16 << 20) / per_block) + 1;
+    if (want < min_blocks) want = min_blocks;
+    if (want < chunk) chunk = want;
+  }
+  const Geom Gmax = stacked_geom(blocks[0], nblocks < chunk ? nblocks : chunk);
+  if ((rc = ensure_scratch(h, Gmax)) != VLCT_OK) return rc;
+  const int narena = (nblocks > chunk) ? 2 : 1;
+  for (int a = 0; a < narena; a++)
+    if ((rc = ensure_arena(h, a, blocks[0], Gmax)) != VLCT_OK) return rc;
+  h->events_used = 0;
+  h->mirror_is_current = false;
+  cudaEvent_t downloaded[2] = { nullptr, nullptr };   // arena free again
+  int sub = 0;
+  for (int first = 0; first < nblocks; first += chunk, sub++) {
+    const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
+    const int a = sub % narena;
+    const Geom G = stacked_geom(blocks[0], nb);
+    if (downloaded[a]) CUDA_TRY(h, cudaStreamWaitEvent(h->in_stream, downloaded[a], 0));
+    if ((rc = batch_copy(h, a, blocks, first, nb, nblocks, G, h->in_stream, true,
+                         COPY_COMPUTE_IN)) != VLCT_OK) return rc;
+    cudaEvent_t ev;
+    if ((rc = record_event(h, h->in_stream, &ev)) != VLCT_OK) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, ev, 0));
+    if ((rc = compute_on_device(h, &h->arena[a], G, dt, nullptr, st)) != VLCT_OK) return rc;
+    if ((rc = record_event(h, st, &ev)) != VLCT_OK) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->out_stream, ev, 0));
+    if ((rc = batch_copy(h, a, blocks, first, nb, nblocks, G, h->out_stream, false,
+                         COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+    if ((rc = record_event(h, h->out_stream, &downloaded[a])) != VLCT_OK) return rc;
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->out_stream));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
   return VLCT_OK;
 }
 
@@ -1084,14 +1213,15 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
                                                  : h->own_stream;
   const int chunk = batch_chunk(h, geom_of(&blocks[0]));
   const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  if ((rc = prepare_ptr_table(h, blocks, nblocks)) != VLCT_OK) return rc;
   for (int first = 0; first < nblocks; first += chunk) {
     const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
     const Geom G = stacked_geom(blocks[0], nb);
-    if ((rc = ensure_arena(h, blocks[0], G)) != VLCT_OK) return rc;
-    if ((rc = batch_copy(h, blocks + first, nb, G, st, true, COPY_TIMESTEP_IN)) != VLCT_OK)
-      return rc;
+    if ((rc = ensure_arena(h, 0, blocks[0], G)) != VLCT_OK) return rc;
+    if ((rc = batch_copy(h, 0, blocks, first, nb, nblocks, G, st, true,
+                         COPY_TIMESTEP_IN)) != VLCT_OK) return rc;
     // the minimum accumulates over the sub-batches
-    if ((rc = timestep_launch(h, &h->arena, G, st, kNoClip, first == 0)) != VLCT_OK)
+    if ((rc = timestep_launch(h, &h->arena[0], G, st, kNoClip, first == 0)) != VLCT_OK)
       return rc;
     // timestep writes "pressure" and (dual energy) total / internal energy
     {
@@ -1103,18 +1233,20 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
                                               &vlct_block::internal_energy };
       const int nout = h->P.de ? 3 : 1;
       for (int o = 0; o < nout; o++) {
-        if (host) {
+        if (h->ptr_table_usable && (!host || h->host_batch_copy_mode == 1)) {
+          int slot = 0;
+          for (int f = 0; f < kNumFields; f++) if (kFields[f].member == outs[o]) slot = f;
+          launch_batch_copy(ctx, h->arena[0].*(outs[o]),
+                            h->d_ptr_table + (size_t) slot * nblocks + first, nb, count,
+                            stride, false, host);
+          if (host) h->copied_bytes[1] += (long long) (nb * count * sizeof(double));
+        } else {
           for (int n = 0; n < nb; n++) {
             CUDA_TRY(h, cudaMemcpyAsync(bb[n].*(outs[o]),
-                                        h->arena.*(outs[o]) + (size_t) n * stride,
+                                        h->arena[0].*(outs[o]) + (size_t) n * stride,
                                         count * sizeof(double), cudaMemcpyDeviceToHost, st));
             h->copied_bytes[1] += (long long) (count * sizeof(double));
           }
-        } else {
-          int slot = 0;
-          for (int f = 0; f < kNumFields; f++) if (kFields[f].member == outs[o]) slot = f;
-          launch_batch_copy(ctx, h->arena.*(outs[o]), h->d_ptr_table + (size_t) slot * nb,
-                            nb, count, stride, false);
         }
       }
     }
@@ -1129,6 +1261,40 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
   return VLCT_OK;
 }
 
+int vlct_host_register(vlct_handle* h, void* ptr, unsigned long long bytes)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (ptr == nullptr || bytes == 0)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_host_register: empty range");
+  CUDA_TRY(h, cudaHostRegister(ptr, (size_t) bytes, cudaHostRegisterPortable |
+                                                     cudaHostRegisterMapped));
+  h->registered[ptr] = (size_t) bytes;
+  return VLCT_OK;
+}
+
+int vlct_host_unregister(vlct_handle* h, void* ptr)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  auto it = h->registered.find(ptr);
+  if (it == h->registered.end())
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_host_unregister: range was not registered through this handle");
+  // nothing of this handle may still be copying from / to the range
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  const char* lo = (const char*) ptr;
+  const char* hi = lo + it->second;
+  for (auto m = h->mapped_host.begin(); m != h->mapped_host.end();) {
+    const char* p = (const char*) m->first;
+    if (p >= lo && p < hi) m = h->mapped_host.erase(m);
+    else ++m;
+  }
+  h->ptr_table_valid = false;
+  h->mirror_is_current = false;
+  h->registered.erase(it);
+  CUDA_TRY(h, cudaHostUnregister(ptr));
+  return VLCT_OK;
+}
+
 int vlct_set_option(vlct_handle* h, const char* key, long long value)
 {
   if (h == nullptr || key == nullptr) return VLCT_ERR_INVALID_CONFIG;
@@ -1138,6 +1304,13 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
   } else if (strcmp(key, "host_mirror_reuse") == 0) {
     h->host_mirror_reuse = (value != 0);
     h->mirror_is_current = false;
+  } else if (strcmp(key, "host_batch_copy_mode") == 0) {
+    if (value < 0 || value > 2)
+      return fail(h, VLCT_ERR_INVALID_CONFIG, "host_batch_copy_mode in {0, 1, 2}");
+    h->host_batch_copy_mode = value;
+  } else if (strcmp(key, "host_batch_blocks") == 0) {
+    if (value < 0) return fail(h, VLCT_ERR_INVALID_CONFIG, "host_batch_blocks >= 0");
+    h->host_batch_blocks = value;
   } else if (strcmp(key, "batch_max_blocks") == 0) {
     if (value < 1) return fail(h, VLCT_ERR_INVALID_CONFIG, "batch_max_blocks >= 1");
     h->batch_max_blocks = value;

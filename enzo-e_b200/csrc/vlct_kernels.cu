@@ -792,11 +792,18 @@ void launch_face_flux(const LaunchCtx& ctx, const Geom& G, const double* flux,
 }
 
 void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,
-                       int nblocks, size_t count, size_t stride, bool to_stacked)
+                       int nblocks, size_t count, size_t stride, bool to_stacked,
+                       bool over_pcie)
 {
   if (count == 0 || nblocks == 0) return;
   int bx = (int) ((count + 255) / 256);
-  const int cap = (148 * 16 + nblocks - 1) / nblocks;
+  // Device-to-device copies want the whole GPU. Copies that read or write
+  // pinned host memory in place are bound by PCIe and must leave the SMs to
+  // the kernels (and to the copy in the other direction) they overlap with:
+  // ~2 thread blocks per SM keep far more bytes in flight than the link needs.
+  const int total = over_pcie ? 148 * 2 : 148 * 16;
+  int cap = (total + nblocks - 1) / nblocks;
+  if (over_pcie && nblocks > total) cap = 1;
   if (bx > cap) bx = cap;
   ScopedLaunch sl(ctx, to_stacked ? "k_batch_gather" : "k_batch_scatter");
   k_batch_copy<<<dim3(bx, nblocks), 256, 0, ctx.st>>>(stacked, ptrs, count, stride,

@@ -166,7 +166,8 @@ void launch_face_flux(const LaunchCtx& ctx, const Geom& G, const double* flux,
 /// batch of blocks <-> their stacked array (ptrs: device table of nblocks
 /// device pointers, `count` elements each, stacked `stride` elements apart)
 void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptrs,
-                       int nblocks, size_t count, size_t stride, bool to_stacked);
+                       int nblocks, size_t count, size_t stride, bool to_stacked,
+                       bool over_pcie = false);
 
 /// halo slab pack / unpack of one field along one axis
 /// lo..lo+g: range along the axis; the slab spans the full other extents

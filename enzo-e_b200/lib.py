@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
     "vlct_compute_dev_part", "vlct_set_option",
     "vlct_compute_batch", "vlct_timestep_batch", "vlct_save_face_fluxes",
+    "vlct_host_register", "vlct_host_unregister",
     "vlct_last_error", "vlct_status_string",
     "vlct_kernel_launches", "vlct_scratch_bytes", "vlct_staged_bytes",
     "vlct_synchronize",
@@ -69,6 +70,8 @@ def load():
         "vlct_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "vlct_compute_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_double]),
         "vlct_timestep_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, dp]),
+        "vlct_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ulonglong]),
+        "vlct_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
         "vlct_save_face_fluxes": (C.c_int, [C.c_void_p, blkp,
                                             C.POINTER(abi.VlctFaceFluxes)]),
         "vlct_last_error": (C.c_char_p, [C.c_void_p]),

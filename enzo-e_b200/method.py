@@ -222,6 +222,15 @@ class EnzoMethodMHDVlct:
                                                   C.byref(out)))
         return out.value
 
+    def host_register(self, array):
+        """page-lock a numpy array for fast staging (vlct_host_register)"""
+        self._check(self._lib.vlct_host_register(
+            self._h, array.ctypes.data_as(C.c_void_p), array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(self._lib.vlct_host_unregister(
+            self._h, array.ctypes.data_as(C.c_void_p)))
+
     def set_option(self, key, value):
         self._check(self._lib.vlct_set_option(self._h, key.encode(), int(value)))
 
