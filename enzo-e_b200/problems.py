@@ -150,3 +150,192 @@ def hydro_blast(n_local, g, lower, width, device="cuda", gamma=5.0 / 3.0,
         f["internal_energy"] = eint.clone()
     f["pressure"] = torch.zeros(shape, dtype=torch.float64, device=device)
     return {k: v.contiguous() for k, v in f.items()}
+
+
+# ---------------------------------------------------------------------------
+# the reference's answer-test problems, generated in device memory
+# ---------------------------------------------------------------------------
+_CELLO_PI = 3.14159265358979324          # src/Cello/cello.hpp:623
+
+
+def _rotation(alpha, beta):
+    """Rotation (src/Enzo/initial/EnzoInitialInclinedWave.cpp:54-117): the
+    wave travels along x0, the axis x rotated by beta about z and alpha about
+    the new y"""
+    ca, sa, cb, sb = math.cos(alpha), math.sin(alpha), math.cos(beta), math.sin(beta)
+    return [[ca * cb, ca * sb, sa], [-1.0 * sb, cb, 0.0],
+            [-1.0 * sa * cb, -1.0 * sa * sb, ca]]
+
+
+def _wave_table(wave_type, gamma, positive_vel, parallel_vel):
+    """background state and eigenvector of a linear wave in conserved form
+    (prepare_MHD_initializers_ / prepare_HD_initializers_,
+    EnzoInitialInclinedWave.cpp:941-1017, 1022-1122)"""
+    sgn = 1.0 if positive_vel else -1.0
+    w = {"b_back": (0.0, 0.0, 0.0), "b1_ev": 0.0, "b2_ev": 0.0, "has_a": False}
+    hd = wave_type in ("sound", "hd_entropy", "hd_transv_entropy_v1",
+                       "hd_transv_entropy_v2")
+    if hd:
+        v0 = 0.0
+        if parallel_vel is not None:
+            v0 = parallel_vel
+        elif wave_type != "sound":
+            v0 = sgn
+        v2sq = v0 * v0
+        w.update(rho_back=1.0, mom_back=(v0, 0.0, 0.0),
+                 etot_back=(1.0 / gamma) / (gamma - 1.0) + 0.5 * v2sq)
+        if wave_type == "sound":
+            h_back = 1.0 / (gamma - 1.0) + 0.5 * v2sq
+            cs = sgn * 1.0
+            w.update(rho_ev=1.0, mom_ev=(v0 + cs, 0.0, 0.0), etot_ev=h_back + v0 * cs)
+        elif wave_type == "hd_entropy":
+            w.update(rho_ev=1.0, mom_ev=(v0, 0.0, 0.0), etot_ev=0.5 * v2sq)
+        elif wave_type == "hd_transv_entropy_v1":
+            w.update(rho_ev=0.0, mom_ev=(0.0, 1.0, 0.0), etot_ev=0.0)
+        else:
+            w.update(rho_ev=0.0, mom_ev=(0.0, 0.0, 1.0), etot_ev=0.0)
+        return w
+    w.update(rho_back=1.0, mom_back=(0.0, 0.0, 0.0), b_back=(1.0, 1.5, 0.0),
+             etot_back=(1.0 / gamma) / (gamma - 1.0) + 1.625, has_a=True)
+    if wave_type == "mhd_entropy":
+        w["mom_back"] = (sgn, 0.0, 0.0)
+        w["etot_back"] += 0.5
+    c = 0.5 / math.sqrt(5.0)
+    if wave_type == "fast":
+        w.update(rho_ev=2.0 * c, mom_ev=(sgn * 4.0 * c, -1.0 * sgn * 2.0 * c, 0.0),
+                 etot_ev=9.0 * c, b1_ev=4.0 * c)
+    elif wave_type == "alfven":
+        w.update(rho_ev=0.0, mom_ev=(0.0, 0.0, -1.0 * sgn), etot_ev=0.0, b2_ev=1.0)
+    elif wave_type == "slow":
+        w.update(rho_ev=4.0 * c, mom_ev=(sgn * 2.0 * c, sgn * 4.0 * c, 0.0),
+                 etot_ev=3.0 * c, b1_ev=-2.0 * c)
+    elif wave_type == "mhd_entropy":
+        w.update(rho_ev=1.0, mom_ev=(sgn, 0.0, 0.0), etot_ev=0.5)
+    else:
+        raise ValueError(f"unknown wave type {wave_type!r}")
+    return w
+
+
+def inclined_wave(n_local, g, lower, width, wave_type, alpha, beta, device="cuda",
+                  gamma=5.0 / 3.0, amplitude=1e-6, lam=1.0, positive_vel=True,
+                  parallel_vel=None, mhd=True, dual_energy=False):
+    """EnzoInitialInclinedWave (src/Enzo/initial/EnzoInitialInclinedWave.cpp:
+    setup_fluid_ :543-643, setup_bfield :426-490) with the face B taken from
+    the curl of the vector potential (EnzoInitialBCenter.cpp:43-127): the
+    linear-wave problems of input/vlct/{MHD,HD}_linear_wave, generated where
+    they are used. wave_type: fast | alfven | slow | mhd_entropy | sound |
+    hd_entropy | hd_transv_entropy_v1 | hd_transv_entropy_v2."""
+    (xc, xf), (yc, yf), (zc, zf) = _coords(n_local, g, lower, width, device)
+    R = _rotation(alpha, beta)
+    w = _wave_table(wave_type, gamma, positive_vel, parallel_vel)
+
+    def rot_fwd(x, y, z):
+        return tuple(R[r][0] * x + R[r][1] * y + R[r][2] * z for r in range(3))
+
+    def rot_inv(r0, r1, r2):
+        return tuple(R[0][c] * r0 + R[1][c] * r1 + R[2][c] * r2 for c in range(3))
+
+    def grid(x, y, z):     # broadcast 1-D coordinates to (z, y, x)
+        return x.view(1, 1, -1), y.view(1, -1, 1), z.view(-1, 1, 1)
+
+    f = {}
+    if mhd:
+        def potential(x, y, z):
+            x0, x1, x2 = rot_fwd(*grid(x, y, z))
+            ct = torch.cos(2.0 * _CELLO_PI * x0 / lam)
+            r0 = x2 * amplitude * w["b1_ev"] * ct - x1 * amplitude * w["b2_ev"] * ct
+            r1 = w["b_back"][2] * x0 + 0.0 * x1
+            r2 = w["b_back"][0] * x1 - w["b_back"][1] * x0
+            return rot_inv(r0, r1, r2)
+        if w["has_a"]:
+            Ax = potential(xc, yf, zf)[0].contiguous()       # (mz+1, my+1, mx)
+            Ay = potential(xf, yc, zf)[1].contiguous()       # (mz+1, my, mx+1)
+            Az = potential(xf, yf, zc)[2].contiguous()       # (mz, my+1, mx+1)
+            dx, dy, dz = width
+            f["bfieldi_x"] = ((Az[:, 1:, :] - Az[:, :-1, :]) / dy
+                              - (Ay[1:, :, :] - Ay[:-1, :, :]) / dz)
+            f["bfieldi_y"] = ((Ax[1:, :, :] - Ax[:-1, :, :]) / dz
+                              - (Az[:, :, 1:] - Az[:, :, :-1]) / dx)
+            f["bfieldi_z"] = ((Ay[:, :, 1:] - Ay[:, :, :-1]) / dx
+                              - (Ax[:, 1:, :] - Ax[:, :-1, :]) / dy)
+        else:
+            mz, my, mx = zc.numel(), yc.numel(), xc.numel()
+            for k, shp in (("x", (mz, my, mx + 1)), ("y", (mz, my + 1, mx)),
+                           ("z", (mz + 1, my, mx))):
+                f["bfieldi_" + k] = torch.zeros(shp, dtype=torch.float64, device=device)
+        _center_b(f)
+    x0, _, _ = rot_fwd(*grid(xc, yc, zc))
+    trig = torch.cos(x0 * 2.0 * _CELLO_PI / lam)
+    rho = w["rho_back"] + amplitude * w["rho_ev"] * trig
+    mom = rot_inv(*(w["mom_back"][c] + amplitude * w["mom_ev"][c] * trig
+                    for c in range(3)))
+    f["density"] = rho
+    for c, k in enumerate("xyz"):
+        f["velocity_" + k] = mom[c] / rho
+    f["total_energy"] = (w["etot_back"] + amplitude * w["etot_ev"] * trig) / rho
+    if dual_energy:                                          # setup_eint_ :495-539
+        ke = 0.5 * sum(f["velocity_" + k] ** 2 for k in "xyz")
+        me = 0.5 * sum(f["bfield_" + k] ** 2 for k in "xyz") / rho if mhd else 0.0
+        f["internal_energy"] = f["total_energy"] - ke - me
+    f["pressure"] = torch.zeros_like(rho)
+    return {k: v.contiguous() for k, v in f.items()}
+
+
+def shock_tube(n_local, g, lower, width, setup="rj2a", aligned_ax=0, device="cuda",
+               gamma=5.0 / 3.0, axis_velocity=0.0, mhd=True, dual_energy=False):
+    """EnzoInitialShockTube (src/Enzo/initial/EnzoInitialShockTube.cpp:37-330):
+    "rj2a" (Ryu & Jones 1995 fig. 2a) or "sod", discontinuity at 0.5 along
+    `aligned_ax`, vector components permuted onto the tube's axis."""
+    if setup == "rj2a":
+        L = dict(rho=1.08, p=0.95, v=(1.2, 0.01, 0.5), b=(1.0155412503859613, 0.5641895835477563))
+        Rt = dict(rho=1.0, p=1.0, v=(0.0, 0.0, 0.0), b=(1.1283791670955126, 0.5641895835477563))
+        b0 = 0.5641895835477563
+    elif setup == "sod":
+        L = dict(rho=1.0, p=1.0, v=(0.0, 0.0, 0.0), b=(0.0, 0.0))
+        Rt = dict(rho=0.125, p=0.1, v=(0.0, 0.0, 0.0), b=(0.0, 0.0))
+        b0 = 0.0
+    else:
+        raise ValueError(f"unknown shock tube {setup!r}")
+    coords = _coords(n_local, g, lower, width, device)
+    mz, my, mx = (coords[2][0].numel(), coords[1][0].numel(), coords[0][0].numel())
+    ia, ja, ka = aligned_ax, (aligned_ax + 1) % 3, (aligned_ax + 2) % 3
+    # index of the first cell right of the discontinuity (cpp:196-206)
+    shock = math.ceil((0.5 - lower[ia]) / width[ia] - 0.5 + g[ia])
+
+    def side_mask(extent_along):       # True = left state, for an array whose
+        idx = torch.arange(extent_along, device=device)       # extent along
+        shape = [1, 1, 1]                                       # the tube is given
+        shape[2 - ia] = -1
+        return (idx < shock).view(shape)
+
+    def pick(lv, rv, shape):
+        m = side_mask(shape[2 - ia]).expand(shape)
+        one = torch.ones(shape, dtype=torch.float64, device=device)
+        return torch.where(m, lv * one, rv * one)
+
+    cshape = (mz, my, mx)
+    f = {"density": pick(L["rho"], Rt["rho"], cshape)}
+    names = "xyz"
+    vl = (L["v"][0] + axis_velocity, L["v"][1], L["v"][2])
+    vr = (Rt["v"][0] + axis_velocity, Rt["v"][1], Rt["v"][2])
+    for c, ax in enumerate((ia, ja, ka)):
+        f["velocity_" + names[ax]] = pick(vl[c], vr[c], cshape)
+
+    def energy(s, v):
+        eint = s["p"] / ((gamma - 1.0) * s["rho"])
+        v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2]
+        b2 = b0 * b0 + s["b"][0] * s["b"][0] + s["b"][1] * s["b"][1]
+        return eint, eint + 0.5 * (v2 + b2 / s["rho"])
+    (el, tl), (er, tr) = energy(L, vl), energy(Rt, vr)
+    f["total_energy"] = pick(tl, tr, cshape)
+    if dual_energy:
+        f["internal_energy"] = pick(el, er, cshape)
+    if mhd:
+        fshape = {0: (mz, my, mx + 1), 1: (mz, my + 1, mx), 2: (mz + 1, my, mx)}
+        f["bfieldi_" + names[ia]] = torch.full(fshape[ia], b0, dtype=torch.float64,
+                                               device=device)
+        f["bfieldi_" + names[ja]] = pick(L["b"][0], Rt["b"][0], fshape[ja])
+        f["bfieldi_" + names[ka]] = pick(L["b"][1], Rt["b"][1], fshape[ka])
+        _center_b(f)
+    f["pressure"] = torch.zeros(cshape, dtype=torch.float64, device=device)
+    return {k: v.contiguous() for k, v in f.items()}
