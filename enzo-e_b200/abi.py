@@ -71,6 +71,34 @@ class VlctBlock(C.Structure):
     )
 
 
+INFLOW_FIELDS = ("density", "velocity_x", "velocity_y", "velocity_z",
+                 "total_energy", "internal_energy",
+                 "bfield_x", "bfield_y", "bfield_z",
+                 "bfieldi_x", "bfieldi_y", "bfieldi_z", "pressure")
+
+
+class VlctInflowValues(C.Structure):
+    """vlct_inflow_values: NaN = the field is not in the boundary's list"""
+    _fields_ = ([(name, C.c_double) for name in INFLOW_FIELDS]
+                + [("passive", C.c_double * VLCT_MAX_PASSIVE)])
+
+
+def inflow_values(values, passive=()):
+    """{field name: constant} (+ one entry per passive scalar, None = not
+    listed) -> VlctInflowValues"""
+    nan = float("nan")
+    unknown = set(values) - set(INFLOW_FIELDS)
+    if unknown:
+        raise KeyError(f"not fields of vlct_block: {sorted(unknown)}")
+    v = VlctInflowValues(**{k: float(values.get(k, nan)) for k in INFLOW_FIELDS})
+    for i in range(VLCT_MAX_PASSIVE):
+        v.passive[i] = nan
+    for i, x in enumerate(passive):
+        if x is not None:
+            v.passive[i] = float(x)
+    return v
+
+
 VLCT_FLUX_FIELDS = 6 + VLCT_MAX_PASSIVE
 
 

@@ -1487,6 +1487,46 @@ int vlct_boundary(vlct_handle* h, const vlct_block* b, int axis, int side, int t
   return VLCT_OK;
 }
 
+int vlct_boundary_inflow(vlct_handle* h, const vlct_block* b, int axis, int side,
+                         const vlct_inflow_values* v)
+{
+  if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_boundary_inflow needs a DEVICE block");
+  if (axis < 0 || axis > 2 || (side != 0 && side != 1) || v == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "bad arguments to vlct_boundary_inflow");
+  const Geom G = geom_of(b);
+  cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  struct Item { double* p; double value; int face; };
+  const Item items[] = {
+    { b->density, v->density, -1 },
+    { b->velocity_x, v->velocity_x, -1 }, { b->velocity_y, v->velocity_y, -1 },
+    { b->velocity_z, v->velocity_z, -1 },
+    { b->total_energy, v->total_energy, -1 },
+    { b->internal_energy, v->internal_energy, -1 },
+    { b->bfield_x, v->bfield_x, -1 }, { b->bfield_y, v->bfield_y, -1 },
+    { b->bfield_z, v->bfield_z, -1 },
+    { b->bfieldi_x, v->bfieldi_x, 0 }, { b->bfieldi_y, v->bfieldi_y, 1 },
+    { b->bfieldi_z, v->bfieldi_z, 2 },
+    { b->pressure, v->pressure, -1 } };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  for (const Item& it : items) {
+    if (it.p == nullptr || it.value != it.value) continue;
+    launch_boundary_axis(ctx, it.p, G.mz + (it.face == 2), G.my + (it.face == 1),
+                         G.mx + (it.face == 0), axis, n[axis], g[axis],
+                         it.face == axis ? 1 : 0, side, VLCT_BOUNDARY_INFLOW, it.value);
+  }
+  for (int s = 0; s < h->P.nsc; s++) {
+    const double value = v->passive[s];
+    if (b->passive[s] == nullptr || value != value) continue;
+    launch_boundary_axis(ctx, b->passive[s], G.mz, G.my, G.mx, axis, n[axis], g[axis],
+                         0, side, VLCT_BOUNDARY_INFLOW, value);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return VLCT_OK;
+}
+
 long long vlct_halo_bytes(const vlct_handle* h, const vlct_block* b, int axis)
 {
   if (h == nullptr || b == nullptr || axis < 0 || axis > 2) return -1;

@@ -38,30 +38,41 @@ enum { W_RHO = 0, W_VI = 1, W_VJ = 2, W_VK = 3, W_P = 4, W_BJ = 5, W_BK = 6 };
 
 template <bool MHD> struct NVars { static constexpr int n = MHD ? 7 : 5; };
 
-/// Primitives of cell c in the frame of sweep DIM, pressure computed on the fly
-/// (EnzoComputePressure.cpp:82-198; same operand order as the reference).
+/// Primitives of a cell in the frame of sweep DIM from its field values, the
+/// pressure computed on the fly (EnzoComputePressure.cpp:82-198; same operand
+/// order as the reference). e = internal_energy with DE, else total_energy.
 template <int DIM, bool MHD, bool DE>
-__device__ __forceinline__ void load_cell(const Params& P, const State& u,
-                                          size_t c, double (&w)[NVars<MHD>::n])
+__device__ __forceinline__ void
+cell_primitives(const Params& P, double rho, const double (&v)[3],
+                const double (&b)[3], double e, double (&w)[NVars<MHD>::n])
 {
   constexpr int JD = (DIM + 1) % 3, KD = (DIM + 2) % 3;
-  double v[3], b[3] = { 0., 0., 0. };
-  const double rho = __ldg(u.rho + c);
-  v[0] = __ldg(u.vx + c); v[1] = __ldg(u.vy + c); v[2] = __ldg(u.vz + c);
-  if (MHD) { b[0] = __ldg(u.bx + c); b[1] = __ldg(u.by + c); b[2] = __ldg(u.bz + c); }
   const double gm1 = P.gamma - 1.0;
   double p;
   if (DE) {
-    p = gm1 * rho * __ldg(u.eint + c);
+    p = gm1 * rho * e;
   } else {
     const double ke = 0.5 * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     double me_den = 0.;
     if (MHD) me_den = 0.5 * (b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
-    p = gm1 * (rho * (__ldg(u.etot + c) - ke) - me_den);
+    p = gm1 * (rho * (e - ke) - me_den);
   }
   w[W_RHO] = rho; w[W_VI] = v[DIM]; w[W_VJ] = v[JD]; w[W_VK] = v[KD];
   w[W_P] = p;
   if (MHD) { w[W_BJ] = b[JD]; w[W_BK] = b[KD]; }
+}
+
+/// Primitives of cell c in the frame of sweep DIM
+template <int DIM, bool MHD, bool DE>
+__device__ __forceinline__ void load_cell(const Params& P, const State& u,
+                                          size_t c, double (&w)[NVars<MHD>::n])
+{
+  double v[3], b[3] = { 0., 0., 0. };
+  const double rho = __ldg(u.rho + c);
+  v[0] = __ldg(u.vx + c); v[1] = __ldg(u.vy + c); v[2] = __ldg(u.vz + c);
+  if (MHD) { b[0] = __ldg(u.bx + c); b[1] = __ldg(u.by + c); b[2] = __ldg(u.bz + c); }
+  const double e = DE ? __ldg(u.eint + c) : __ldg(u.etot + c);
+  cell_primitives<DIM, MHD, DE>(P, rho, v, b, e, w);
 }
 
 __device__ __forceinline__ void prefetch_l1(const double* p)
@@ -293,6 +304,61 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
 // ---------------------------------------------------------------------------
 constexpr int kMarchThreads = 128;
 
+// The cells a column needs next are fetched kRingAhead faces ahead with
+// cp.async into a ring of thread-private shared-memory slots: no registers are
+// held across the Riemann solve for them, and the loads that feed the slopes
+// hit shared memory instead of waiting for L2 / HBM (the marching kernels spent
+// a quarter of their stall cycles on that scoreboard).
+#ifndef VLCT_MARCH_RING
+#define VLCT_MARCH_RING 1
+#endif
+constexpr int kRingAhead = 3, kRingDepth = 4;    // depth: a power of two > ahead
+template <bool MHD> struct RingVars { static constexpr int n = MHD ? 9 : 5; };
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* src)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{ asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait()
+{ asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+/// start the copy of cell c (and of the longitudinal face field at fb) into
+/// one ring slot; slot points at this thread's first entry
+template <bool MHD, bool DE>
+__device__ __forceinline__ void ring_issue(double* slot, const State& u, size_t c,
+                                           const double* bi, size_t fb)
+{
+  constexpr int T = kMarchThreads;
+  cp_async8(slot, u.rho + c);
+  cp_async8(slot + T, u.vx + c);
+  cp_async8(slot + 2 * T, u.vy + c);
+  cp_async8(slot + 3 * T, u.vz + c);
+  cp_async8(slot + 4 * T, (DE ? u.eint : u.etot) + c);
+  if (MHD) {
+    cp_async8(slot + 5 * T, u.bx + c);
+    cp_async8(slot + 6 * T, u.by + c);
+    cp_async8(slot + 7 * T, u.bz + c);
+    cp_async8(slot + 8 * T, bi + fb);
+  }
+}
+
+/// primitives of the cell held by a ring slot (+ the face field that came along)
+template <int DIM, bool MHD, bool DE>
+__device__ __forceinline__ void ring_cell(const Params& P, const double* slot,
+                                          double (&w)[NVars<MHD>::n], double& blong)
+{
+  constexpr int T = kMarchThreads;
+  double v[3], b[3] = { 0., 0., 0. };
+  const double rho = slot[0];
+  v[0] = slot[T]; v[1] = slot[2 * T]; v[2] = slot[3 * T];
+  const double e = slot[4 * T];
+  if (MHD) { b[0] = slot[5 * T]; b[1] = slot[6 * T]; b[2] = slot[7 * T]; blong = slot[8 * T]; }
+  cell_primitives<DIM, MHD, DE>(P, rho, v, b, e, w);
+}
+
 template <int DIM, int RECON, int SOLVER, bool DE>
 __global__ void __launch_bounds__(kMarchThreads,
                                   (RECON != RECON_NN && SOLVER == SOLVER_HLLD)
@@ -357,16 +423,42 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   }
 
   const int mdim = (DIM == 1) ? G.my : (int) G.levels();
+  constexpr int kFirst = PLM ? 2 : 1;       // the cell an iteration adds: c + kFirst sd
+#if VLCT_MARCH_RING
+  constexpr int kSlot = RingVars<MHD>::n * kMarchThreads;      // doubles per slot
+  __shared__ double ring[kRingDepth * kSlot];
+  double* const ring0 = ring + threadIdx.x;
+#pragma unroll
+  for (int a = 0; a < kRingAhead; a++) {
+    if (f0 + kFirst + a < mdim)
+      ring_issue<MHD, DE>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi, fb + a * sd);
+    cp_async_commit();
+  }
+  int slot = 0;
+#else
   constexpr int kAhead = 2;                 // prefetch distance, in faces
+#endif
 #pragma unroll 1
   for (int f = f0; f < f1; f++, c += sd, fb += sd) {
     double Wn[NV], wr[NV], wl_next[NV];
-    if (f + (PLM ? 2 : 1) + kAhead < mdim) {
-      prefetch_cell<MHD, DE>(u, c + ((PLM ? 2 : 1) + kAhead) * sd);
+    double blong = 0.;
+#if VLCT_MARCH_RING
+    if (f + kFirst + kRingAhead < mdim)
+      ring_issue<MHD, DE>(ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
+                          c + (kFirst + kRingAhead) * sd, bi, fb + kRingAhead * sd);
+    cp_async_commit();
+    cp_async_wait<kRingAhead>();            // the group of this face has landed
+    ring_cell<DIM, MHD, DE>(P, ring0 + slot * kSlot, Wn, blong);
+    slot = (slot + 1) & (kRingDepth - 1);
+#else
+    if (f + kFirst + kAhead < mdim) {
+      prefetch_cell<MHD, DE>(u, c + (kFirst + kAhead) * sd);
       if (MHD) prefetch_l1(bi + fb + kAhead * sd);
     }
+    load_cell<DIM, MHD, DE>(P, u, c + kFirst * sd, Wn);
+    if (MHD) blong = __ldg(bi + fb);
+#endif
     if (PLM) {
-      load_cell<DIM, MHD, DE>(P, u, c + 2 * sd, Wn);
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         const double h = limited_slope<RECON>(Wm[v], Wc[v], Wn[v], P.theta) * 0.5;
@@ -376,12 +468,9 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
       apply_floors<MHD>(P, wr);
       apply_floors<MHD>(P, wl_next);
     } else {
-      load_cell<DIM, MHD, DE>(P, u, c + sd, Wn);
 #pragma unroll
       for (int v = 0; v < NV; v++) { wl[v] = Wc[v]; wr[v] = Wn[v]; }
     }
-    double blong = 0.;
-    if (MHD) blong = __ldg(bi + fb);
     solve_and_store<DIM, RECON, SOLVER, DE>(P, wl, wr, blong, F, spec, c, sd);
 #pragma unroll
     for (int v = 0; v < NV; v++) {
@@ -426,6 +515,15 @@ void flux_go(const FluxLaunch& L)
     const unsigned gx = (unsigned) ((cols + kMarchThreads - 1) / kMarchThreads);
     const unsigned gy = (unsigned) ((nf + chunk - 1) / chunk) *
                         (D == 2 ? (unsigned) L.G.nrep : 1u);
+#if VLCT_MARCH_RING
+    // 4 resident blocks need 4 x (36 KB ring + 1 KB) of the SM's shared memory
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      cudaFuncSetAttribute(k_flux_march<D, RECON, SOLVER, DE>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+      carveout_set = true;
+    }
+#endif
     k_flux_march<D, RECON, SOLVER, DE><<<dim3(gx, gy), kMarchThreads, 0, L.st>>>(
         L.P, L.G, L.cur, L.spec, L.bi, L.F, b, chunk);
   }

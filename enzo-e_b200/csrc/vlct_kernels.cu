@@ -480,6 +480,13 @@ k_boundary_axis(double* p, int n0, int n1, int n2, int axis, int n, int g,
     idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
     const int ig = idx[axis];
     int src, dst;
+    if (type == VLCT_BOUNDARY_INFLOW) {
+      // BoundaryValue::enforce (Cello/problem_BoundaryValue.cpp:190-202): the g
+      // outermost layers take the value (passed in `sign`)
+      idx[axis] = (side == 0) ? ig : n + g + cen + ig;
+      p[((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0]] = sign;
+      continue;
+    }
     if (type == VLCT_BOUNDARY_OUTFLOW) {
       if (side == 0) { src = g;               dst = g - ig - 1; }
       else           { src = n + g - 1 + cen; dst = src + ig + 1; }

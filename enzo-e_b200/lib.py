@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = (
     "vlct_synchronize",
     "vlct_profile_enable", "vlct_profile_reset", "vlct_profile_count",
     "vlct_profile_get", "vlct_selftest_fpops",
-    "vlct_refresh_periodic", "vlct_boundary", "vlct_halo_bytes", "vlct_halo_pack",
+    "vlct_refresh_periodic", "vlct_boundary", "vlct_boundary_inflow",
+    "vlct_halo_bytes", "vlct_halo_pack",
     "vlct_halo_unpack",
 )
 
@@ -89,6 +90,8 @@ def load():
                                           C.POINTER(C.c_longlong)]),
         "vlct_refresh_periodic": (C.c_int, [C.c_void_p, blkp, C.c_int]),
         "vlct_boundary": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, C.c_int]),
+        "vlct_boundary_inflow": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int,
+                                           C.POINTER(abi.VlctInflowValues)]),
         "vlct_halo_bytes": (C.c_longlong, [C.c_void_p, blkp, C.c_int]),
         "vlct_halo_pack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),
         "vlct_halo_unpack": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_int, dp]),

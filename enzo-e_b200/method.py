@@ -265,6 +265,15 @@ class EnzoMethodMHDVlct:
         self._check(self._lib.vlct_boundary(
             self._h, C.byref(block.c_block), axis, side, abi.BOUNDARY[kind]))
 
+    def boundary_inflow(self, block, axis, side, values, passive=()):
+        """BoundaryValue::enforce ("inflow") with constant values on one face of
+        the domain: values = {field name: constant} is the boundary's field
+        list (Cello/problem_BoundaryValue.cpp:131-273); passive = one constant
+        (or None) per "color" field."""
+        v = abi.inflow_values(values, passive)
+        self._check(self._lib.vlct_boundary_inflow(
+            self._h, C.byref(block.c_block), axis, side, C.byref(v)))
+
     def halo_bytes(self, block, axis):
         return self._lib.vlct_halo_bytes(self._h, C.byref(block.c_block), axis)
 

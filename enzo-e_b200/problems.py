@@ -339,3 +339,95 @@ def shock_tube(n_local, g, lower, width, setup="rj2a", aligned_ax=0, device="cud
         _center_b(f)
     f["pressure"] = torch.zeros(cshape, dtype=torch.float64, device=device)
     return {k: v.contiguous() for k, v in f.items()}
+
+
+def cloud(n_local, g, lower, width, subsample_n, cloud_radius, center,
+          cloud_density, wind_density, wind_velocity, wind_total_energy,
+          wind_internal_energy=0.0, device="cuda", mhd=False, dual_energy=True,
+          bfield=(0.0, 0.0, 0.0)):
+    """EnzoInitialCloud (src/Enzo/initial/EnzoInitialCloud.cpp:606-748) without
+    a density perturbation (perturb_Nwaves = 0, the default): a sphere of
+    cloud_density at rest in a wind along +x, in pressure equilibrium. Cells cut
+    by the sphere's surface get the volume-weighted density of their 2^n per
+    axis sub-cells and a mass-weighted velocity (cpp:320-386). `bfield`: the
+    uniform field the reference expects to find pre-initialised (cpp:452-523)."""
+    f64 = dict(dtype=torch.float64, device=device)
+    m = [n_local[a] + 2 * g[a] for a in range(3)]
+    sqr_radius = cloud_radius * cloud_radius
+    nsub = 2 ** subsample_n
+    # prep_subcell_offsets_ (cpp:246-256)
+    offs = []
+    for a in range(3):
+        cur, o = 1.0 / 2 ** (subsample_n + 1), []
+        o.append(cur * width[a])
+        for _ in range(1, nsub):
+            cur += 1.0 / 2 ** subsample_n
+            o.append(cur * width[a])
+        offs.append(o)
+
+    def along(a, v):                       # 1-D array along axis a -> (z, y, x)
+        shape = [1, 1, 1]
+        shape[2 - a] = -1
+        return v.view(shape)
+
+    near2, far2, sub2 = [], [], []
+    for a in range(3):
+        # Data::field_cell_faces (Cello/data_Data.cpp:91-121): xm + ix * hx
+        idx = torch.arange(m[a] + 1, **f64) - g[a]
+        face = lower[a] + idx * width[a]
+        left, right, c = face[:-1], face[1:], center[a]
+        # SphereRegion::check_intersect (cpp:204-237)
+        inside_far = torch.where((c - left) > (right - c), left, right)
+        nearest = torch.where(c <= left, left,
+                              torch.where(c >= right, right, torch.full_like(left, c)))
+        furthest = torch.where(c <= left, right,
+                               torch.where(c >= right, left, inside_far))
+        dn, df = nearest - c, furthest - c
+        near2.append(along(a, dn * dn))
+        far2.append(along(a, df * df))
+        sub = []
+        for o in offs[a]:
+            ds = (left + o) - c
+            sub.append(along(a, ds * ds))
+        sub2.append(sub)
+    enclosed = ((far2[0] + far2[1]) + far2[2]) <= sqr_radius
+    overlap = ((near2[0] + near2[1]) + near2[2]) <= sqr_radius
+    count = torch.zeros((m[2], m[1], m[0]), dtype=torch.int32, device=device)
+    for sz in sub2[2]:
+        for sy in sub2[1]:
+            for sx in sub2[0]:
+                count += (((sx + sy) + sz) <= sqr_radius).to(torch.int32)
+    frac = count.to(torch.float64) / float(nsub ** 3)
+    frac = torch.where(enclosed, torch.ones_like(frac),
+                       torch.where(overlap, frac, torch.zeros_like(frac)))
+
+    avg_density = frac * cloud_density * 1.0 + (1.0 - frac) * wind_density
+    ratio = torch.full_like(avg_density, wind_density) / avg_density   # true division
+    wind_mass_weight = (1.0 - frac) * ratio
+    f = {"density": avg_density,
+         "velocity_x": wind_mass_weight * wind_velocity,
+         "velocity_y": torch.zeros_like(frac), "velocity_z": torch.zeros_like(frac)}
+    magnetic_edens = 0.0
+    if mhd:
+        magnetic_edens = 0.5 * (bfield[0] * bfield[0] + bfield[1] * bfield[1]
+                                + bfield[2] * bfield[2])
+    if dual_energy:
+        f["internal_energy"] = wind_internal_energy * ratio
+        eint_density = wind_internal_energy * wind_density
+    else:
+        eint_density = ((wind_total_energy - 0.5 * wind_velocity * wind_velocity)
+                        * wind_density - magnetic_edens)
+    vx = f["velocity_x"]
+    etot = (torch.full_like(frac, eint_density + magnetic_edens) / avg_density
+            + 0.5 * vx * vx)
+    f["total_energy"] = torch.where(frac == 0, torch.full_like(frac, wind_total_energy),
+                                    etot)
+    if mhd:
+        names = "xyz"
+        for a in range(3):
+            f["bfield_" + names[a]] = torch.full_like(frac, bfield[a])
+            shape = [m[2], m[1], m[0]]
+            shape[2 - a] += 1
+            f["bfieldi_" + names[a]] = torch.full(shape, bfield[a], **f64)
+    f["pressure"] = torch.zeros_like(frac)
+    return {k: v.contiguous() for k, v in f.items()}

@@ -359,10 +359,32 @@ int vlct_refresh_periodic(vlct_handle *h, const vlct_block *block, int axes);
  *   reflecting  ghost layers mirror the active zone; the vector component
  *               along `axis` (velocity_, bfield_, bfieldi_) changes sign
  * The layers span the full ghost-including extent of the other two axes.
- * Masks and "inflow" (Value-initialised, problem-specific) are not covered. */
-enum { VLCT_BOUNDARY_OUTFLOW = 0, VLCT_BOUNDARY_REFLECTING = 1 };
+ * Masks are not covered. */
+enum { VLCT_BOUNDARY_OUTFLOW = 0, VLCT_BOUNDARY_REFLECTING = 1,
+       VLCT_BOUNDARY_INFLOW = 2 /* vlct_boundary_inflow only */ };
 int vlct_boundary(vlct_handle *h, const vlct_block *block, int axis, int side,
                   int type);
+
+/* "inflow" boundary, BoundaryValue::enforce
+ * (src/Cello/problem_BoundaryValue.cpp:131-273), for value-expressions that
+ * are constants (as in input/vlct/dual_energy_cloud/initial_cloud_HD.in:77-95):
+ * the g ghost layers of one face of the domain are set to a value, for the
+ * fields in the boundary's field list only. For a field that is face-centred
+ * along `axis` these are its g outermost layers; the boundary face itself is
+ * not touched (ix0 = 0 resp. ndx - gx with ndx = nx + 2 gx + 1, cpp:190-202).
+ * A field is in the list when its pointer in `block` is non-NULL and its entry
+ * in `values` is not a NaN. */
+typedef struct vlct_inflow_values {
+  double density;
+  double velocity_x, velocity_y, velocity_z;
+  double total_energy, internal_energy;
+  double bfield_x, bfield_y, bfield_z;
+  double bfieldi_x, bfieldi_y, bfieldi_z;
+  double pressure;
+  double passive[VLCT_MAX_PASSIVE];
+} vlct_inflow_values;
+int vlct_boundary_inflow(vlct_handle *h, const vlct_block *block, int axis,
+                         int side, const vlct_inflow_values *values);
 
 /* Pack / unpack the ghost-exchange slab of all fields along one axis
  * (axis 0,1,2 = x,y,z; side 0 = lower, 1 = upper) into / from a contiguous

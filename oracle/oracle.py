@@ -206,6 +206,12 @@ def _ic_lib():
         lib.vlct_oracle_boundary.restype = C.c_int
         lib.vlct_oracle_boundary.argtypes = [
             C.POINTER(abi.VlctBlock), C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.vlct_oracle_boundary_inflow.restype = C.c_int
+        lib.vlct_oracle_boundary_inflow.argtypes = [
+            C.POINTER(abi.VlctBlock), C.c_int, C.c_int, C.c_int,
+            C.POINTER(abi.VlctInflowValues)]
+        lib.vlct_ic_cloud.restype = C.c_int
+        lib.vlct_ic_cloud.argtypes = [C.POINTER(abi.VlctBlock), dp, C.c_int, dp]
         lib._ic_ready = True
     return lib
 
@@ -251,3 +257,26 @@ def boundary(blk, axis, side, kind, n_passive=0):
                                         BOUNDARY_TYPES[kind])
     if rc != 0:
         raise RuntimeError(f"vlct_oracle_boundary failed ({rc})")
+
+
+def boundary_inflow(blk, axis, side, values, passive=(), n_passive=0):
+    """BoundaryValue::enforce with constant values (host memory): values =
+    {field name: constant} is the boundary's field list."""
+    v = abi.inflow_values(values, passive)
+    rc = _ic_lib().vlct_oracle_boundary_inflow(C.byref(blk), n_passive, axis,
+                                               side, C.byref(v))
+    if rc != 0:
+        raise RuntimeError(f"vlct_oracle_boundary_inflow failed ({rc})")
+
+
+def ic_cloud(blk, lower, subsample_n, cloud_radius, center, cloud_density,
+             wind_density, wind_velocity, wind_total_energy,
+             wind_internal_energy):
+    """EnzoInitialCloud (no perturbation) on a host block, ghost zones too;
+    magnetic fields (if any) must already be initialised."""
+    lo = (C.c_double * 3)(*lower)
+    p = (C.c_double * 9)(cloud_radius, *center, cloud_density, wind_density,
+                         wind_velocity, wind_total_energy, wind_internal_energy)
+    rc = _ic_lib().vlct_ic_cloud(C.byref(blk), lo, subsample_n, p)
+    if rc != 0:
+        raise RuntimeError(f"vlct_ic_cloud failed ({rc})")

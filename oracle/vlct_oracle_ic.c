@@ -7,6 +7,7 @@
  *
  *   vlct_ic_inclined_wave   initial/EnzoInitialInclinedWave.cpp
  *   vlct_ic_shock_tube      initial/EnzoInitialShockTube.cpp
+ *   vlct_ic_cloud           initial/EnzoInitialCloud.cpp (unperturbed cloud)
  *   (face-B from a vector potential, centred B)  initial/EnzoInitialBCenter.cpp
  *
  * plus the periodic ghost-zone refresh of a single block
@@ -605,5 +606,200 @@ int vlct_oracle_boundary(const vlct_block *b, int n_passive, int axis, int side,
       boundary_axis(face[f], mz + (f == 2), my + (f == 1), mx + (f == 0), axis,
                     n[axis], g[axis], f == axis, side, type,
                     f == axis ? -1.0 : 1.0);
+  return 0;
+}
+
+/* BoundaryValue::enforce (Cello/problem_BoundaryValue.cpp:131-273) for constant
+ * value-expressions: the g outermost layers of one side take the value; the
+ * other axes run over their full extent. next = extent along `axis`. */
+static void inflow_axis(double *p, int n0, int n1, int n2, int axis, int g,
+                        int side, double value)
+{
+  const int ext[3] = { n2, n1, n0 };
+  int lo[3] = { 0, 0, 0 }, hi[3] = { n2, n1, n0 };
+  if (side == 0) hi[axis] = g; else lo[axis] = ext[axis] - g;
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++)
+        p[((size_t) k * n1 + j) * n2 + i] = value;
+}
+
+/* One "inflow" Boundary object applied to one face of the domain: the fields
+ * with a non-NULL pointer in b and a non-NaN entry in v form its field list. */
+int vlct_oracle_boundary_inflow(const vlct_block *b, int n_passive, int axis,
+                                int side, const vlct_inflow_values *v)
+{
+  const int mx = b->nx + 2 * b->gx, my = b->ny + 2 * b->gy, mz = b->nz + 2 * b->gz;
+  const int g[3] = { b->gx, b->gy, b->gz };
+  if (axis < 0 || axis > 2 || (side != 0 && side != 1) || v == NULL) return 1;
+  struct { double *p; double value; int face; } item[] = {
+    { b->density, v->density, -1 },
+    { b->velocity_x, v->velocity_x, -1 }, { b->velocity_y, v->velocity_y, -1 },
+    { b->velocity_z, v->velocity_z, -1 },
+    { b->total_energy, v->total_energy, -1 },
+    { b->internal_energy, v->internal_energy, -1 },
+    { b->bfield_x, v->bfield_x, -1 }, { b->bfield_y, v->bfield_y, -1 },
+    { b->bfield_z, v->bfield_z, -1 },
+    { b->bfieldi_x, v->bfieldi_x, 0 }, { b->bfieldi_y, v->bfieldi_y, 1 },
+    { b->bfieldi_z, v->bfieldi_z, 2 },
+    { b->pressure, v->pressure, -1 } };
+  for (size_t c = 0; c < sizeof(item) / sizeof(item[0]); c++) {
+    if (item[c].p == NULL || isnan(item[c].value)) continue;
+    const int f = item[c].face;
+    inflow_axis(item[c].p, mz + (f == 2), my + (f == 1), mx + (f == 0), axis,
+                g[axis], side, item[c].value);
+  }
+  for (int s = 0; s < n_passive; s++)
+    if (b->passive[s] && !isnan(v->passive[s]))
+      inflow_axis(b->passive[s], mz, my, mx, axis, g[axis], side, v->passive[s]);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* spherical cloud in a wind                                                 */
+/* ------------------------------------------------------------------------ */
+
+/* SphereRegion::check_point (initial/EnzoInitialCloud.cpp:194-200) */
+static int cloud_check_point(const double *center, double sqr_radius, double x,
+                             double y, double z)
+{
+  double dx = x - center[0];
+  double dy = y - center[1];
+  double dz = z - center[2];
+  return (dx * dx + dy * dy + dz * dz) <= sqr_radius;
+}
+
+/* CloudInitHelper::query_cell without a perturbation (cpp:320-386):
+ * fraction of the cell [left, right] enclosed by the sphere */
+static double cloud_frac_enclosed(const double *center, double sqr_radius,
+                                  const double *left, const double *right,
+                                  int nsub, double num_subsampled_cells,
+                                  const double *off[3])
+{
+  /* SphereRegion::check_intersect (cpp:204-237) */
+  double nearest[3], furthest[3];
+  for (int i = 0; i < 3; i++) {
+    if (center[i] <= left[i]) {
+      nearest[i] = left[i]; furthest[i] = right[i];
+    } else if (center[i] >= right[i]) {
+      nearest[i] = right[i]; furthest[i] = left[i];
+    } else {
+      nearest[i] = center[i];
+      if ((center[i] - left[i]) > (right[i] - center[i])) furthest[i] = left[i];
+      else furthest[i] = right[i];
+    }
+  }
+  if (cloud_check_point(center, sqr_radius, furthest[0], furthest[1], furthest[2]))
+    return 1.0;                                   /* enclosed_cell */
+  if (!cloud_check_point(center, sqr_radius, nearest[0], nearest[1], nearest[2]))
+    return 0.0;                                   /* no_overlap */
+  int n_enclosed = 0;                             /* partial_overlap */
+  for (int sz = 0; sz < nsub; sz++) {
+    double sub_zc = left[2] + off[2][sz];
+    for (int sy = 0; sy < nsub; sy++) {
+      double sub_yc = left[1] + off[1][sy];
+      for (int sx = 0; sx < nsub; sx++) {
+        double sub_xc = left[0] + off[0][sx];
+        if (cloud_check_point(center, sqr_radius, sub_xc, sub_yc, sub_zc))
+          n_enclosed++;
+      }
+    }
+  }
+  return (double) n_enclosed / num_subsampled_cells;   /* cpp:377 */
+}
+
+/* EnzoInitialCloud::enforce_block (initial/EnzoInitialCloud.cpp:606-748) with
+ * perturb_Nwaves = 0 (the default; the perturbation is then exactly 0), no
+ * "color" fields (the input/vlct/dual_energy_cloud files define no Group:color, so
+ * cloud_dye / metal_density are not touched), magnetic fields pre-initialised
+ * by the caller and uniform (MHDHandler, cpp:452-523).
+ * p[] = { cloud_radius, center_x, center_y, center_z, cloud_density,
+ *         wind_density, wind_velocity, wind_total_energy, wind_internal_energy }
+ * lower: domain coordinate of the block's first active cell. */
+int vlct_ic_cloud(const vlct_block *b, const double *lower, int subsample_n,
+                  const double *p)
+{
+  const int mx = b->nx + 2 * b->gx, my = b->ny + 2 * b->gy, mz = b->nz + 2 * b->gz;
+  const int m[3] = { mx, my, mz }, g[3] = { b->gx, b->gy, b->gz };
+  const double h[3] = { b->dx, b->dy, b->dz };
+  const double center[3] = { p[1], p[2], p[3] };
+  const double sqr_radius = p[0] * p[0];
+  const double density_cloud = p[4], density_wind = p[5], velocity_wind = p[6],
+               etot_wind = p[7], eint_wind = p[8];
+  if (subsample_n < 0 || p[0] <= 0.) return 1;
+
+  /* Data::field_cell_faces with cx = cy = cz = 1 (Cello/data_Data.cpp:91-121) */
+  double *xf[3];
+  for (int a = 0; a < 3; a++) {
+    xf[a] = (double *) malloc(sizeof(double) * (size_t) (m[a] + 1));
+    for (int i = -g[a]; i < m[a] - g[a] + 1; i++)
+      xf[a][i + g[a]] = lower[a] + (i + 0.) * h[a];
+  }
+  /* prep_subcell_offsets_ (cpp:246-256) */
+  const int nsub = (int) pow(2, subsample_n);
+  double *off[3];
+  for (int a = 0; a < 3; a++) {
+    off[a] = (double *) malloc(sizeof(double) * (size_t) nsub);
+    double cur_frac = 1. / pow(2, subsample_n + 1);
+    off[a][0] = cur_frac * h[a];
+    for (int i = 1; i < nsub; i++) {
+      cur_frac += 1. / pow(2, subsample_n);
+      off[a][i] = cur_frac * h[a];
+    }
+  }
+  const double *coff[3] = { off[0], off[1], off[2] };
+  const double num_subsampled_cells = pow(pow(2, subsample_n), 3);   /* cpp:269 */
+
+  /* MHDHandler: B is assumed uniform over the active zone (cpp:498-511) */
+  const int mhd = (b->bfield_x != NULL);
+  double magnetic_edens_wind = 0.;
+  if (mhd) {
+    const size_t c = ((size_t) b->gz * my + b->gy) * mx + b->gx;
+    magnetic_edens_wind = 0.5 * (b->bfield_x[c] * b->bfield_x[c] +
+                                 b->bfield_y[c] * b->bfield_y[c] +
+                                 b->bfield_z[c] * b->bfield_z[c]);
+  }
+  const int dual_energy = (b->internal_energy != NULL);
+  double eint_density;
+  if (dual_energy) {
+    eint_density = eint_wind * density_wind;
+  } else {
+    eint_density = ((etot_wind - 0.5 * velocity_wind * velocity_wind)
+                    * density_wind - magnetic_edens_wind);
+  }
+  if (!(eint_density > 0)) return 2;
+
+  for (int iz = 0; iz < mz; iz++)
+    for (int iy = 0; iy < my; iy++)
+      for (int ix = 0; ix < mx; ix++) {
+        const size_t c = ((size_t) iz * my + iy) * mx + ix;
+        b->velocity_y[c] = 0.;
+        b->velocity_z[c] = 0.;
+        const double left[3] = { xf[0][ix], xf[1][iy], xf[2][iz] };
+        const double right[3] = { xf[0][ix + 1], xf[1][iy + 1], xf[2][iz + 1] };
+        double frac_enclosed = cloud_frac_enclosed(center, sqr_radius, left, right,
+                                                   nsub, num_subsampled_cells, coff);
+        double perturbation = 0.;
+        perturbation += 1.;
+        double avg_density = (frac_enclosed * density_cloud * perturbation +
+                              (1. - frac_enclosed) * density_wind);
+        b->density[c] = avg_density;
+        double wind_to_average_ratio = density_wind / avg_density;
+        double wind_mass_weight = (1. - frac_enclosed) * wind_to_average_ratio;
+        b->velocity_x[c] = (wind_mass_weight * velocity_wind);
+        if (dual_energy) b->internal_energy[c] = eint_wind * wind_to_average_ratio;
+        if (frac_enclosed == 0) {
+          b->total_energy[c] = etot_wind;
+        } else {
+          double magnetic_edens = 0.;
+          if (mhd)
+            magnetic_edens = 0.5 * (b->bfield_x[c] * b->bfield_x[c] +
+                                    b->bfield_y[c] * b->bfield_y[c] +
+                                    b->bfield_z[c] * b->bfield_z[c]);
+          b->total_energy[c] = ((eint_density + magnetic_edens) / avg_density +
+                                0.5 * b->velocity_x[c] * b->velocity_x[c]);
+        }
+      }
+  for (int a = 0; a < 3; a++) { free(xf[a]); free(off[a]); }
   return 0;
 }

@@ -371,3 +371,99 @@ def passive_l1_norm(s0, s1):
     resid = [np.sum(np.abs(s0[k] - s1[k])) / float(s0[k].size)
              for k in PASSIVE_FIELDS]
     return float(np.sqrt(np.sum(np.square(np.array(resid)))))
+
+
+# ---------------------------------------------------------------------------
+# cloud in a wind with dual energy: symmetry test
+# (input/vlct/dual_energy_cloud/*.in, run_dual_energy_cloud_test.py)
+# ---------------------------------------------------------------------------
+# max tolerated asymmetry, run_dual_energy_cloud_test.py:80-85
+CLOUD_MAX_ASYM = {"hlld": 7.3e-13, "hllc": 4.6e-13, "hlle": 3.2e-13}
+# initial_cloud_HD.in:26-63
+CLOUD = dict(subsample_n=2, cloud_radius=1.0, center=(0.0, 0.0, 0.0),
+             cloud_density=1.610075932356949e+01,
+             wind_density=8.944866290871940e-02,
+             wind_velocity=1.341500614584355e+01,
+             wind_total_energy=1.619661509037183e+02,
+             wind_internal_energy=7.198495595720811e+01)
+# Boundary:hydro_upwind:value (initial_cloud_HD.in:83-94); metal_density and
+# cloud_dye are not in a "color" group there, i.e. not fields of the method
+CLOUD_INFLOW = {"density": 8.944866290871940e-02,
+                "velocity_x": 1.341500614584355e+01,
+                "velocity_y": 0.0, "velocity_z": 0.0,
+                "total_energy": 1.619661509037183e+02,
+                "internal_energy": 7.198495595720811e+01}
+CLOUD_INFLOW_B = {k: 0.0 for k in ("bfield_x", "bfieldi_x", "bfield_y",
+                                   "bfieldi_y", "bfield_z", "bfieldi_z")}
+CLOUD_LOWER, CLOUD_T_STOP = (-2.0, -2.0, -2.0), 0.0625
+
+
+def cloud_config(solver):
+    """{hlld,hlle}_cloud.in: vlct_de.incl (CT with B = 0); hllc_cloud.in:
+    vl_de.incl (no_bfield); theta_limiter 1.5, floors from initial_cloud_HD.in"""
+    return make_config(riemann=solver, recon="plm", theta=1.5,
+                       mhd=(solver != "hllc"), courant=0.4,
+                       gamma=1.6666666666666667, dual_energy=True, eta=0.001,
+                       dfloor=1.e-15, pfloor=1.0e-30)
+
+
+def cloud_setup(solver):
+    """32^3 cells on [-2,2]^3 (8 per cloud radius), one block."""
+    cfg = cloud_config(solver)
+    n, g, d = (32, 32, 32), (3, 3, 3), (0.125,) * 3
+    f = alloc_fields(cfg, n, g)
+    blk = oracle.numpy_block(f, n, g, d)
+    oracle.ic_cloud(blk, CLOUD_LOWER, **CLOUD)
+    return cfg, f, blk, n, g, d, CLOUD_T_STOP
+
+
+def cloud_refresh(mhd, boundary, boundary_inflow):
+    """Block::update_boundary_ over Boundary:list = [downwind, hydro_upwind,
+    yedge, zedge (, bfield_upwind)] (initial_cloud_HD.in:66-112,
+    initial_cloud_MHD.in:27-40): every Boundary object in list order, each over
+    the faces it applies to (Cello/mesh_Block.cpp:1057-1077)."""
+    def refresh(b):
+        boundary(b, 0, 1, "outflow")
+        boundary_inflow(b, 0, 0, CLOUD_INFLOW)
+        for axis in (1, 2):
+            boundary(b, axis, 0, "outflow")
+            boundary(b, axis, 1, "outflow")
+        if mhd:
+            boundary_inflow(b, 0, 0, CLOUD_INFLOW_B)
+    return refresh
+
+
+def slice_asym(grid, slice_ax, slice_ind, flip_across):
+    """run_dual_energy_cloud_test.py:27-54; grid is indexed (x, y, z)"""
+    if slice_ax == 'x':
+        slice_arr = grid[slice_ind, :, :]
+        flipped = (grid[slice_ind, :, ::-1] if flip_across == 'y'
+                   else grid[slice_ind, ::-1, :])
+    elif slice_ax == 'y':
+        slice_arr = grid[:, slice_ind, :]
+        flipped = (grid[:, slice_ind, ::-1] if flip_across == 'x'
+                   else grid[::-1, slice_ind, :])
+    else:
+        slice_arr = grid[:, :, slice_ind]
+        flipped = (grid[:, ::-1, slice_ind] if flip_across == 'x'
+                   else grid[::-1, :, slice_ind])
+    return float(np.sum(np.abs((slice_arr - flipped) / slice_arr)))
+
+
+def cloud_asymmetries(f, g):
+    """check_cloud_asym (run_dual_energy_cloud_test.py:56-77): the three
+    slices of the density the reference test inspects"""
+    gx, gy, gz = g
+    grid = f["density"][gz:-gz, gy:-gy, gx:-gx].transpose(2, 1, 0)
+    return [slice_asym(grid, *args) for args in
+            (('z', 16, 'x'), ('y', 16, 'x'), ('x', 16, 'z'))]
+
+
+def run_cloud(solver, kind="oracle"):
+    cfg, f, blk, n, g, d, t_stop = cloud_setup(solver)
+    method = oracle.CpuMethod(cfg, g, kind=kind)
+    refresh = cloud_refresh(cfg.mhd_choice == 1, oracle.boundary,
+                            oracle.boundary_inflow)
+    dts = evolve(method, blk, t_stop, refresh, dump_times=(t_stop,))
+    method.close()
+    return cfg, f, g, dts

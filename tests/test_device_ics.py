@@ -1,6 +1,6 @@
 """The problem initialisers that generate the reference's answer-test problems
 directly in device memory (enzo-e_b200/problems.py: inclined linear waves,
-shock tubes) against the oracle's C restatement of the reference's Initial
+shock tubes, the cloud in a wind) against the oracle's C restatement of the reference's Initial
 classes -- on the CPU here (torch as the array library), and on the GPU
 through whole golden runs."""
 import numpy as np
@@ -36,6 +36,37 @@ def test_shock_tubes_match_oracle_ic(axis):
                         gamma=cfg.gamma, axis_velocity=P.SOD_BKG_VELOCITY,
                         dual_energy=True)
     assert all(np.array_equal(got[k].numpy(), f[k]) for k in f)
+
+
+@pytest.mark.parametrize("solver", ["hlld", "hllc"])
+def test_cloud_matches_oracle_ic(solver):
+    """EnzoInitialCloud: the answer test's cloud, bit for bit"""
+    from enzo_e_b200 import problems as DP
+    cfg, f, blk, n, g, d, t_stop = P.cloud_setup(solver)
+    got = DP.cloud(n, g, P.CLOUD_LOWER, d, device="cpu", mhd=cfg.mhd_choice == 1,
+                   **P.CLOUD)
+    assert set(got) == set(f)
+    assert all(np.array_equal(got[k].numpy(), f[k]) for k in f)
+    inside = f["density"] == P.CLOUD["cloud_density"]
+    outside = f["density"] == P.CLOUD["wind_density"]
+    assert inside.sum() > 1000 and 0 < (~inside & ~outside).sum() < inside.sum()
+
+
+def test_cloud_off_centre_matches_oracle_ic():
+    """an off-centre sphere on cells whose width is not a power of two, 8^3
+    sub-cells, without dual energy: hundreds of distinct cut-cell fractions"""
+    from enzo_e_b200 import problems as DP
+    cfg = P.make_config(riemann="hllc", recon="plm", mhd=False)
+    n, g, d = (20, 14, 18), (3, 3, 3), (0.11, 0.11, 0.11)
+    lower = (-1.0, -0.8, -0.9)
+    kw = dict(P.CLOUD, center=(0.13, -0.07, 0.21), cloud_radius=0.61, subsample_n=3,
+              wind_internal_energy=0.0)
+    f = P.alloc_fields(cfg, n, g)
+    oracle.ic_cloud(oracle.numpy_block(f, n, g, d), lower, **kw)
+    got = DP.cloud(n, g, lower, d, device="cpu", mhd=False, dual_energy=False, **kw)
+    assert set(got) == set(f)
+    assert all(np.array_equal(got[k].numpy(), f[k]) for k in f)
+    assert np.unique(f["density"]).size > 100
 
 
 @pytest.mark.gpu

@@ -112,3 +112,36 @@ def test_boundary_kernels_match_oracle(kind):
             eq = bit_equal(want, got)
             assert all(eq.values()), (axis, side, [k for k, v in eq.items() if not v])
     method.close()
+
+
+def test_inflow_boundary_kernel_matches_oracle():
+    """vlct_boundary_inflow against the oracle's restatement of
+    BoundaryValue::enforce: every axis and side, a field list that mixes cell-
+    and face-centred fields and one of two passive scalars"""
+    from helpers import make_config, random_state, copy_state, bit_equal, oracle
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(riemann="hlld", recon="plm", mhd=True, dual_energy=True,
+                      n_passive=2)
+    n, g, d = (9, 5, 7), (3, 3, 3), (0.1, 0.1, 0.1)
+    passive = [f"passive_{i}" for i in range(2)]
+    values = {"density": 0.25, "velocity_x": 1.5, "total_energy": 9.0,
+              "internal_energy": 7.0, "bfieldi_x": -2.0, "bfieldi_z": 3.0,
+              "bfield_y": 0.0}
+    host = random_state(cfg, n, g, seed=43)
+    method = EnzoMethodMHDVlct(config=cfg)
+    for axis in range(3):
+        for side in (0, 1):
+            want = copy_state(host)
+            blk = oracle.numpy_block(want, n, g, d, passive)
+            oracle.boundary_inflow(blk, axis, side, values, passive=(None, 0.5),
+                                   n_passive=2)
+            dev = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+            block = Block(dev, n, g, d, passive=passive)
+            method.boundary_inflow(block, axis, side, values, passive=(None, 0.5))
+            method.synchronize()
+            got = {k: v.cpu().numpy() for k, v in dev.items()}
+            eq = bit_equal(want, got)
+            assert all(eq.values()), (axis, side, [k for k, v in eq.items() if not v])
+            changed = [k for k in host if not np.array_equal(host[k], got[k])]
+            assert sorted(changed) == sorted(list(values) + ["passive_1"])
+    method.close()

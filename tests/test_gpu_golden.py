@@ -314,3 +314,43 @@ def test_passive_scalar_sound_wave_golden_on_device(axis):
     m.close()
     assert dts == dts2
     assert all(bit_equal(f2, f).values())
+
+
+# ---------------------------------------------------------------------------
+# cloud in a wind, dual energy, inflow / outflow boundaries: symmetry test
+# (input/vlct/run_dual_energy_cloud_test.py:80-85), generated, refreshed and
+# evolved on the device
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["hlld", "hllc", "hlle"])
+def test_dual_energy_cloud_symmetry_on_device(solver):
+    import torch
+    from enzo_e_b200 import problems as DP
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = P.cloud_config(solver)
+    mhd = cfg.mhd_choice == 1
+    n, g, d = (32, 32, 32), (3, 3, 3), (0.125,) * 3
+    dev = DP.cloud(n, g, P.CLOUD_LOWER, d, device="cuda", mhd=mhd, **P.CLOUD)
+    method = EnzoMethodMHDVlct(config=cfg)
+    block = Block(dev, n, g, d)
+
+    class Run:
+        def timestep(self, _b):
+            return method.timestep(block)
+
+        def compute(self, _b, dt):
+            method.compute(block, dt)
+    refresh = P.cloud_refresh(
+        mhd, lambda b, ax, side, kind: method.boundary(block, ax, side, kind),
+        lambda b, ax, side, values: method.boundary_inflow(block, ax, side, values))
+    dts = P.evolve(Run(), None, P.CLOUD_T_STOP, refresh, dump_times=(P.CLOUD_T_STOP,))
+    method.synchronize()
+    f = {k: v.cpu().numpy() for k, v in dev.items()}
+    method.close()
+    asym = P.cloud_asymmetries(f, g)
+    assert max(asym) <= P.CLOUD_MAX_ASYM[solver], asym
+    # and the whole run matches the oracle's bits (IC, boundaries, every dt)
+    cfg2, f2, g2, dts2 = P.run_cloud(solver)
+    assert dts == dts2
+    eq = bit_equal(f2, f)
+    eq.pop("pressure", None)
+    assert all(eq.values()), {k: v for k, v in eq.items() if not v}

@@ -162,6 +162,46 @@ def test_boundary_conditions_follow_enzo_boundary():
                 assert all(bit_equal(want, f).values()), (kind, axis, side)
 
 
+def test_inflow_boundary_follows_boundary_value():
+    """"inflow" ghost fill against a direct numpy statement of
+    BoundaryValue::enforce (Cello/problem_BoundaryValue.cpp:131-273): the g
+    outermost layers of the listed fields, boundary face untouched"""
+    cfg = make_config(riemann="hlld", recon="plm", mhd=True, dual_energy=True)
+    n, g, d = (6, 5, 4), (3, 3, 3), (0.1, 0.1, 0.1)
+    values = {"density": 0.25, "velocity_x": 1.5, "internal_energy": 7.0,
+              "bfieldi_x": -2.0, "bfieldi_z": 3.0, "bfield_y": 0.0}
+    for axis in range(3):
+        for side in (0, 1):
+            f = random_state(cfg, n, g, seed=32)
+            want = copy_state(f)
+            blk = oracle.numpy_block(f, n, g, d)
+            oracle.boundary_inflow(blk, axis, side, values)
+            for name, val in values.items():
+                v = np.moveaxis(want[name], 2 - axis, 0)
+                if side == 0:
+                    v[:g[axis]] = val
+                else:
+                    v[v.shape[0] - g[axis]:] = val
+            assert all(bit_equal(want, f).values()), (axis, side)
+
+
+@pytest.mark.parametrize("solver", ["hlld", "hllc", "hlle"])
+def test_dual_energy_cloud_symmetry(solver):
+    """run_dual_energy_cloud_test.py:80-85: a cloud in a Mach-1.5 wind (32^3,
+    dual energy, inflow / outflow boundaries) run to t = 0.0625 keeps the
+    density symmetric about the wind axis to the reference's tolerance"""
+    cfg, f, g, dts = P.run_cloud(solver)
+    asym = P.cloud_asymmetries(f, g)
+    assert max(asym) <= P.CLOUD_MAX_ASYM[solver], asym
+    act = (slice(3, -3),) * 3
+    assert f["density"][act].max() > 16.0 and f["density"][act].min() > 0.0
+    assert len(dts) > 20
+    if oracle.have_ref():          # the reference's own compiled sources agree
+        cfg2, f2, g2, dts2 = P.run_cloud(solver, kind="ref")
+        assert dts == dts2
+        assert all(bit_equal(f, f2).values())
+
+
 def test_compiled_reference_reproduces_rj2a_golden():
     """the reference's own compiled sources on the same shock tube"""
     if not oracle.have_ref():
