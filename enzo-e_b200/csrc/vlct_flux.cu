@@ -166,6 +166,60 @@ solve_and_store(const Params& P, const double* wl_, const double* wr_,
   }
 }
 
+// The cells a column needs next are fetched kRingAhead faces ahead with
+// cp.async into a ring of thread-private shared-memory slots: no registers are
+// held across the Riemann solve for them, and the loads that feed the slopes
+// hit shared memory instead of waiting for L2 / HBM (the marching kernels spent
+// a quarter of their stall cycles on that scoreboard).
+#ifndef VLCT_MARCH_RING
+#define VLCT_MARCH_RING 1
+#endif
+constexpr int kRingAhead = 3, kRingDepth = 4;    // depth: a power of two > ahead
+template <bool MHD> struct RingVars { static constexpr int n = MHD ? 9 : 5; };
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* src)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{ asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait()
+{ asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+/// start the copy of cell c (and of the longitudinal face field at fb) into
+/// one ring slot; slot points at this thread's first entry, T = entries per
+/// variable
+template <bool MHD, bool DE, int T>
+__device__ __forceinline__ void ring_issue(double* slot, const State& u, size_t c,
+                                           const double* bi, size_t fb)
+{
+  cp_async8(slot, u.rho + c);
+  cp_async8(slot + T, u.vx + c);
+  cp_async8(slot + 2 * T, u.vy + c);
+  cp_async8(slot + 3 * T, u.vz + c);
+  cp_async8(slot + 4 * T, (DE ? u.eint : u.etot) + c);
+  if (MHD) {
+    cp_async8(slot + 5 * T, u.bx + c);
+    cp_async8(slot + 6 * T, u.by + c);
+    cp_async8(slot + 7 * T, u.bz + c);
+    cp_async8(slot + 8 * T, bi + fb);
+  }
+}
+
+/// primitives of the cell held by a ring slot (+ the face field that came along)
+template <int DIM, bool MHD, bool DE, int T>
+__device__ __forceinline__ void ring_cell(const Params& P, const double* slot,
+                                          double (&w)[NVars<MHD>::n], double& blong)
+{
+  double v[3], b[3] = { 0., 0., 0. };
+  const double rho = slot[0];
+  v[0] = slot[T]; v[1] = slot[2 * T]; v[2] = slot[3 * T];
+  const double e = slot[4 * T];
+  if (MHD) { b[0] = slot[5 * T]; b[1] = slot[6 * T]; b[2] = slot[7 * T]; blong = slot[8 * T]; }
+  cell_primitives<DIM, MHD, DE>(P, rho, v, b, e, w);
+}
+
 // ---------------------------------------------------------------------------
 // sweep along x: one warp = 32 consecutive faces of one row
 // ---------------------------------------------------------------------------
@@ -246,13 +300,17 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
       j = box.lo[1];
       unstack(G, box, (row + 1) / (unsigned) nyb, kl, k);
     }
+    double W[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) W[v] = 0.;
+    double blong = 0.;
     if (row + 1 < row1 && i < G.mx) {
       prefetch_cell<MHD, DE>(u, cidx(G, k, j, i));
       if (MHD) prefetch_l1(bi + fidx(G, 0, k, j, i + 1));
     }
-    double W[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) W[v] = 0.;
+    // face f of the sweep <-> index f+1 of the face-centred array; loaded here,
+    // with the cell, ahead of the slopes, so that its latency is hidden (x sweeps -6 %)
+    if (MHD && lane < nf) blong = __ldg(bi + fidx(G, 0, kc, jc, i + 1));
     if (i < G.mx) {
       load_cell<0, MHD, DE>(P, u, rowbase + i, W);
 #pragma unroll
@@ -291,9 +349,6 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
 
     if (lane < nf) {
       const size_t c = rowbase + i;
-      double blong = 0.;
-      // face f of the sweep <-> index f+1 of the face-centred array
-      if (MHD) blong = __ldg(bi + fidx(G, 0, kc, jc, i + 1));
       solve_and_store<0, RECON, SOLVER, DE>(P, wl, wr, blong, F, spec, c, 1);
     }
   }
@@ -304,60 +359,6 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
 // ---------------------------------------------------------------------------
 constexpr int kMarchThreads = 128;
 
-// The cells a column needs next are fetched kRingAhead faces ahead with
-// cp.async into a ring of thread-private shared-memory slots: no registers are
-// held across the Riemann solve for them, and the loads that feed the slopes
-// hit shared memory instead of waiting for L2 / HBM (the marching kernels spent
-// a quarter of their stall cycles on that scoreboard).
-#ifndef VLCT_MARCH_RING
-#define VLCT_MARCH_RING 1
-#endif
-constexpr int kRingAhead = 3, kRingDepth = 4;    // depth: a power of two > ahead
-template <bool MHD> struct RingVars { static constexpr int n = MHD ? 9 : 5; };
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* src)
-{
-  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit()
-{ asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait()
-{ asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
-/// start the copy of cell c (and of the longitudinal face field at fb) into
-/// one ring slot; slot points at this thread's first entry
-template <bool MHD, bool DE>
-__device__ __forceinline__ void ring_issue(double* slot, const State& u, size_t c,
-                                           const double* bi, size_t fb)
-{
-  constexpr int T = kMarchThreads;
-  cp_async8(slot, u.rho + c);
-  cp_async8(slot + T, u.vx + c);
-  cp_async8(slot + 2 * T, u.vy + c);
-  cp_async8(slot + 3 * T, u.vz + c);
-  cp_async8(slot + 4 * T, (DE ? u.eint : u.etot) + c);
-  if (MHD) {
-    cp_async8(slot + 5 * T, u.bx + c);
-    cp_async8(slot + 6 * T, u.by + c);
-    cp_async8(slot + 7 * T, u.bz + c);
-    cp_async8(slot + 8 * T, bi + fb);
-  }
-}
-
-/// primitives of the cell held by a ring slot (+ the face field that came along)
-template <int DIM, bool MHD, bool DE>
-__device__ __forceinline__ void ring_cell(const Params& P, const double* slot,
-                                          double (&w)[NVars<MHD>::n], double& blong)
-{
-  constexpr int T = kMarchThreads;
-  double v[3], b[3] = { 0., 0., 0. };
-  const double rho = slot[0];
-  v[0] = slot[T]; v[1] = slot[2 * T]; v[2] = slot[3 * T];
-  const double e = slot[4 * T];
-  if (MHD) { b[0] = slot[5 * T]; b[1] = slot[6 * T]; b[2] = slot[7 * T]; blong = slot[8 * T]; }
-  cell_primitives<DIM, MHD, DE>(P, rho, v, b, e, w);
-}
 
 template <int DIM, int RECON, int SOLVER, bool DE>
 __global__ void __launch_bounds__(kMarchThreads,
@@ -431,7 +432,7 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
 #pragma unroll
   for (int a = 0; a < kRingAhead; a++) {
     if (f0 + kFirst + a < mdim)
-      ring_issue<MHD, DE>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi, fb + a * sd);
+      ring_issue<MHD, DE, kMarchThreads>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi, fb + a * sd);
     cp_async_commit();
   }
   int slot = 0;
@@ -444,11 +445,11 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
     double blong = 0.;
 #if VLCT_MARCH_RING
     if (f + kFirst + kRingAhead < mdim)
-      ring_issue<MHD, DE>(ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
+      ring_issue<MHD, DE, kMarchThreads>(ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
                           c + (kFirst + kRingAhead) * sd, bi, fb + kRingAhead * sd);
     cp_async_commit();
     cp_async_wait<kRingAhead>();            // the group of this face has landed
-    ring_cell<DIM, MHD, DE>(P, ring0 + slot * kSlot, Wn, blong);
+    ring_cell<DIM, MHD, DE, kMarchThreads>(P, ring0 + slot * kSlot, Wn, blong);
     slot = (slot + 1) & (kRingDepth - 1);
 #else
     if (f + kFirst + kAhead < mdim) {
