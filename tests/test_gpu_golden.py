@@ -153,6 +153,60 @@ def test_orszag_tang_properties_192():
     method.close()
 
 
+def test_full_size_512_bit_identical_to_oracle():
+    """BASELINE's headline configuration at full size (Orszag-Tang 512^3,
+    PLM + HLLD + CT) against the CPU oracle, bit for bit: the problem is
+    extruded along z and periodic, so a 512 x 512 x 4 slab evolves through the
+    same planes. The oracle runs the slab from the first levels of the GPU's own
+    initial state; after two cycles every dt, the lowest and the highest levels
+    of every field (ghost zones included) and -- through z-invariance on the
+    device -- every other level of the 512^3 block equal the oracle's."""
+    import torch
+    from enzo_e_b200 import problems
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    N, nzs, g = 512, 4, (3, 3, 3)
+    d = (1.0 / N,) * 3
+    cfg = make_config(riemann="hlld", recon="plm", theta=1.5, mhd=True)
+    f = problems.orszag_tang((N, N, N), g, (0.0, 0.0, 0.0), d, device="cuda")
+    ms = nzs + 2 * g[2]                       # levels of the slab
+    levels = lambda k: ms + (1 if k == "bfieldi_z" else 0)   # noqa: E731
+    host = {k: v[:levels(k)].cpu().numpy().copy() for k, v in f.items()}
+    method = EnzoMethodMHDVlct(config=cfg)
+    block = Block(f, (N, N, N), g, d)
+    dts = []
+    for _ in range(2):
+        dts.append(method.timestep(block))
+        method.refresh_periodic(block, 7)
+        method.compute(block, dts[-1])
+    method.synchronize()
+
+    cpu = oracle.CpuMethod(cfg, g)
+    blk = oracle.numpy_block(host, (N, N, nzs), g, d)
+    dts_cpu = []
+    for _ in range(2):
+        dts_cpu.append(cpu.timestep(blk))
+        oracle.refresh_periodic(blk, 0)
+        cpu.compute(blk, dts_cpu[-1])
+    cpu.close()
+    assert dts == dts_cpu
+
+    half = ms // 2
+    for k, v in f.items():
+        if k == "pressure":
+            continue
+        n_lev = levels(k)
+        lo = v[:half].cpu().numpy()
+        hi = v[v.shape[0] - (n_lev - half):].cpu().numpy()
+        assert np.array_equal(lo.view(np.uint64), host[k][:half].view(np.uint64)), k
+        assert np.array_equal(hi.view(np.uint64), host[k][half:].view(np.uint64)), k
+        # the levels in between: identical to the first active level
+        inner = v[g[2]:v.shape[0] - g[2]]
+        assert bool((inner == inner[0:1]).all()), f"{k} is not z-invariant"
+    assert not np.array_equal(host["density"][g[2]], np.full_like(host["density"][g[2]],
+                                                                  host["density"][g[2], 0, 0]))
+    method.close()
+
+
 def _permute_state(f, cfg):
     """(x,y,z) -> (y,z,x): new x axis = old y, ... ; vector components cycle"""
     def arr(a):
