@@ -1442,14 +1442,21 @@ int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
   std::vector<RefreshField> fields;
   collect_fields(h, b, G, fields);
   const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
+  WrapTable table;
+  table.count = 0;
+  for (const RefreshField& f : fields) {
+    if (table.count == kMaxWrapFields)
+      return fail(h, VLCT_ERR_INTERNAL, "too many fields for the wrap table");
+    table.p[table.count] = f.p;
+    table.face[table.count++] = f.face;
+  }
   for (int axis = 0; axis < 3; axis++) {
     if (!(axes & (1 << axis))) continue;
     if (n[axis] < g[axis])
       return fail(h, VLCT_ERR_INVALID_BLOCK,
                   "periodic refresh needs n >= ghost depth along every axis");
-    for (const RefreshField& f : fields)
-      launch_wrap_axis(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
-                       f.n2, axis, n[axis], g[axis], f.face == axis ? 1 : 0);
+    launch_wrap_axis_all(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my,
+                         G.mx, axis, n[axis], g[axis]);
   }
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
@@ -1558,7 +1565,11 @@ int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
   collect_fields(h, b, G, fields);
   const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
   size_t off = 0;
+  SlabTable table;
+  table.count = 0;
   for (const RefreshField& f : fields) {
+    if (table.count == kMaxWrapFields)
+      return fail(h, VLCT_ERR_INTERNAL, "too many fields for the slab table");
     // Along `axis` a cell-centred field has ghosts [0,g) and [g+n, 2g+n); a
     // field that is face-centred along `axis` (cen = 1) has n+1 active faces
     // [g, g+n] and ghosts [0,g), [g+n+1, 2g+n+1). The shared boundary face is
@@ -1572,13 +1583,17 @@ int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
     int lo;
     if (pack) lo = (side == 0) ? g[axis] + cen : n[axis];
     else      lo = (side == 0) ? 0 : g[axis] + n[axis] + cen;
-    launch_slab_copy(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
-                     f.n2, axis, lo, width, buffer + off, pack);
+    table.p[table.count] = f.p;
+    table.face[table.count] = f.face;
+    table.lo[table.count] = lo;
+    table.off[table.count++] = (long long) off;
     const int ext[3] = { f.n2, f.n1, f.n0 };
     size_t cnt = (size_t) width;
     for (int a = 0; a < 3; a++) if (a != axis) cnt *= (size_t) ext[a];
     off += cnt;
   }
+  launch_slab_copy_all(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+                       axis, g[axis], buffer, pack);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
 }

@@ -434,10 +434,16 @@ __global__ void k_step_params(const double* dt_dev, double dt_host, int nstages,
 // ---------------------------------------------------------------------------
 // ghost-zone helpers (stand-ins for the refresh phase on a unigrid)
 // ---------------------------------------------------------------------------
+/// the periodic wrap of all fields of a block along one axis in one launch:
+/// blockIdx.y = field (face: -1 cell-centred, else the axis it is face-centred on)
 __global__ void __launch_bounds__(256)
-k_wrap_axis(double* p, int n0, int n1, int n2, int axis, int n, int g, int cen)
+k_wrap_axis_all(const __grid_constant__ WrapTable T, int mz, int my, int mx, int axis,
+                int n, int g)
 {
-  // threads enumerate the ghost layers only: 2g layers along `axis`
+  const int face = T.face[blockIdx.y];
+  double* const p = T.p[blockIdx.y];
+  const int n0 = mz + (face == 2), n1 = my + (face == 1), n2 = mx + (face == 0);
+  const int cen = (face == axis) ? 1 : 0;
   const int ext[3] = { n2, n1, n0 };
   int sh[3] = { ext[0], ext[1], ext[2] };
   sh[axis] = 2 * g;
@@ -448,7 +454,7 @@ k_wrap_axis(double* p, int n0, int n1, int n2, int axis, int n, int g, int cen)
     idx[0] = (int) (t % sh[0]);
     idx[1] = (int) ((t / sh[0]) % sh[1]);
     idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
-    int a = idx[axis];
+    const int a = idx[axis];
     int dst, src;
     if (a < g) { dst = a; src = a + n; }
     else       { dst = g + n + cen + (a - g); src = dst - n; }
@@ -536,12 +542,18 @@ k_batch_copy(double* __restrict__ stacked, double* const* __restrict__ ptrs,
   }
 }
 
+/// ghost-exchange slabs of all fields of a block along one axis, packed into /
+/// unpacked from one contiguous buffer in one launch: blockIdx.y = field
 __global__ void __launch_bounds__(256)
-k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
-            double* buffer, int pack)
+k_slab_copy_all(const __grid_constant__ SlabTable T, int mz, int my, int mx, int axis,
+                int width, double* buffer, int pack)
 {
-  const int ext[3] = { n2, n1, n0 };
-  int sh[3] = { ext[0], ext[1], ext[2] };
+  const int face = T.face[blockIdx.y];
+  double* const field = T.p[blockIdx.y];
+  double* const buf = buffer + T.off[blockIdx.y];
+  const int lo = T.lo[blockIdx.y];
+  const int n1 = my + (face == 1), n2 = mx + (face == 0);
+  int sh[3] = { n2, n1, mz + (face == 2) };
   sh[axis] = width;
   const size_t total = (size_t) sh[0] * sh[1] * sh[2];
   for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -552,8 +564,8 @@ k_slab_copy(double* field, int n0, int n1, int n2, int axis, int lo, int width,
     idx[2] = (int) (t / ((size_t) sh[0] * sh[1]));
     idx[axis] += lo;
     const size_t f = ((size_t) idx[2] * n1 + idx[1]) * n2 + idx[0];
-    if (pack) buffer[t] = field[f];
-    else      field[f] = buffer[t];
+    if (pack) buf[t] = field[f];
+    else      field[f] = buf[t];
   }
 }
 
@@ -758,18 +770,20 @@ void launch_step_params(const LaunchCtx& ctx, const double* dt_dev, double dt_ho
                                      width[2], out);
 }
 
-void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
-                      int axis, int n, int g, int cen)
+void launch_wrap_axis_all(const LaunchCtx& ctx, const WrapTable& T, int mz, int my,
+                          int mx, int axis, int n, int g)
 {
-  cudaStream_t st = ctx.st;
-  const int ext[3] = { n2, n1, n0 };
+  if (T.count == 0) return;
+  // sized for the largest (face-centred) field; every field strides over its own
+  const int ext[3] = { mx + 1, my + 1, mz + 1 };
   size_t total = (size_t) 2 * g;
   for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
   if (total == 0) return;
   int blocks = (int) ((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int cap = (148 * 16 + T.count - 1) / T.count;
+  if (blocks > cap) blocks = cap;
   ScopedLaunch sl(ctx, "k_wrap_axis");
-  k_wrap_axis<<<blocks, 256, 0, st>>>(p, n0, n1, n2, axis, n, g, cen);
+  k_wrap_axis_all<<<dim3(blocks, T.count), 256, 0, ctx.st>>>(T, mz, my, mx, axis, n, g);
 }
 
 void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
@@ -817,18 +831,20 @@ void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptr
                                                       to_stacked ? 1 : 0);
 }
 
-void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,
-                      int axis, int lo, int width, double* buffer, bool pack)
+void launch_slab_copy_all(const LaunchCtx& ctx, const SlabTable& T, int mz, int my,
+                          int mx, int axis, int width, double* buffer, bool pack)
 {
-  cudaStream_t st = ctx.st;
-  const int ext[3] = { n2, n1, n0 };
+  if (T.count == 0) return;
+  const int ext[3] = { mx + 1, my + 1, mz + 1 };
   size_t total = (size_t) width;
   for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
   if (total == 0) return;
   int blocks = (int) ((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int cap = (148 * 16 + T.count - 1) / T.count;
+  if (blocks > cap) blocks = cap;
   ScopedLaunch sl(ctx, pack ? "k_slab_pack" : "k_slab_unpack");
-  k_slab_copy<<<blocks, 256, 0, st>>>(field, n0, n1, n2, axis, lo, width, buffer, pack ? 1 : 0);
+  k_slab_copy_all<<<dim3(blocks, T.count), 256, 0, ctx.st>>>(T, mz, my, mx, axis, width,
+                                                             buffer, pack ? 1 : 0);
 }
 
 }  // namespace vlct

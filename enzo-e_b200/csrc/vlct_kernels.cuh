@@ -148,8 +148,15 @@ void launch_timestep(const LaunchCtx& ctx, const Params& P, const Geom& G,
                      unsigned long long* dt_bits, ZClip zc = kNoClip);
 
 /// periodic self-refresh of one field along one axis
-void launch_wrap_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
-                      int axis, int n, int g, int cen);
+/// every field of a block, for the one-launch periodic wrap along an axis
+constexpr int kMaxWrapFields = 16 + kMaxPassive;
+struct WrapTable {
+  double* p[kMaxWrapFields];
+  int face[kMaxWrapFields];   // -1: cell-centred; 0/1/2: face-centred along x/y/z
+  int count;
+};
+void launch_wrap_axis_all(const LaunchCtx& ctx, const WrapTable& T, int mz, int my,
+                          int mx, int axis, int n, int g);
 
 /// outflow / reflecting boundary of one field on one face of the domain
 void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
@@ -171,7 +178,14 @@ void launch_batch_copy(const LaunchCtx& ctx, double* stacked, double* const* ptr
 
 /// halo slab pack / unpack of one field along one axis
 /// lo..lo+g: range along the axis; the slab spans the full other extents
-void launch_slab_copy(const LaunchCtx& ctx, double* field, int n0, int n1, int n2,
-                      int axis, int lo, int width, double* buffer, bool pack);
+struct SlabTable {
+  double* p[kMaxWrapFields];
+  int face[kMaxWrapFields];
+  int lo[kMaxWrapFields];           // first layer of the slab along the axis
+  long long off[kMaxWrapFields];    // offset of the field's slab in the buffer
+  int count;
+};
+void launch_slab_copy_all(const LaunchCtx& ctx, const SlabTable& T, int mz, int my,
+                          int mx, int axis, int width, double* buffer, bool pack);
 
 }  // namespace vlct
