@@ -1483,13 +1483,19 @@ int vlct_boundary(vlct_handle* h, const vlct_block* b, int axis, int side, int t
                               { b->velocity_z, b->bfield_z, b->bfieldi_z } };
   std::vector<RefreshField> fields;
   collect_fields(h, b, G, fields);
+  BoundaryTable table;
+  table.count = 0;
   for (const RefreshField& f : fields) {
+    if (table.count == kMaxWrapFields)
+      return fail(h, VLCT_ERR_INTERNAL, "too many fields for the boundary table");
     double sign = 1.0;
     for (int c = 0; c < 3; c++) if (f.p == vec[axis][c]) sign = -1.0;
-    launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, f.p, f.n0, f.n1,
-                         f.n2, axis, n[axis], g[axis], f.face == axis ? 1 : 0,
-                         side, type, sign);
+    table.p[table.count] = f.p;
+    table.face[table.count] = f.face;
+    table.sign[table.count++] = sign;
   }
+  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+                       axis, n[axis], g[axis], side, type);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
 }
@@ -1517,19 +1523,23 @@ int vlct_boundary_inflow(vlct_handle* h, const vlct_block* b, int axis, int side
     { b->bfieldi_x, v->bfieldi_x, 0 }, { b->bfieldi_y, v->bfieldi_y, 1 },
     { b->bfieldi_z, v->bfieldi_z, 2 },
     { b->pressure, v->pressure, -1 } };
-  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  BoundaryTable table;
+  table.count = 0;
   for (const Item& it : items) {
     if (it.p == nullptr || it.value != it.value) continue;
-    launch_boundary_axis(ctx, it.p, G.mz + (it.face == 2), G.my + (it.face == 1),
-                         G.mx + (it.face == 0), axis, n[axis], g[axis],
-                         it.face == axis ? 1 : 0, side, VLCT_BOUNDARY_INFLOW, it.value);
+    table.p[table.count] = it.p;
+    table.face[table.count] = it.face;
+    table.sign[table.count++] = it.value;
   }
   for (int s = 0; s < h->P.nsc; s++) {
     const double value = v->passive[s];
     if (b->passive[s] == nullptr || value != value) continue;
-    launch_boundary_axis(ctx, b->passive[s], G.mz, G.my, G.mx, axis, n[axis], g[axis],
-                         0, side, VLCT_BOUNDARY_INFLOW, value);
+    table.p[table.count] = b->passive[s];
+    table.face[table.count] = -1;
+    table.sign[table.count++] = value;
   }
+  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+                       axis, n[axis], g[axis], side, VLCT_BOUNDARY_INFLOW);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
 }

@@ -470,10 +470,17 @@ k_wrap_axis_all(const __grid_constant__ WrapTable T, int mz, int my, int mx, int
 /// (enzo-core/EnzoBoundary.cpp:164-283 reflecting, :352-466 outflow): threads
 /// enumerate the g ghost layers of one side; the other two axes run over their
 /// full, ghost- and centering-including extent like the reference's loops.
+/// (all fields of the boundary in one launch: blockIdx.y = field; T.sign holds
+/// the field's sign under reflection resp. its inflow value)
 __global__ void __launch_bounds__(256)
-k_boundary_axis(double* p, int n0, int n1, int n2, int axis, int n, int g,
-                int cen, int side, int type, double sign)
+k_boundary_axis(const __grid_constant__ BoundaryTable T, int mz, int my, int mx,
+                int axis, int n, int g, int side, int type)
 {
+  const int face = T.face[blockIdx.y];
+  double* const p = T.p[blockIdx.y];
+  const double sign = T.sign[blockIdx.y];
+  const int n0 = mz + (face == 2), n1 = my + (face == 1), n2 = mx + (face == 0);
+  const int cen = (face == axis) ? 1 : 0;
   const int ext[3] = { n2, n1, n0 };
   int sh[3] = { ext[0], ext[1], ext[2] };
   sh[axis] = g;
@@ -786,19 +793,20 @@ void launch_wrap_axis_all(const LaunchCtx& ctx, const WrapTable& T, int mz, int 
   k_wrap_axis_all<<<dim3(blocks, T.count), 256, 0, ctx.st>>>(T, mz, my, mx, axis, n, g);
 }
 
-void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
-                          int axis, int n, int g, int cen, int side, int type,
-                          double sign)
+void launch_boundary_axis(const LaunchCtx& ctx, const BoundaryTable& T, int mz, int my,
+                          int mx, int axis, int n, int g, int side, int type)
 {
-  const int ext[3] = { n2, n1, n0 };
+  if (T.count == 0) return;
+  const int ext[3] = { mx + 1, my + 1, mz + 1 };
   size_t total = (size_t) g;
   for (int a = 0; a < 3; a++) if (a != axis) total *= (size_t) ext[a];
   if (total == 0) return;
   int blocks = (int) ((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int cap = (148 * 16 + T.count - 1) / T.count;
+  if (blocks > cap) blocks = cap;
   ScopedLaunch sl(ctx, "k_boundary_axis");
-  k_boundary_axis<<<blocks, 256, 0, ctx.st>>>(p, n0, n1, n2, axis, n, g, cen, side,
-                                              type, sign);
+  k_boundary_axis<<<dim3(blocks, T.count), 256, 0, ctx.st>>>(T, mz, my, mx, axis, n, g,
+                                                             side, type);
 }
 
 void launch_face_flux(const LaunchCtx& ctx, const Geom& G, const double* flux,

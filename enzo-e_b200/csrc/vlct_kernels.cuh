@@ -159,9 +159,14 @@ void launch_wrap_axis_all(const LaunchCtx& ctx, const WrapTable& T, int mz, int 
                           int mx, int axis, int n, int g);
 
 /// outflow / reflecting boundary of one field on one face of the domain
-void launch_boundary_axis(const LaunchCtx& ctx, double* p, int n0, int n1, int n2,
-                          int axis, int n, int g, int cen, int side, int type,
-                          double sign);
+struct BoundaryTable {
+  double* p[kMaxWrapFields];
+  int face[kMaxWrapFields];
+  double sign[kMaxWrapFields];      // reflecting: +-1; inflow: the value
+  int count;
+};
+void launch_boundary_axis(const LaunchCtx& ctx, const BoundaryTable& T, int mz, int my,
+                          int mx, int axis, int n, int g, int side, int type);
 
 /// out[(i1, i0)] = *dtdx * flux[.. at ..]: one face of the block for the
 /// flux-correction output (dim: normal axis; n0/g0, n1/g1: active size and
