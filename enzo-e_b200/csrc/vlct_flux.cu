@@ -22,7 +22,8 @@
 //                 and marches along the sweep axis with a rolling window of
 //                 primitives in registers; a warp reads 32 consecutive x, so
 //                 every load and store is coalesced and each array is read
-//                 exactly once.
+//                 exactly once. The cells of the next faces arrive through a
+//                 cp.async ring of thread-private shared-memory slots.
 //
 // Results are bit-identical to the reference's value-safe CPU build: the same
 // expressions in the same order (vlct_physics.cuh), compiled with -fmad=false.
@@ -171,9 +172,6 @@ solve_and_store(const Params& P, const double* wl_, const double* wr_,
 // held across the Riemann solve for them, and the loads that feed the slopes
 // hit shared memory instead of waiting for L2 / HBM (the marching kernels spent
 // a quarter of their stall cycles on that scoreboard).
-#ifndef VLCT_MARCH_RING
-#define VLCT_MARCH_RING 1
-#endif
 constexpr int kRingAhead = 3, kRingDepth = 4;    // depth: a power of two > ahead
 template <bool MHD> struct RingVars { static constexpr int n = MHD ? 9 : 5; };
 
@@ -425,40 +423,29 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
 
   const int mdim = (DIM == 1) ? G.my : (int) G.levels();
   constexpr int kFirst = PLM ? 2 : 1;       // the cell an iteration adds: c + kFirst sd
-#if VLCT_MARCH_RING
   constexpr int kSlot = RingVars<MHD>::n * kMarchThreads;      // doubles per slot
   __shared__ double ring[kRingDepth * kSlot];
   double* const ring0 = ring + threadIdx.x;
 #pragma unroll
   for (int a = 0; a < kRingAhead; a++) {
     if (f0 + kFirst + a < mdim)
-      ring_issue<MHD, DE, kMarchThreads>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi, fb + a * sd);
+      ring_issue<MHD, DE, kMarchThreads>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi,
+                                         fb + a * sd);
     cp_async_commit();
   }
   int slot = 0;
-#else
-  constexpr int kAhead = 2;                 // prefetch distance, in faces
-#endif
 #pragma unroll 1
   for (int f = f0; f < f1; f++, c += sd, fb += sd) {
     double Wn[NV], wr[NV], wl_next[NV];
     double blong = 0.;
-#if VLCT_MARCH_RING
     if (f + kFirst + kRingAhead < mdim)
-      ring_issue<MHD, DE, kMarchThreads>(ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
-                          c + (kFirst + kRingAhead) * sd, bi, fb + kRingAhead * sd);
+      ring_issue<MHD, DE, kMarchThreads>(
+          ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
+          c + (kFirst + kRingAhead) * sd, bi, fb + kRingAhead * sd);
     cp_async_commit();
     cp_async_wait<kRingAhead>();            // the group of this face has landed
     ring_cell<DIM, MHD, DE, kMarchThreads>(P, ring0 + slot * kSlot, Wn, blong);
     slot = (slot + 1) & (kRingDepth - 1);
-#else
-    if (f + kFirst + kAhead < mdim) {
-      prefetch_cell<MHD, DE>(u, c + (kFirst + kAhead) * sd);
-      if (MHD) prefetch_l1(bi + fb + kAhead * sd);
-    }
-    load_cell<DIM, MHD, DE>(P, u, c + kFirst * sd, Wn);
-    if (MHD) blong = __ldg(bi + fb);
-#endif
     if (PLM) {
 #pragma unroll
       for (int v = 0; v < NV; v++) {
@@ -516,7 +503,6 @@ void flux_go(const FluxLaunch& L)
     const unsigned gx = (unsigned) ((cols + kMarchThreads - 1) / kMarchThreads);
     const unsigned gy = (unsigned) ((nf + chunk - 1) / chunk) *
                         (D == 2 ? (unsigned) L.G.nrep : 1u);
-#if VLCT_MARCH_RING
     // 4 resident blocks need 4 x (36 KB ring + 1 KB) of the SM's shared memory
     static bool carveout_set = false;
     if (!carveout_set) {
@@ -524,7 +510,6 @@ void flux_go(const FluxLaunch& L)
                            cudaFuncAttributePreferredSharedMemoryCarveout, 75);
       carveout_set = true;
     }
-#endif
     k_flux_march<D, RECON, SOLVER, DE><<<dim3(gx, gy), kMarchThreads, 0, L.st>>>(
         L.P, L.G, L.cur, L.spec, L.bi, L.F, b, chunk);
   }
