@@ -271,12 +271,23 @@ def boundary_inflow(blk, axis, side, values, passive=(), n_passive=0):
 
 def ic_cloud(blk, lower, subsample_n, cloud_radius, center, cloud_density,
              wind_density, wind_velocity, wind_total_energy,
-             wind_internal_energy):
+             wind_internal_energy, ref_method=None):
     """EnzoInitialCloud (no perturbation) on a host block, ghost zones too;
-    magnetic fields (if any) must already be initialised."""
+    magnetic fields (if any) must already be initialised. ref_method: a
+    CpuMethod(kind="ref") whose field list the block matches -- then the
+    reference's own compiled EnzoInitialCloud::enforce_block fills the block
+    instead of the C restatement."""
     lo = (C.c_double * 3)(*lower)
     p = (C.c_double * 9)(cloud_radius, *center, cloud_density, wind_density,
                          wind_velocity, wind_total_energy, wind_internal_energy)
-    rc = _ic_lib().vlct_ic_cloud(C.byref(blk), lo, subsample_n, p)
+    if ref_method is not None:
+        assert ref_method.kind == "ref"
+        fn = ref_method._lib.vlct_ref_ic_cloud
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock),
+                       C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        rc = fn(ref_method._h, C.byref(blk), lo, subsample_n, p)
+    else:
+        rc = _ic_lib().vlct_ic_cloud(C.byref(blk), lo, subsample_n, p)
     if rc != 0:
         raise RuntimeError(f"vlct_ic_cloud failed ({rc})")

@@ -259,6 +259,20 @@ public:
   { if (x) *x = xm[0]; if (y) *y = xm[1]; if (z) *z = xm[2]; }
   void field_cell_width(double* hx, double* hy, double* hz) const
   { if (hx) *hx = h[0]; if (hy) *hy = h[1]; if (hz) *hz = h[2]; }
+  /// positions of cell centres (c = 0) or faces (c = 1) along each axis, ghost
+  /// zones included: lower + (index + 0.5 (1 - c)) * width, the expression of
+  /// Data::field_cell_faces (src/Cello/data_Data.cpp:91-121)
+  void field_cell_faces(double* x, double* y, double* z, int gx, int gy, int gz,
+                        int cx, int cy, int cz) const {
+    const int n[3] = { field_data.nx, field_data.ny, field_data.nz };
+    const int g[3] = { gx, gy, gz }, c[3] = { cx, cy, cz };
+    double* out[3] = { x, y, z };
+    for (int a = 0; a < 3; a++) {
+      const double d = (c[a] == 0) ? 0.5 : 0;
+      for (int i = -g[a]; i < n[a] + g[a] + c[a]; i++)
+        out[a][i + g[a]] = xm[a] + (i + d) * h[a];
+    }
+  }
   FieldData field_data;
   double xm[3] = {0,0,0};
   double h[3] = {1,1,1};
@@ -342,6 +356,24 @@ public:
   }
   int value_integer(const std::string& key, int deflt) const
   { const std::string* p = param(key); return p ? atoi(p->c_str()) : deflt; }
+  /// list parameters are stored as "v0,v1,v2"
+  int list_length(const std::string& key) const {
+    const std::string* p = param(key);
+    if (p == nullptr || p->empty()) return 0;
+    return 1 + (int) std::count(p->begin(), p->end(), ',');
+  }
+  double list_value_float(int index, const std::string& key,
+                          double deflt = 0.0) const {
+    const std::string* p = param(key);
+    if (p == nullptr) return deflt;
+    std::size_t pos = 0;
+    for (int i = 0; i < index; i++) {
+      pos = p->find(',', pos);
+      if (pos == std::string::npos) return deflt;
+      pos++;
+    }
+    return atof(p->c_str() + pos);
+  }
   std::string full_name(const std::string& key) const
   { return path_ + ":" + key; }
   std::string get_group_path() const { return path_; }
@@ -380,6 +412,21 @@ public:
 protected:
   int ir_post_;
   double courant_;
+};
+
+class Hierarchy;
+
+/// src/Cello/problem_Initial.hpp: only what an Initial subclass needs to compile
+class Initial : public PUP::able {
+public:
+  Initial(int cycle, double time) throw() : cycle_(cycle), time_(time) {}
+  Initial(CkMigrateMessage* m) : PUP::able(m), cycle_(0), time_(0.0) {}
+  virtual ~Initial() {}
+  virtual void pup(PUP::er& p) { PUP::able::pup(p); }
+  virtual void enforce_block(Block* block, const Hierarchy* hierarchy) throw() = 0;
+protected:
+  int cycle_;
+  double time_;
 };
 
 class Physics : public PUP::able {

@@ -17,6 +17,9 @@
 #include "Cello/cello.hpp"
 #include "Enzo/enzo.hpp"
 #include "Enzo/hydro-mhd/hydro-mhd.hpp"
+#ifndef VLCT_SHIM_GPU_ADAPTER
+#include "Enzo/initial/initial.hpp"     // the reference's EnzoInitialCloud
+#endif
 
 #include "../../include/vlct.h"
 
@@ -354,6 +357,34 @@ int SHIM_FN(timestep)(void* handle, const vlct_block* b, double* dt_out)
   *dt_out = h->method->timestep(&blk);
   return 0;
 }
+
+#ifndef VLCT_SHIM_GPU_ADAPTER
+/// The reference's own EnzoInitialCloud::enforce_block
+/// (src/Enzo/initial/EnzoInitialCloud.cpp:606-748, compiled unmodified) on the
+/// caller's arrays. lower: coordinates of the block's first active cell;
+/// p[] = { cloud_radius, center_x, center_y, center_z, cloud_density,
+///         wind_density, wind_velocity, wind_total_energy, wind_internal_energy }
+/// (the Initial:cloud parameters of input/vlct/dual_energy_cloud).
+int vlct_ref_ic_cloud(void* handle, const vlct_block* b, const double* lower,
+                      int subsample_n, const double* p)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->ctx->descr);
+  bind_block(h, blk, b);
+  for (int a = 0; a < 3; a++) blk.data()->xm[a] = lower[a];
+  ParameterGroup pg;
+  pg.set("subsample_n", std::to_string(subsample_n));
+  const char* keys[9] = { "cloud_radius", "cloud_center_x", "cloud_center_y",
+                          "cloud_center_z", "cloud_density", "wind_density",
+                          "wind_velocity", "wind_total_energy",
+                          "wind_internal_energy" };
+  for (int k = 0; k < 9; k++) pg.set(keys[k], fmt_double(p[k]));
+  EnzoInitialCloud initial(0, 0.0, pg);
+  initial.enforce_block(&blk, nullptr);
+  return 0;
+}
+#endif
 
 const char* SHIM_FN(name)(void* handle)
 {

@@ -202,6 +202,37 @@ def test_dual_energy_cloud_symmetry(solver):
         assert all(bit_equal(f, f2).values())
 
 
+@pytest.mark.parametrize("case", ["answer_test_hlld", "answer_test_hllc",
+                                  "off_centre"])
+def test_cloud_ic_restatement_equals_compiled_reference(case):
+    """oracle/vlct_oracle_ic.c:vlct_ic_cloud against the reference's own
+    EnzoInitialCloud::enforce_block (compiled unmodified into oracle/_ref),
+    bit for bit, ghost zones included"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    if case == "off_centre":
+        cfg = make_config(riemann="hllc", recon="plm", mhd=False)
+        n, g, d = (20, 14, 18), (3, 3, 3), (0.11, 0.11, 0.11)
+        lower = (-1.0, -0.8, -0.9)
+        kw = dict(P.CLOUD, center=(0.13, -0.07, 0.21), cloud_radius=0.61,
+                  subsample_n=3, wind_internal_energy=0.0)
+    else:
+        cfg = P.cloud_config(case[-4:])
+        n, g, d = (32, 32, 32), (3, 3, 3), (0.125,) * 3
+        lower, kw = P.CLOUD_LOWER, P.CLOUD
+    f = P.alloc_fields(cfg, n, g)
+    oracle.ic_cloud(oracle.numpy_block(f, n, g, d), lower, **kw)
+    f_ref = P.alloc_fields(cfg, n, g)
+    for k in f_ref:                 # everything the initialiser must overwrite
+        if not k.startswith("bfield") and k != "pressure":
+            f_ref[k][...] = np.nan
+    ref = oracle.CpuMethod(cfg, g, kind="ref")
+    oracle.ic_cloud(oracle.numpy_block(f_ref, n, g, d), lower, ref_method=ref, **kw)
+    ref.close()
+    assert all(bit_equal(f, f_ref).values()), bit_equal(f, f_ref)
+    assert np.unique(f["density"]).size > 10
+
+
 def test_compiled_reference_reproduces_rj2a_golden():
     """the reference's own compiled sources on the same shock tube"""
     if not oracle.have_ref():
