@@ -250,9 +250,21 @@ def refresh_periodic(blk, n_passive=0, axes=7):
 BOUNDARY_TYPES = {"outflow": 0, "reflecting": 1}
 
 
-def boundary(blk, axis, side, kind, n_passive=0):
+def boundary(blk, axis, side, kind, n_passive=0, ref_method=None):
     """EnzoBoundary::enforce on one face of the domain (host memory);
-    kind: "outflow" | "reflecting"; side 0 = lower, 1 = upper."""
+    kind: "outflow" | "reflecting"; side 0 = lower, 1 = upper. ref_method: a
+    CpuMethod(kind="ref") whose field list the block matches -- then the
+    reference's own compiled EnzoBoundary does it instead of the restatement."""
+    if ref_method is not None:
+        assert ref_method.kind == "ref"
+        fn = ref_method._lib.vlct_ref_boundary
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_int, C.c_int,
+                       C.c_int]
+        rc = fn(ref_method._h, C.byref(blk), axis, side, BOUNDARY_TYPES[kind])
+        if rc != 0:
+            raise RuntimeError(f"vlct_ref_boundary failed ({rc})")
+        return
     rc = _ic_lib().vlct_oracle_boundary(C.byref(blk), n_passive, axis, side,
                                         BOUNDARY_TYPES[kind])
     if rc != 0:

@@ -62,6 +62,14 @@ enum class InitCycleKind { fresh, charmrestart, fresh_or_noncharm_restart };
 
 enum { ir_post_unset = -1 };
 
+// src/Cello/cello.hpp:94-95 (flat index of a C-ordered (z, y, x) array)
+inline int INDEX(int ix, int iy, int iz, int nx, int ny)
+{ return ix + nx * (iy + ny * iz); }
+
+// src/Cello/cello.hpp:111-124
+enum face_enum { face_lower = 0, face_upper = 1, face_all };
+enum axis_enum { axis_x = 0, axis_y = 1, axis_z = 2, axis_all };
+
 //----------------------------------------------------------------------
 
 class Grouping {
@@ -153,6 +161,9 @@ public:
   void centering(int id, int* cx, int* cy, int* cz) const
   { descr_->centering(id, cx, cy, cz); }
   int precision(int id) const { return descr_->precision(id); }
+  int field_count() const { return descr_->field_count(); }
+  bool is_temporary(int) const { return false; }   // only permanent fields here
+  char* values(int id) { return reinterpret_cast<char*>(data_->ptrs.at(id)); }
   void size(int* nx, int* ny, int* nz) const
   { if (nx) *nx = data_->nx; if (ny) *ny = data_->ny; if (nz) *nz = data_->nz; }
   void dimensions(int id, int* mx, int* my, int* mz) const {
@@ -262,8 +273,16 @@ public:
   /// positions of cell centres (c = 0) or faces (c = 1) along each axis, ghost
   /// zones included: lower + (index + 0.5 (1 - c)) * width, the expression of
   /// Data::field_cell_faces (src/Cello/data_Data.cpp:91-121)
-  void field_cell_faces(double* x, double* y, double* z, int gx, int gy, int gz,
-                        int cx, int cy, int cz) const {
+  void upper(double* x, double* y, double* z) const {
+    const int n[3] = { field_data.nx, field_data.ny, field_data.nz };
+    double* out[3] = { x, y, z };
+    for (int a = 0; a < 3; a++) if (out[a]) *out[a] = xm[a] + n[a] * h[a];
+  }
+  void field_cells(double* x, double* y, double* z, int gx = 0, int gy = 0,
+                   int gz = 0) const
+  { field_cell_faces(x, y, z, gx, gy, gz, 0, 0, 0); }
+  void field_cell_faces(double* x, double* y, double* z, int gx = 0, int gy = 0,
+                        int gz = 0, int cx = 1, int cy = 1, int cz = 1) const {
     const int n[3] = { field_data.nx, field_data.ny, field_data.nz };
     const int g[3] = { gx, gy, gz }, c[3] = { cx, cy, cz };
     double* out[3] = { x, y, z };
@@ -412,6 +431,34 @@ public:
 protected:
   int ir_post_;
   double courant_;
+};
+
+/// src/Cello/problem_Mask.hpp: never instantiated here (boundaries without masks)
+class Mask {
+public:
+  virtual ~Mask() {}
+  virtual bool evaluate(double t, double x, double y, double z) const = 0;
+};
+
+/// src/Cello/problem_Boundary.hpp:14-120: what a Boundary subclass needs
+class Boundary : public PUP::able {
+public:
+  Boundary() throw() : axis_(axis_all), face_(face_all), mask_(nullptr) {}
+  Boundary(axis_enum axis, face_enum face, std::shared_ptr<Mask> mask) throw()
+    : axis_(axis), face_(face), mask_(mask) {}
+  Boundary(CkMigrateMessage* m)
+    : PUP::able(m), axis_(axis_all), face_(face_all), mask_(nullptr) {}
+  virtual ~Boundary() throw() {}
+  virtual void pup(PUP::er& p) { PUP::able::pup(p); }
+  virtual void enforce(Block* block, face_enum face = face_all,
+                       axis_enum axis = axis_all) const throw() = 0;
+protected:
+  bool applies_(axis_enum axis, face_enum face) const throw()
+  { return ((axis_ == axis_all || axis == axis_) &&
+            (face_ == face_all || face == face_)); }
+  axis_enum axis_;
+  face_enum face_;
+  std::shared_ptr<Mask> mask_;
 };
 
 class Hierarchy;

@@ -39,5 +39,6 @@ namespace enzo {
 // real reference headers
 #include "Enzo/utils/utils.hpp"
 #include "Enzo/fluid-props/fluid-props.hpp"
+#include "Enzo/enzo-core/EnzoBoundary.hpp"   // real: outflow / reflecting
 
 #endif /* VLCT_SHIM_ENZO_HPP */

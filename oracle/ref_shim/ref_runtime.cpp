@@ -384,6 +384,22 @@ int vlct_ref_ic_cloud(void* handle, const vlct_block* b, const double* lower,
   initial.enforce_block(&blk, nullptr);
   return 0;
 }
+
+/// The reference's own EnzoBoundary::enforce (src/Enzo/enzo-core/EnzoBoundary.cpp,
+/// compiled unmodified) for one face of the domain, on every field of the
+/// block: type 0 = "outflow", 1 = "reflecting" (the numbering of vlct.h).
+int vlct_ref_boundary(void* handle, const vlct_block* b, int axis, int side, int type)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->ctx->descr);
+  bind_block(h, blk, b);
+  EnzoBoundary boundary(axis_all, face_all, nullptr,
+                        type == VLCT_BOUNDARY_OUTFLOW ? boundary_type_outflow
+                                                      : boundary_type_reflecting);
+  boundary.enforce(&blk, side == 0 ? face_lower : face_upper, (axis_enum) axis);
+  return 0;
+}
 #endif
 
 const char* SHIM_FN(name)(void* handle)

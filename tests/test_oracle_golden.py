@@ -162,6 +162,31 @@ def test_boundary_conditions_follow_enzo_boundary():
                 assert all(bit_equal(want, f).values()), (kind, axis, side)
 
 
+@pytest.mark.parametrize("kind", ["outflow", "reflecting"])
+def test_boundary_restatement_equals_compiled_reference(kind):
+    """oracle/vlct_oracle_ic.c:vlct_oracle_boundary against the reference's own
+    EnzoBoundary::enforce (compiled unmodified into oracle/_ref): every axis and
+    side, cell- and face-centred fields, dual energy, two passive scalars"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    cfg = make_config(riemann="hlld", recon="plm", mhd=True, dual_energy=True,
+                      n_passive=2)
+    n, g, d = (7, 5, 6), (3, 3, 3), (0.1, 0.1, 0.1)
+    names = passive_names(cfg)
+    ref = oracle.CpuMethod(cfg, g, kind="ref")
+    for axis in range(3):
+        for side in (0, 1):
+            f = random_state(cfg, n, g, seed=37)
+            f_ref = copy_state(f)
+            oracle.boundary(oracle.numpy_block(f, n, g, d, names), axis, side, kind,
+                            n_passive=2)
+            oracle.boundary(oracle.numpy_block(f_ref, n, g, d, names), axis, side,
+                            kind, ref_method=ref)
+            eq = bit_equal(f, f_ref)
+            assert all(eq.values()), (axis, side, [k for k, v in eq.items() if not v])
+    ref.close()
+
+
 def test_inflow_boundary_follows_boundary_value():
     """"inflow" ghost fill against a direct numpy statement of
     BoundaryValue::enforce (Cello/problem_BoundaryValue.cpp:131-273): the g
