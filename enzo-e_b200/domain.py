@@ -13,6 +13,11 @@ the min-reduction of the timestep (src/Cello/control_stopping.cpp:96-142).
     block wraps onto itself on the device.
   * slabs are packed/unpacked by CUDA kernels (csrc: k_slab_copy) and moved
     with NCCL send/recv (torch.distributed P2P) over NVLink
+  * a non-periodic domain (`boundaries`: Cello's Boundary:list, in order):
+    bricks at a domain face have no neighbour across it; once all exchanges
+    are done every boundary object is enforced on the faces it applies to,
+    like Block::update_boundary_ (src/Cello/mesh_Block.cpp:1057-1077,
+    control_refresh.cpp:229-232)
   * dt = all_reduce(MIN) of the per-block timestep
   * `step()` overlaps the exchange along z (the last axis of the refresh) with
     the update: the slabs are packed and handed to NCCL, the interior part of
@@ -55,13 +60,53 @@ def proc_grid(world, slabs=False):
 
 
 class Domain:
-    def __init__(self, rank=0, world=1, grid=None):
+    def __init__(self, rank=0, world=1, grid=None, boundaries=None):
+        """boundaries: None = periodic domain; else the Boundary objects of the
+        problem in list order, each a dict
+          {"type": "outflow" | "reflecting" | "inflow",
+           "axis": 0 | 1 | 2 | None (all), "face": 0 | 1 | None (both),
+           "values": {field: constant}, "passive": (...)}   # inflow only
+        An axis that no entry applies to stays periodic."""
         self.rank, self.world = rank, world
         self.grid = tuple(grid) if grid else proc_grid(world)
         px, py, pz = self.grid
         assert px * py * pz == world
         # rank = (cz * py + cy) * px + cx
         self.coords = (rank % px, (rank // px) % py, rank // (px * py))
+        self.boundaries = [dict(b) for b in (boundaries or [])]
+        self.periodic = [True, True, True]
+        for b in self.boundaries:
+            if b["type"] not in ("outflow", "reflecting", "inflow"):
+                raise ValueError(f"unknown boundary type {b['type']!r}")
+            for axis in ([0, 1, 2] if b.get("axis") is None else [b["axis"]]):
+                self.periodic[axis] = False
+
+    def on_boundary(self, axis, side):
+        """does this brick touch the (non-periodic) domain face?"""
+        if self.periodic[axis]:
+            return False
+        return self.coords[axis] == (0 if side == 0 else self.grid[axis] - 1)
+
+    def apply_boundaries(self, method, block, boundary=None, boundary_inflow=None):
+        """Block::update_boundary_: every Boundary object in list order, each
+        over the faces (x lower, x upper, y lower, ...) it applies to and this
+        brick has on the domain boundary."""
+        boundary = boundary or method.boundary
+        boundary_inflow = boundary_inflow or method.boundary_inflow
+        for b in self.boundaries:
+            for axis in range(3):
+                if b.get("axis") is not None and b["axis"] != axis:
+                    continue
+                for side in (0, 1):
+                    if b.get("face") is not None and b["face"] != side:
+                        continue
+                    if not self.on_boundary(axis, side):
+                        continue
+                    if b["type"] == "inflow":
+                        boundary_inflow(block, axis, side, b["values"],
+                                        b.get("passive", ()))
+                    else:
+                        boundary(block, axis, side, b["type"])
 
     def neighbor(self, axis, direction):
         c = list(self.coords)
@@ -75,8 +120,9 @@ class Domain:
 
     # -- refresh ---------------------------------------------------------------
     def refresh(self, method, block, buffers=None, pack=None, unpack=None,
-                wrap=None, alloc=None, defer_z=False):
-        """Fill all ghost zones of `block` (periodic domain).
+                wrap=None, alloc=None, defer_z=False, boundary=None,
+                boundary_inflow=None):
+        """Fill all ghost zones of `block`.
 
         pack/unpack/wrap/alloc default to the CUDA kernels behind `method`;
         the gloo CPU tests pass host stand-ins to exercise the neighbour and
@@ -95,17 +141,24 @@ class Domain:
                                    device="cuda")
         if buffers is None:
             buffers = self.__dict__.setdefault("_buffers", {})
+        bc = (boundary, boundary_inflow)
         for axis in range(3):
             if self.grid[axis] == 1:
-                wrap(block, 1 << axis)
+                if self.periodic[axis]:
+                    wrap(block, 1 << axis)
                 continue
             key = axis
             if key not in buffers:
                 nbytes = method.halo_bytes(block, axis)
                 buffers[key] = [alloc(nbytes) for _ in range(4)]
             send_lo, send_hi, recv_lo, recv_hi = buffers[key]
-            pack(block, axis, 0, send_lo)
-            pack(block, axis, 1, send_hi)
+            # no neighbour across a non-periodic domain face
+            has_lo = not self.on_boundary(axis, 0)
+            has_hi = not self.on_boundary(axis, 1)
+            if has_lo:
+                pack(block, axis, 0, send_lo)
+            if has_hi:
+                pack(block, axis, 1, send_hi)
             lo, hi = self.neighbor(axis, -1), self.neighbor(axis, +1)
             # If the block's kernels run on torch's current stream (bench.py
             # does that), packs, NCCL and unpacks are stream-ordered and no
@@ -113,28 +166,50 @@ class Domain:
             same_stream = getattr(block, "stream_is_current", False)
             if send_lo.is_cuda and not same_stream:
                 method.synchronize()
-            ops = [dist.P2POp(dist.isend, send_lo, lo),
-                   dist.P2POp(dist.isend, send_hi, hi),
-                   dist.P2POp(dist.irecv, recv_hi, hi),
-                   dist.P2POp(dist.irecv, recv_lo, lo)]
-            reqs = dist.batch_isend_irecv(ops)
-            pending = (reqs, axis, recv_lo, recv_hi, unpack, same_stream)
+            ops = []
+            if has_lo:
+                ops.append(dist.P2POp(dist.isend, send_lo, lo))
+            if has_hi:
+                ops.append(dist.P2POp(dist.isend, send_hi, hi))
+                ops.append(dist.P2POp(dist.irecv, recv_hi, hi))
+            if has_lo:
+                ops.append(dist.P2POp(dist.irecv, recv_lo, lo))
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            pending = (reqs, axis, recv_lo if has_lo else None,
+                       recv_hi if has_hi else None, unpack, same_stream, bc)
             if defer_z and axis == 2:
                 # NCCL works on its own stream, ordered after the packs; the
-                # caller's stream only joins it in refresh_finish()
+                # caller's stream only joins it in refresh_finish(). What the
+                # interior part of the update reads of the x / y domain
+                # boundaries does not depend on the z ghosts: enforce them now
+                # (refresh_finish enforces everything again, in order, once the
+                # z ghosts are there)
+                if self.boundaries:
+                    self.apply_boundaries(method, block, *bc)
                 return pending
-            self.refresh_finish(method, block, pending)
+            self._finish_axis(method, block, pending)
+        if self.boundaries:
+            self.apply_boundaries(method, block, *bc)
         return None
 
-    def refresh_finish(self, method, block, pending):
-        """Wait for a deferred exchange and unpack its ghost slabs."""
-        reqs, axis, recv_lo, recv_hi, unpack, same_stream = pending
+    def _finish_axis(self, method, block, pending):
+        reqs, axis, recv_lo, recv_hi, unpack, same_stream, _ = pending
         for req in reqs:
             req.wait()
-        if recv_lo.is_cuda and not same_stream:
+        if not same_stream and any(
+                t is not None and t.is_cuda for t in (recv_lo, recv_hi)):
             torch.cuda.current_stream().synchronize()
-        unpack(block, axis, 0, recv_lo)
-        unpack(block, axis, 1, recv_hi)
+        if recv_lo is not None:
+            unpack(block, axis, 0, recv_lo)
+        if recv_hi is not None:
+            unpack(block, axis, 1, recv_hi)
+
+    def refresh_finish(self, method, block, pending):
+        """Wait for a deferred exchange, unpack its ghost slabs and enforce the
+        domain boundaries."""
+        self._finish_axis(method, block, pending)
+        if self.boundaries:
+            self.apply_boundaries(method, block, *pending[6])
 
     def step(self, method, block, dt, overlap=True):
         """refresh + compute of one cycle (dt: device-resident, already

@@ -433,6 +433,16 @@ def cloud_refresh(mhd, boundary, boundary_inflow):
     return refresh
 
 
+def cloud_boundary_list(mhd):
+    """the same Boundary:list in the form enzo_e_b200.domain.Domain takes"""
+    out = [dict(type="outflow", axis=0, face=1),
+           dict(type="inflow", axis=0, face=0, values=CLOUD_INFLOW),
+           dict(type="outflow", axis=1), dict(type="outflow", axis=2)]
+    if mhd:
+        out.append(dict(type="inflow", axis=0, face=0, values=CLOUD_INFLOW_B))
+    return out
+
+
 def slice_asym(grid, slice_ax, slice_ind, flip_across):
     """run_dual_energy_cloud_test.py:27-54; grid is indexed (x, y, z)"""
     if slice_ax == 'x':

@@ -82,6 +82,38 @@ class HostKernels:
                     a[self._slab(a, axis, g + cen, g)]
 
 
+    # -- domain boundaries (EnzoBoundary.cpp:164-283,352-466 /
+    #    problem_BoundaryValue.cpp:131-273; the GPU kernels are checked against
+    #    the oracle's restatement of the same rules in test_gpu_domain.py) ------
+    def boundary(self, blk, axis, side, kind):
+        n, g = blk.n[axis], blk.g[axis]
+        for name in FIELDS:
+            a = np.moveaxis(blk.fields[name], 2 - axis, 0)     # a view
+            cen = 1 if face_axis(name) == axis else 0
+            sign = -1.0 if (kind == "reflecting" and name in (
+                "velocity_" + "xyz"[axis], "bfield_" + "xyz"[axis],
+                "bfieldi_" + "xyz"[axis])) else 1.0
+            for ig in range(g):
+                if kind == "outflow":
+                    src = g if side == 0 else n + g - 1 + cen
+                    dst = g - ig - 1 if side == 0 else src + ig + 1
+                else:
+                    src = g + cen + ig if side == 0 else n + g - 1 - ig
+                    dst = g - ig - 1 if side == 0 else n + g + ig + cen
+                a[dst] = sign * a[src]
+
+    def boundary_inflow(self, blk, axis, side, values, passive=()):
+        g = blk.g[axis]
+        for name, val in values.items():
+            if name not in blk.fields:
+                continue
+            a = np.moveaxis(blk.fields[name], 2 - axis, 0)
+            if side == 0:
+                a[:g] = val
+            else:
+                a[a.shape[0] - g:] = val
+
+
 def global_value(name, ix, iy, iz, N):
     """a periodic integer-valued function of the GLOBAL index (faces share
     the index of the cell on their upper side)"""
@@ -204,3 +236,116 @@ def test_single_rank_refresh_wraps():
                 alloc=lambda nbytes: torch.empty(nbytes // 8, dtype=torch.float64))
     for name in FIELDS:
         assert np.array_equal(blk.fields[name], want.fields[name]), name
+
+
+# ---------------------------------------------------------------------------
+# non-periodic domains: no exchange across a domain face, then every Boundary
+# object in list order (Block::update_boundary_)
+# ---------------------------------------------------------------------------
+CLOUD_LIKE = [dict(type="outflow", axis=0, face=1),
+              dict(type="inflow", axis=0, face=0,
+                   values={"density": 0.5, "velocity_x": 2.0}),
+              dict(type="outflow", axis=1), dict(type="reflecting", axis=2),
+              dict(type="inflow", axis=0, face=0, values={"bfieldi_y": 0.0,
+                                                          "bfield_x": 0.0})]
+TUBE_X = [dict(type="outflow", axis=0)]          # periodic across the tube
+
+
+def expected_global(boundaries, n, g, grid):
+    """the same rules on ONE block that covers the whole domain"""
+    from enzo_e_b200.domain import Domain
+    N = tuple(n[a] * grid[a] for a in range(3))
+    blk = make_block((0, 0, 0), N, g, N, fill_ghosts=False)
+    k = HostKernels()
+    Domain(0, 1, boundaries=boundaries).refresh(
+        k, blk, pack=k.halo_pack, unpack=k.halo_unpack, wrap=k.wrap,
+        boundary=k.boundary, boundary_inflow=k.boundary_inflow,
+        alloc=lambda nbytes: torch.empty(nbytes // 8, dtype=torch.float64))
+    return blk
+
+
+def local_part(glob, coords, n, g):
+    """the levels a brick (ghost zones included) occupies in the global block"""
+    out = {}
+    for name, a in glob.fields.items():
+        fa = face_axis(name)
+        sl = tuple(slice(coords[2 - k] * n[2 - k],
+                         coords[2 - k] * n[2 - k] + n[2 - k] + 2 * g[2 - k]
+                         + (1 if fa == 2 - k else 0)) for k in range(3))
+        out[name] = a[sl]
+    return out
+
+
+def _worker_bc(rank, world, port, grid, which, defer, result_q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from enzo_e_b200.domain import Domain
+        boundaries = {"cloud": CLOUD_LIKE, "tube": TUBE_X}[which]
+        dom = Domain(rank, world, grid=grid, boundaries=boundaries)
+        n, g = (6, 5, 4), (3, 3, 3)
+        N = tuple(n[a] * grid[a] for a in range(3))
+        blk = make_block(dom.coords, n, g, N, fill_ghosts=False)
+        want = local_part(expected_global(boundaries, n, g, grid), dom.coords, n, g)
+        k = HostKernels()
+        kw = dict(pack=k.halo_pack, unpack=k.halo_unpack, wrap=k.wrap,
+                  boundary=k.boundary, boundary_inflow=k.boundary_inflow,
+                  alloc=lambda nbytes: torch.empty(nbytes // 8, dtype=torch.float64))
+        pending = dom.refresh(k, blk, defer_z=defer, **kw)
+        assert (pending is not None) == (defer and grid[2] > 1)
+        if pending is not None:
+            dom.refresh_finish(k, blk, pending)
+        bad = [name for name in FIELDS
+               if not np.array_equal(blk.fields[name], want[name])]
+        result_q.put((rank, bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("grid,which,defer", [
+    ((2, 1, 1), "cloud", False), ((1, 2, 1), "cloud", False),
+    ((1, 1, 2), "cloud", False), ((1, 1, 2), "cloud", True),
+    ((2, 1, 1), "tube", False), ((1, 1, 2), "tube", True)])
+def test_non_periodic_domain_two_ranks(grid, which, defer):
+    """two bricks of a domain with inflow / outflow / reflecting faces get the
+    ghost zones one block covering the whole domain gets"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_bc,
+                         args=(r, world, port, grid, which, defer, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad in results:
+        assert not bad, f"rank {rank}: ghost zones wrong in {bad}"
+
+
+def test_single_block_boundaries_follow_list_order():
+    """one brick: the refresh of a non-periodic domain = wrap of the periodic
+    axes, then every Boundary object in list order"""
+    n, g = (6, 5, 4), (3, 3, 3)
+    got = expected_global(CLOUD_LIKE, n, g, (1, 1, 1))
+    want = make_block((0, 0, 0), n, g, n, fill_ghosts=False)
+    k = HostKernels()
+    k.boundary(want, 0, 1, "outflow")
+    k.boundary_inflow(want, 0, 0, CLOUD_LIKE[1]["values"])
+    for side in (0, 1):
+        k.boundary(want, 1, side, "outflow")
+    for side in (0, 1):
+        k.boundary(want, 2, side, "reflecting")
+    k.boundary_inflow(want, 0, 0, CLOUD_LIKE[4]["values"])
+    for name in FIELDS:
+        assert np.array_equal(got.fields[name], want.fields[name]), name
+    # an axis without a boundary object stays periodic
+    got = expected_global(TUBE_X, n, g, (1, 1, 1))
+    a = got.fields["density"]
+    assert np.array_equal(a[:3], a[4:7]) and np.array_equal(a[:, :3], a[:, 5:8])
+    assert np.array_equal(a[:, :, 0], a[:, :, 3]) and np.array_equal(a[:, :, 2], a[:, :, 3])

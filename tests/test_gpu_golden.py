@@ -408,3 +408,37 @@ def test_dual_energy_cloud_symmetry_on_device(solver):
     eq = bit_equal(f2, f)
     eq.pop("pressure", None)
     assert all(eq.values()), {k: v for k, v in eq.items() if not v}
+
+
+@pytest.mark.parametrize("solver", ["hllc", "hlld"])
+def test_cloud_through_the_domain_driver(solver):
+    """the cloud run with the refresh left to the unigrid driver (Domain with the
+    problem's Boundary:list): the same bits as the oracle's run"""
+    from enzo_e_b200 import problems as DP
+    from enzo_e_b200.domain import Domain
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = P.cloud_config(solver)
+    mhd = cfg.mhd_choice == 1
+    n, g, d = (32, 32, 32), (3, 3, 3), (0.125,) * 3
+    dev = DP.cloud(n, g, P.CLOUD_LOWER, d, device="cuda", mhd=mhd, **P.CLOUD)
+    method = EnzoMethodMHDVlct(config=cfg)
+    block = Block(dev, n, g, d)
+    dom = Domain(0, 1, boundaries=P.cloud_boundary_list(mhd))
+    assert dom.periodic == [False, False, False]
+
+    class Run:
+        def timestep(self, _b):
+            return method.timestep(block)
+
+        def compute(self, _b, dt):
+            method.compute(block, dt)
+    dts = P.evolve(Run(), None, P.CLOUD_T_STOP, lambda _b: dom.refresh(method, block),
+                   dump_times=(P.CLOUD_T_STOP,))
+    method.synchronize()
+    f = {k: v.cpu().numpy() for k, v in dev.items()}
+    method.close()
+    cfg2, f2, g2, dts2 = P.run_cloud(solver)
+    assert dts == dts2
+    eq = bit_equal(f2, f)
+    eq.pop("pressure", None)
+    assert all(eq.values()), {k: v for k, v in eq.items() if not v}
