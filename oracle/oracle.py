@@ -217,9 +217,24 @@ def _ic_lib():
 
 
 def ic_inclined_wave(blk, lower, gamma, wave_type, alpha, beta, amplitude=1e-6,
-                     lam=1.0, positive_vel=True, parallel_vel=None):
-    """EnzoInitialInclinedWave on a host block (fills ghost zones too)."""
+                     lam=1.0, positive_vel=True, parallel_vel=None,
+                     ref_method=None):
+    """EnzoInitialInclinedWave on a host block (fills ghost zones too).
+    ref_method: a CpuMethod(kind="ref") whose field list (and gamma) the block
+    matches -- then the reference's own compiled initialiser fills the block."""
     lo = (C.c_double * 3)(*lower)
+    if ref_method is not None:
+        assert ref_method.kind == "ref" and parallel_vel is None
+        fn = ref_method._lib.vlct_ref_ic_inclined_wave
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.POINTER(C.c_double),
+                       C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                       C.c_int]
+        rc = fn(ref_method._h, C.byref(blk), lo, wave_type.encode(), alpha, beta,
+                amplitude, lam, 1 if positive_vel else 0)
+        if rc != 0:
+            raise RuntimeError(f"vlct_ref_ic_inclined_wave failed ({rc})")
+        return
     pv = _DBL_MIN if parallel_vel is None else float(parallel_vel)
     rc = _ic_lib().vlct_ic_inclined_wave(
         C.byref(blk), lo, gamma, wave_type.encode(), alpha, beta, amplitude,
@@ -229,8 +244,20 @@ def ic_inclined_wave(blk, lower, gamma, wave_type, alpha, beta, amplitude=1e-6,
 
 
 def ic_shock_tube(blk, lower, gamma, setup, aligned_ax=0, axis_velocity=0.0,
-                  trans_velocity=0.0, flipped=False):
+                  trans_velocity=0.0, flipped=False, ref_method=None):
+    """EnzoInitialShockTube on a host block; ref_method as in ic_inclined_wave."""
     lo = (C.c_double * 3)(*lower)
+    if ref_method is not None:
+        assert ref_method.kind == "ref"
+        fn = ref_method._lib.vlct_ref_ic_shock_tube
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.POINTER(C.c_double),
+                       C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int]
+        rc = fn(ref_method._h, C.byref(blk), lo, setup.encode(), aligned_ax,
+                axis_velocity, trans_velocity, 1 if flipped else 0)
+        if rc != 0:
+            raise RuntimeError(f"vlct_ref_ic_shock_tube failed ({rc})")
+        return
     rc = _ic_lib().vlct_ic_shock_tube(
         C.byref(blk), lo, gamma, setup.encode(), aligned_ax, axis_velocity,
         trans_velocity, 1 if flipped else 0)

@@ -162,6 +162,13 @@ public:
   { descr_->centering(id, cx, cy, cz); }
   int precision(int id) const { return descr_->precision(id); }
   int field_count() const { return descr_->field_count(); }
+  /// src/Cello/data_FieldData.cpp:254-264
+  void cell_width(double xm, double xp, double* hx, double ym = 0, double yp = 0,
+                  double* hy = 0, double zm = 0, double zp = 0, double* hz = 0) const {
+    if (hx) *hx = (xp - xm) / data_->nx;
+    if (hy) *hy = (yp - ym) / data_->ny;
+    if (hz) *hz = (zp - zm) / data_->nz;
+  }
   bool is_temporary(int) const { return false; }   // only permanent fields here
   char* values(int id) { return reinterpret_cast<char*>(data_->ptrs.at(id)); }
   void size(int* nx, int* ny, int* nz) const
@@ -459,6 +466,25 @@ protected:
   axis_enum axis_;
   face_enum face_;
   std::shared_ptr<Mask> mask_;
+};
+
+/// Inert stand-ins for the parameter-file machinery (flex / bison generated in
+/// the reference): no parameter exists, so EnzoInitialBCenter holds no Value
+/// expressions and only its static array helpers do any work here.
+enum parameter_type_shim { parameter_unknown, parameter_list };
+class Parameters {
+public:
+  void group_set(int, const std::string&) {}
+  int type(const std::string&) const { return parameter_unknown; }
+  int list_length(const std::string&) const { return 0; }
+  void pup(PUP::er&) {}
+};
+class Value {
+public:
+  Value(Parameters*, const std::string&) {}
+  template <class T>
+  void evaluate(T*, double, int, int, double*, int, int, double*, int, int,
+                double*) const {}
 };
 
 class Hierarchy;

@@ -385,6 +385,52 @@ int vlct_ref_ic_cloud(void* handle, const vlct_block* b, const double* lower,
   return 0;
 }
 
+/// The reference's own EnzoInitialShockTube::enforce_block
+/// (src/Enzo/initial/EnzoInitialShockTube.cpp, compiled unmodified); gamma comes
+/// from the handle's fluid properties like in the reference.
+int vlct_ref_ic_shock_tube(void* handle, const vlct_block* b, const double* lower,
+                           const char* setup, int aligned_ax, double axis_velocity,
+                           double trans_velocity, int flipped)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->ctx->descr);
+  bind_block(h, blk, b);
+  for (int a = 0; a < 3; a++) blk.data()->xm[a] = lower[a];
+  ParameterGroup pg;
+  pg.set("setup_name", setup);
+  pg.set("aligned_ax", aligned_ax == 0 ? "x" : (aligned_ax == 1 ? "y" : "z"));
+  pg.set("axis_velocity", fmt_double(axis_velocity));
+  pg.set("transverse_velocity", fmt_double(trans_velocity));
+  pg.set("flip_initialize", flipped ? "true" : "false");
+  EnzoInitialShockTube initial(0, 0.0, pg);
+  initial.enforce_block(&blk, nullptr);
+  return 0;
+}
+
+/// The reference's own EnzoInitialInclinedWave::enforce_block
+/// (src/Enzo/initial/EnzoInitialInclinedWave.cpp, compiled unmodified).
+int vlct_ref_ic_inclined_wave(void* handle, const vlct_block* b, const double* lower,
+                              const char* wave_type, double alpha, double beta,
+                              double amplitude, double lambda, int positive_vel)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  EnzoBlock blk(&h->ctx->descr);
+  bind_block(h, blk, b);
+  for (int a = 0; a < 3; a++) blk.data()->xm[a] = lower[a];
+  ParameterGroup pg;
+  pg.set("wave_type", wave_type);
+  pg.set("alpha", fmt_double(alpha));
+  pg.set("beta", fmt_double(beta));
+  pg.set("amplitude", fmt_double(amplitude));
+  pg.set("lambda", fmt_double(lambda));
+  pg.set("positive_vel", positive_vel ? "true" : "false");
+  EnzoInitialInclinedWave initial(0, 0.0, pg);
+  initial.enforce_block(&blk, nullptr);
+  return 0;
+}
+
 /// The reference's own EnzoBoundary::enforce (src/Enzo/enzo-core/EnzoBoundary.cpp,
 /// compiled unmodified) for one face of the domain, on every field of the
 /// block: type 0 = "outflow", 1 = "reflecting" (the numbering of vlct.h).

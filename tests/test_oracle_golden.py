@@ -258,6 +258,55 @@ def test_cloud_ic_restatement_equals_compiled_reference(case):
     assert np.unique(f["density"]).size > 10
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_shock_tube_ic_restatement_equals_compiled_reference(axis):
+    """vlct_ic_shock_tube against the reference's own EnzoInitialShockTube (+ the
+    static helpers of EnzoInitialBCenter), compiled unmodified into oracle/_ref:
+    Ryu-Jones 2a, Sod in the Mach-10 frame, and its flipped version"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    for setup in ("rj2a", "sod", "sod_flipped"):
+        lower = [0.0, 0.0, 0.0]
+        if setup == "rj2a":
+            cfg, f, blk, n, g, d, _ = P.rj2a_setup(axis)
+            kw = dict(setup="rj2a", aligned_ax=axis)
+        else:
+            flipped = setup.endswith("flipped")
+            cfg, f, blk, n, g, d, _ = P.sod_de_setup(axis, flipped)
+            if flipped:
+                lower[axis] = -P.SOD_OFFSET
+            kw = dict(setup="sod", aligned_ax=axis,
+                      axis_velocity=P.SOD_BKG_VELOCITY, flipped=flipped)
+        f_ref = P.alloc_fields(cfg, n, g)
+        ref = oracle.CpuMethod(cfg, g, kind="ref")
+        oracle.ic_shock_tube(oracle.numpy_block(f_ref, n, g, d), tuple(lower),
+                             cfg.gamma, ref_method=ref, **kw)
+        ref.close()
+        eq = bit_equal(f, f_ref)
+        assert all(eq.values()), (setup, [k for k, v in eq.items() if not v])
+
+
+@pytest.mark.parametrize("name,mhd", [(n, True) for n in sorted(P.MHD_WAVES)]
+                         + [(n, False) for n in sorted(P.HD_WAVES)])
+def test_inclined_wave_ic_restatement_equals_compiled_reference(name, mhd):
+    """vlct_ic_inclined_wave against the reference's own EnzoInitialInclinedWave
+    (rotation, eigenvectors, vector potential -> face B -> centred B, total
+    energy; same libm), bit for bit, both propagation directions"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available")
+    wave_type = (P.MHD_WAVES if mhd else P.HD_WAVES)[name][0]
+    for positive_vel in (True, False):
+        cfg, f, blk, n, g, d, _ = P.linear_wave_setup(name, 16, mhd, positive_vel)
+        f_ref = P.alloc_fields(cfg, n, g)
+        ref = oracle.CpuMethod(cfg, g, kind="ref")
+        oracle.ic_inclined_wave(oracle.numpy_block(f_ref, n, g, d), (0.0, 0.0, 0.0),
+                                cfg.gamma, wave_type, P.ALPHA, P.BETA, 1e-6, 1.0,
+                                positive_vel, ref_method=ref)
+        ref.close()
+        eq = bit_equal(f, f_ref)
+        assert all(eq.values()), (positive_vel, [k for k, v in eq.items() if not v])
+
+
 def test_compiled_reference_reproduces_rj2a_golden():
     """the reference's own compiled sources on the same shock tube"""
     if not oracle.have_ref():
