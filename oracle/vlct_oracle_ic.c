@@ -2,8 +2,10 @@
  *
  * CPU restatements of the reference's problem initialisers that the vlct
  * answer tests use, so that the golden L1 norms of input/vlct/run_*_test.py
- * can be reproduced on raw arrays (the reference's Initial classes need the
- * Block/Value machinery and cannot be compiled stand-alone):
+ * can be reproduced on raw arrays -- also on the GPU box, where the reference
+ * tree does not exist. Each is pinned bit for bit against the reference's own
+ * Initial class compiled into oracle/_ref (tests/test_oracle_golden.py:
+ * test_*_restatement_equals_compiled_reference):
  *
  *   vlct_ic_inclined_wave   initial/EnzoInitialInclinedWave.cpp
  *   vlct_ic_shock_tube      initial/EnzoInitialShockTube.cpp
