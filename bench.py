@@ -4,9 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            (our CUDA path)
     python bench.py --impl reference --gpus N --steps K ...  (reference CPU path)
 
-Workload (config.workload): BASELINE.json configs[2], the 3-D Orszag-Tang
-vortex on 512^3 cells per GPU, MHD VL+CT with PLM (theta 1.5) + HLLD + CT,
-fp64, one periodic brick per GPU (weak scaling: the global grid grows with N).
+Headline workload (config.workload): BASELINE.json configs[2], the 3-D
+Orszag-Tang vortex on 512^3 cells per GPU, MHD VL+CT with PLM (theta 1.5) +
+HLLD + CT, fp64, one periodic brick per GPU (weak scaling: the global grid
+grows with N; N = 8 is a 2x2x2 arrangement = global 1024^3 with x, y and z
+ghost exchanges). `--workload` selects another BASELINE configuration as the
+headline; by default the other ones are ALSO measured (short runs, same
+process) and reported under "workloads":
+
+    turbulence  configs[3]  decaying MHD turbulence, 512^3 per GPU (N = 8:
+                            1024^3 as 2x2x2 bricks), all HLLD regions populated
+                            along every axis
+    ot_s4       configs[4]  the headline problem + 4 passive scalars
+    sod256      configs[1]  3-D Sod, hydro, PLM + HLLC + dual energy, 256^3 (N = 1)
+    fastwave64  configs[0]  fast magnetosonic linear wave, 128x64x64 (N = 1)
 
 A "step" is one full simulation cycle of the path on one block per GPU:
     timestep() -> min over ranks -> ghost refresh (device wrap / NCCL exchange)
@@ -14,8 +25,10 @@ A "step" is one full simulation cycle of the path on one block per GPU:
 metric = cell-updates/s = active cells of all ranks * steps / seconds, timed on
 the device with CUDA events, max over ranks.
 
-Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the roofline
-accounting (algorithmic bytes per kernel launch and per cell-update).
+Prints ONE JSON line (rank 0). `roofline` is SURVEY 8(d)'s step figure
+(value x algorithmic bytes per cell-update / measured HBM peak); the per-kernel
+numbers are under `roofline_families`, the FP64-issue roofline under
+`roofline_fp64`. See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -31,8 +44,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cell-updates/sec (fp64 VL+CT MHD)"
 UNIT = "cell-updates/s"
-B_ALG_STEP = 416.0        # compulsory bytes per MHD cell-update
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+# FP64 issue rate of a B200: one DP warp-instruction per 2 cycles per SM
+# sub-partition (scripts/microbench/dp_pipe.cu): 148 x 4 x 0.5 x 1.965 GHz
+FP64_WARP_INST_PER_S = 148 * 4 * 0.5 * 1.965e9
 
 
 def measured_peaks():
@@ -82,7 +97,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
         for line in self.lines:
@@ -92,6 +107,7 @@ class ClockSampler:
             try:
                 sm.append(float(parts[1]))
                 smax.append(float(parts[2]))
+                power.append(float(parts[3]))
             except ValueError:
                 continue
             for name, val in zip(names, parts[4:8]):
@@ -99,11 +115,12 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
+                "power_w_median": statistics.median(power) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------
-# workload
+# workloads
 # --------------------------------------------------------------------------
 PARAMS = {
     "Method:mhd_vlct:mhd_choice": "constrained_transport",
@@ -116,19 +133,103 @@ PARAMS = {
     "Physics:fluid_props:floors:density": 1e-200,
     "Physics:fluid_props:floors:pressure": 1e-200,
 }
+HYDRO_DE = {
+    "Method:mhd_vlct:mhd_choice": "no_bfield",
+    "Method:mhd_vlct:riemann_solver": "hllc",
+    "Method:mhd_vlct:reconstruct_method": "plm",
+    "Method:mhd_vlct:theta_limiter": 1.5,
+    "Method:mhd_vlct:time_scheme": "vl",
+    "Method:mhd_vlct:courant": 0.3,
+    "Physics:fluid_props:eos:gamma": 1.4,
+    "Physics:fluid_props:dual_energy:type": "modern",
+    "Physics:fluid_props:dual_energy:eta": 1e-3,
+    "Physics:fluid_props:floors:density": 1e-200,
+    "Physics:fluid_props:floors:pressure": 1e-200,
+}
+LINWAVE = dict(PARAMS, **{"Method:mhd_vlct:theta_limiter": 2.0,
+                          "Method:mhd_vlct:courant": 0.4,
+                          "Physics:fluid_props:eos:gamma": 1.6666666666666667})
 GHOST = (3, 3, 3)
 
+# name -> description of a BASELINE configuration. bytes = SURVEY 8(d)'s
+# ALGORITHMIC bytes per cell-update: MHD 416 B (+40 B per passive scalar),
+# hydro + dual energy 240 B. dp_inst = fp64 warp-instructions per 32
+# cell-updates (ncu opmix of the shipped kernels, profiles/; data dependent).
+WORKLOADS = {
+    "ot": dict(config="configs[2]", title="Orszag-Tang vortex", params=PARAMS,
+               n_passive=0, bytes=416.0, multi_gpu=True,
+               solver="MHD VL+CT: PLM(theta=1.5) + HLLD + CT, periodic"),
+    "turbulence": dict(config="configs[3]", title="decaying MHD turbulence "
+                       "(solenoidal modes |k|<=3, seed 20240517, rms Mach 0.5, beta 2)",
+                       params=PARAMS, n_passive=0, bytes=416.0, multi_gpu=True,
+                       solver="MHD VL+CT: PLM(theta=1.5) + HLLD + CT, periodic"),
+    "ot_s4": dict(config="configs[4]", title="Orszag-Tang vortex + 4 passive scalars",
+                  params=PARAMS, n_passive=4, bytes=416.0 + 4 * 40.0, multi_gpu=True,
+                  solver="MHD VL+CT: PLM(theta=1.5) + HLLD + CT + 4 scalars, periodic"),
+    "sod256": dict(config="configs[1]", title="3-D Sod problem", params=HYDRO_DE,
+                   n_passive=0, bytes=240.0, multi_gpu=False, size=256,
+                   solver="hydro VL: PLM(theta=1.5) + HLLC + dual energy, "
+                          "outflow along x, periodic across"),
+    "fastwave64": dict(config="configs[0]", title="fast magnetosonic linear wave "
+                       "(input/vlct/MHD_linear_wave, N = 64)", params=LINWAVE,
+                       n_passive=0, bytes=416.0, multi_gpu=False, size=64,
+                       solver="MHD VL+CT: PLM(theta=2) + HLLD + CT, periodic"),
+}
 
-def workload_config(size, world, grid):
-    return {"workload": f"Orszag-Tang vortex, {size}^3 cells per GPU "
-                        f"(global {size * grid[0]}x{size * grid[1]}x{size * grid[2]}), "
-                        "MHD VL+CT: PLM(theta=1.5) + HLLD + CT, periodic",
-            "cells_per_gpu": size ** 3, "ghost_depth": 3,
-            "riemann_solver": "hlld", "reconstruct_method": "plm",
-            "courant": 0.3, "gamma": 5.0 / 3.0,
-            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} bricks",
+
+def local_shape(name, size):
+    if name == "fastwave64":
+        return (2 * size, size, size)
+    return (size, size, size)
+
+
+def workload_config(name, size, world, grid, layout):
+    w = WORKLOADS[name]
+    n = local_shape(name, size)
+    glob = tuple(n[a] * grid[a] for a in range(3))
+    return {"workload": f"{w['title']}, {n[0]}x{n[1]}x{n[2]} cells per GPU "
+                        f"(global {glob[0]}x{glob[1]}x{glob[2]}), {w['solver']} "
+                        f"[BASELINE {w['config']}]",
+            "name": name, "cells_per_gpu": n[0] * n[1] * n[2], "ghost_depth": 3,
+            "riemann_solver": w["params"]["Method:mhd_vlct:riemann_solver"],
+            "reconstruct_method": "plm", "n_passive": w["n_passive"],
+            "courant": w["params"]["Method:mhd_vlct:courant"],
+            "gamma": w["params"]["Physics:fluid_props:eos:gamma"],
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} {layout}",
+            "algorithmic_bytes_per_cell_update": w["bytes"],
             "step": "timestep + dt min-reduce + ghost refresh + compute (dt device-resident: vlct_timestep_dev / vlct_compute_dev; with a z split the z ghost exchange overlaps the interior update)",
-            "l2_policy": "inputs (>=1.1 GB per field) exceed the 126 MB L2"}
+            "l2_policy": "inputs (>=1.1 GB per field at 512^3, 143 MB at 256^3) exceed the 126 MB L2"
+                         if n[0] * n[1] * n[2] >= 256 ** 3 else
+                         "L2 flushed between timed steps (a 256 MB buffer is rewritten)"}
+
+
+def make_fields(name, n_local, lower, width, global_n, dev):
+    from enzo_e_b200 import problems
+    w = WORKLOADS[name]
+    if name in ("ot", "ot_s4"):
+        return problems.orszag_tang(n_local, GHOST, lower, width, device=dev,
+                                    n_passive=w["n_passive"])
+    if name == "turbulence":
+        return problems.turbulence(n_local, GHOST, lower, width, global_n, device=dev)
+    if name == "sod256":
+        return problems.hydro_sod(n_local, GHOST, lower, width, device=dev, gamma=1.4)
+    if name == "fastwave64":
+        return problems.inclined_wave(n_local, GHOST, lower, width, "fast",
+                                      0.7297276562269663, 1.1071487177940904,
+                                      device=dev, gamma=1.6666666666666667)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def workload_widths(name, n_local, grid):
+    if name == "fastwave64":      # domain 3 x 1.5 x 1.5
+        return (3.0 / n_local[0], 1.5 / n_local[1], 1.5 / n_local[2])
+    return tuple(1.0 / (n_local[a] * grid[a]) for a in range(3))
+
+
+def workload_boundaries(name):
+    if name == "sod256":
+        return [{"type": "outflow", "axis": 0}]
+    return None
 
 
 def cpu_threads():
@@ -138,108 +239,159 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def run_cpu_sample(seconds_target=12.0, block=48, threads=None, steps_cap=200):
-    """Time the reference CPU path (oracle/_ref when present, else the oracle
-    port) on `threads` host threads, one `block`^3 brick of the Orszag-Tang
-    workload per thread, for about `seconds_target` seconds."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import torch
-    import oracle
-    from enzo_e_b200 import abi, problems
+class CpuArm:
+    """The reference CPU path (oracle/_ref = the reference's own sources when
+    present, else the oracle port) on `threads` host threads, one `block`^3
+    brick of the workload per thread (the reference's natural unit: one Cello
+    block per compute() call; 64^3 as BASELINE.md section 3 states)."""
 
-    threads = threads or cpu_threads()
-    kind = "ref" if oracle.have_ref() else "oracle"
-    if kind == "oracle" and not oracle.have_oracle():
-        oracle.build("oracle")
-    # same parameters as PARAMS, set directly on the struct so that the CPU
-    # arm never loads the CUDA library
-    cfg = abi.default_config()
-    cfg.mhd_choice = abi.MHD_CHOICE["constrained_transport"]
-    cfg.riemann_solver = abi.RIEMANN["hlld"]
-    cfg.reconstruct_method = abi.RECON["plm"]
-    cfg.theta_limiter = 1.5
-    cfg.courant = 0.3
-    cfg.gamma = 5.0 / 3.0
-    cfg.density_floor = cfg.pressure_floor = 1e-200
-    n, g = (block, block, block), GHOST
-    width = (1.0 / 512,) * 3
-    workers = []
-    for t in range(threads):
-        lower = ((t % 8) * block * width[0], ((t // 8) % 8) * block * width[1],
-                 (t // 64) * block * width[2])
-        f = {k: v.numpy().copy() for k, v in problems.orszag_tang(
-            n, g, lower, width, device="cpu").items()}
-        blk = oracle.numpy_block(f, n, g, width)
-        workers.append((oracle.CpuMethod(cfg, g, kind=kind), blk, f))
+    def __init__(self, name="ot", block=64, threads=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        from enzo_e_b200 import abi
+        self.oracle = oracle
+        self.threads = threads or cpu_threads()
+        self.block = block
+        self.kind = "ref" if oracle.have_ref() else "oracle"
+        if self.kind == "oracle" and not oracle.have_oracle():
+            oracle.build("oracle")
+        w = WORKLOADS[name]
+        prm = w["params"]
+        # same parameters as the GPU arm, set directly on the struct so that
+        # the CPU arm never loads the CUDA library
+        cfg = abi.default_config()
+        cfg.mhd_choice = abi.MHD_CHOICE[prm["Method:mhd_vlct:mhd_choice"]]
+        cfg.riemann_solver = abi.RIEMANN[prm["Method:mhd_vlct:riemann_solver"]]
+        cfg.reconstruct_method = abi.RECON["plm"]
+        cfg.theta_limiter = prm["Method:mhd_vlct:theta_limiter"]
+        cfg.courant = prm["Method:mhd_vlct:courant"]
+        cfg.gamma = prm["Physics:fluid_props:eos:gamma"]
+        cfg.density_floor = cfg.pressure_floor = 1e-200
+        if "Physics:fluid_props:dual_energy:type" in prm:
+            cfg.dual_energy = 1
+            cfg.dual_energy_eta = prm["Physics:fluid_props:dual_energy:eta"]
+        cfg.n_passive = w["n_passive"]
+        self.n_passive = w["n_passive"]
+        n = (block, block, block)
+        # the bricks tile a corner of the 512^3 problem (cell width 1/512)
+        size = 512 if w.get("size") is None else w["size"]
+        width = (1.0 / size,) * 3
+        per_axis = max(1, size // block)
+        passive = tuple(f"passive_{k}" for k in range(w["n_passive"]))
+        self.workers = []
+        for t in range(self.threads):
+            c = (t % per_axis, (t // per_axis) % per_axis, (t // per_axis ** 2) % per_axis)
+            lower = tuple(c[a] * block * width[a] for a in range(3))
+            f = {k: v.numpy().copy() for k, v in make_fields(
+                name if name != "fastwave64" else "ot", n, lower, width,
+                (size,) * 3, "cpu").items()}
+            blk = oracle.numpy_block(f, n, GHOST, width, passive)
+            self.workers.append((oracle.CpuMethod(cfg, GHOST, kind=self.kind), blk, f))
 
-    def one_step(w):
+    def one_step(self, w):
         m, blk, _ = w
         dt = m.timestep(blk)
-        oracle.refresh_periodic(blk, 0)
+        self.oracle.refresh_periodic(blk, self.n_passive)
         m.compute(blk, dt)
 
-    # calibrate with one step on one thread
-    t0 = time.perf_counter()
-    one_step(workers[0])
-    per_step = time.perf_counter() - t0
-    nsteps = max(2, min(steps_cap, int(seconds_target / max(per_step, 1e-6))))
+    def sample(self, nsteps, threads=None):
+        """`nsteps` full cycles (timestep + refresh + compute) of every brick of
+        the first `threads` workers, all at once; returns (cell-updates/s, s)"""
+        workers = self.workers[:threads or self.threads]
 
-    def loop(w):
-        for _ in range(nsteps):
-            one_step(w)
+        def loop(w):
+            for _ in range(nsteps):
+                self.one_step(w)
 
-    ths = [threading.Thread(target=loop, args=(w,)) for w in workers]
-    t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
-    elapsed = time.perf_counter() - t0
-    for m, _, _ in workers:
-        m.close()
-    cells = threads * block ** 3 * nsteps
-    return {"value": cells / elapsed, "unit": UNIT, "cores": threads,
-            "kind": "reference" if kind == "ref" else "port",
-            "sample": f"{threads} threads x one {block}^3 brick of the "
-                      f"Orszag-Tang workload x {nsteps} full steps "
-                      f"(timestep+refresh+compute), {elapsed:.1f} s",
-            "seconds": elapsed, "steps": nsteps}
+        ths = [threading.Thread(target=loop, args=(w,)) for w in workers]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        elapsed = time.perf_counter() - t0
+        return len(workers) * self.block ** 3 * nsteps / elapsed, elapsed
+
+    def calibrate(self, seconds):
+        """steps per sample so that one all-thread sample takes ~`seconds`"""
+        _, one = self.sample(1)
+        return max(1, min(200, int(seconds / max(one, 1e-6))))
+
+    def close(self):
+        for m, _, _ in self.workers:
+            m.close()
+
+
+def run_cpu_baseline(name, seconds_target=12.0, block=64):
+    """the bench line's `cpu_baseline`: one bounded all-core sample (+ a
+    single-core one) of the reference CPU path on the headline workload"""
+    arm = CpuArm(name, block=block)
+    nsteps = arm.calibrate(seconds_target * 0.75)
+    value, elapsed = arm.sample(nsteps)
+    one_core, one_elapsed = arm.sample(max(1, nsteps // 4), threads=1)
+    out = {"value": value, "unit": UNIT, "cores": arm.threads,
+           "kind": "reference" if arm.kind == "ref" else "port",
+           "sample": f"{arm.threads} threads x one {block}^3 brick of the "
+                     f"workload x {nsteps} full cycles (timestep+refresh+compute), "
+                     f"{elapsed:.1f} s",
+           "single_core_value": one_core,
+           "single_core_sample": f"1 thread x one {block}^3 brick x "
+                                 f"{max(1, nsteps // 4)} cycles, {one_elapsed:.1f} s"}
+    arm.close()
+    return out
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path
+    (oracle/_ref) on all host cores. A "step" of this arm is one bounded
+    sample: every thread advances its own 64^3 brick of the workload by a fixed
+    number of cycles; value = cell-updates of the timed samples / their wall
+    time, so steps x ms_per_step is the time this run really spent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    name = args.workload
     grid = _grid(args.gpus, args.layout)
     t_all = time.perf_counter()
-    samples = []
+    arm = CpuArm(name, block=args.cpu_block)
+    steps = max(5, args.steps)            # median of >= 5 samples
+    per = max(1.0, min(12.0, 100.0 / (steps + args.warmup + 2)))
+    cycles = arm.calibrate(per)
     for _ in range(args.warmup):
-        run_cpu_sample(seconds_target=1.0, block=args.cpu_block)
-    per = max(2.0, min(20.0, 150.0 / max(1, args.steps)))
-    for _ in range(args.steps):
-        samples.append(run_cpu_sample(seconds_target=per, block=args.cpu_block))
-    value = statistics.median(s["value"] for s in samples)
-    cells_per_step = args.size ** 3 * args.gpus
-    best = samples[0]
+        arm.sample(max(1, cycles // 2))
+    samples = [arm.sample(cycles) for _ in range(steps)]
+    single = [arm.sample(max(1, cycles // 2), threads=1) for _ in range(5)]
+    arm.close()
+    value = statistics.median(v for v, _ in samples)
+    ms = 1e3 * statistics.median(t for _, t in samples)
+    one_core = statistics.median(v for v, _ in single)
+    size = WORKLOADS[name].get("size", args.size)
+    n = local_shape(name, size)
+    cells_per_step = n[0] * n[1] * n[2] * args.gpus
+    sample = (f"{arm.threads} threads x one {args.cpu_block}^3 brick of the workload "
+              f"x {cycles} full cycles per sample; median of {steps} samples")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * cells_per_step / value,
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.size, args.gpus, grid),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": best["cores"],
-                             "kind": best["kind"], "sample": best["sample"]},
+            "config": workload_config(name, size, args.gpus, grid, args.layout),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads,
+                             "kind": "reference" if arm.kind == "ref" else "port",
+                             "sample": sample, "single_core_value": one_core,
+                             "all_core_samples": [v for v, _ in samples],
+                             "single_core_samples": [v for v, _ in single]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "ms_per_step = time the CPU path would need for one step of "
-                    "the full workload at the sampled per-cell rate",
+            "step_definition": "one bounded sample (see cpu_baseline.sample); "
+                               "ms_per_step is its measured wall time",
+            "full_workload_ms_per_step_extrapolated": 1e3 * cells_per_step / value,
             "wall_s": time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
 
 
-def _grid(world, layout="slabs"):
+def _grid(world, layout="bricks"):
     from enzo_e_b200.domain import proc_grid
     return proc_grid(world, slabs=(layout == "slabs"))
 
@@ -291,12 +443,81 @@ def family_rooflines(report, m, hbm_gbs):
     return fam
 
 
+class Setup:
+    """one rank's block of a workload + the Method driving it"""
+
+    def __init__(self, name, size, domain_args, dev, layout):
+        import torch
+        from enzo_e_b200.domain import Domain
+        from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+        rank, world = domain_args
+        w = WORKLOADS[name]
+        self.name, self.w = name, w
+        self.domain = Domain(rank, world, grid=_grid(world, layout),
+                             boundaries=workload_boundaries(name))
+        grid = self.domain.grid
+        self.n_local = local_shape(name, size)
+        self.width = workload_widths(name, self.n_local, grid)
+        lower = self.domain.lower_corner(self.n_local, self.width)
+        global_n = tuple(self.n_local[a] * grid[a] for a in range(3))
+        self.passive = tuple(f"passive_{k}" for k in range(w["n_passive"]))
+        self.fields = make_fields(name, self.n_local, lower, self.width, global_n, dev)
+        self.method = EnzoMethodMHDVlct(w["params"], n_passive=w["n_passive"])
+        self.block = Block(self.fields, self.n_local, GHOST, self.width,
+                           passive=self.passive)   # torch's current stream
+        assert self.block.stream_is_current
+        self.dt_dev = torch.empty(1, dtype=torch.float64, device=dev)
+        self.dev = dev
+        self.cells = self.n_local[0] * self.n_local[1] * self.n_local[2]
+        # small blocks fit the L2: flush it between timed steps
+        self.flush = None
+        if self.cells < 256 ** 3:
+            self.flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device=dev)
+
+    def step(self, overlap=True):
+        # dt stays on the device (vlct_timestep_dev / vlct_compute_dev): the
+        # cycles queue back to back, nothing waits for the host
+        if self.flush is not None:
+            self.flush.add_(1.0)
+        dt = self.method.timestep_dev(self.block, out=self.dt_dev)
+        dt = self.domain.global_dt(dt, self.dev)
+        # refresh + compute; with a z split the z exchange runs under the
+        # interior part of the update (Domain.step)
+        self.domain.step(self.method, self.block, dt, overlap=overlap)
+        return dt
+
+    def close(self):
+        self.method.close()
+        self.fields.clear()
+        self.block = None
+
+
+def timed_steps(setup, stream, steps, warmup, sync_all, overlap=True):
+    import torch
+    for _ in range(warmup):
+        setup.step(overlap)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush_ms = 0.0
+    if setup.flush is not None:      # cost of the L2 flush alone, subtracted below
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(steps):
+            setup.flush.add_(1.0)
+        f1.record(stream)
+        sync_all()
+        flush_ms = f0.elapsed_time(f1)
+    e0.record(stream)
+    for _ in range(steps):
+        dt = setup.step(overlap)
+    e1.record(stream)
+    sync_all()
+    return e0.elapsed_time(e1) - flush_ms, dt
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from enzo_e_b200 import problems
-    from enzo_e_b200.domain import Domain
-    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -308,6 +529,7 @@ def run_ours(args):
                          "CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    pin_note = pin_rank_to_cores(local_rank, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         opts = None
@@ -317,59 +539,45 @@ def run_ours(args):
         except Exception:
             pass
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-    domain = Domain(rank, world, grid=_grid(world, args.layout))
-    grid = domain.grid
-    size = args.size
-    n_local = (size, size, size)
-    width = tuple(1.0 / (size * grid[a]) for a in range(3))
-    lower = domain.lower_corner(n_local, width)
+    name = args.workload
+    if world > 1 and not WORKLOADS[name]["multi_gpu"]:
+        raise SystemExit(f"workload {name} is a single-GPU configuration")
+    size = WORKLOADS[name].get("size", args.size)
+    hbm_gbs, peak_kind = measured_peaks()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
-        fields = problems.orszag_tang(n_local, GHOST, lower, width, device=dev)
-        method = EnzoMethodMHDVlct(PARAMS)
-        block = Block(fields, n_local, GHOST, width)   # torch's current stream
-        assert block.stream_is_current
-
-        dt_dev = torch.empty(1, dtype=torch.float64, device=dev)
-
-        def step(overlap=not args.no_overlap):
-            # dt stays on the device (vlct_timestep_dev / vlct_compute_dev):
-            # the cycles queue back to back, nothing waits for the host
-            dt = method.timestep_dev(block, out=dt_dev)
-            dt = domain.global_dt(dt, dev)
-            # refresh + compute; with a z split the z exchange runs under the
-            # interior part of the update (Domain.step)
-            domain.step(method, block, dt, overlap=overlap)
-            return dt
-
-        def sync_all():
-            torch.cuda.synchronize(dev)
-            if world > 1:
-                dist.barrier()
-                torch.cuda.synchronize(dev)
+        setup = Setup(name, size, (rank, world), dev, args.layout)
+        method, block, domain = setup.method, setup.block, setup.domain
+        grid = domain.grid
+        if args.wavefront is not None:
+            method.set_option("wavefront", args.wavefront)
+        overlap = not args.no_overlap
 
         for _ in range(args.warmup):
-            step()
+            setup.step(overlap)
         sync_all()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         launches0 = method.kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            dt = step()
-        e1.record(stream)
-        sync_all()
-        elapsed_ms = e0.elapsed_time(e1)
+        elapsed_ms, dt = timed_steps(setup, stream, args.steps, 0, sync_all, overlap)
         launches = method.kernel_launches() - launches0
         clocks = sampler.stop() if rank == 0 else None
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        cells = size ** 3 * world * args.steps
+        elapsed_ms = reduce_max(elapsed_ms)
+        cells = setup.cells * world * args.steps
         value = cells / (elapsed_ms * 1e-3)
 
         # ---- compute()-only timing and per-kernel profile (live, same process)
@@ -388,62 +596,60 @@ def run_ours(args):
         method.profile(True)
         nprof = 4
         for _ in range(nprof):
-            step(overlap=False)
+            setup.step(overlap=False)
         sync_all()
         report = method.profile_report()
         method.profile(False)
+        last_dt = float(dt.item())
+        scratch_gb = method.scratch_bytes() / 1e9
 
-    hbm_gbs, peak_kind = measured_peaks()
+    b_alg = WORKLOADS[name]["bytes"]
     groups = dict(report)
     total_prof_ms = sum(ms for ms, _ in groups.values())
-    m = size + 2 * GHOST[0]
-    fam = family_rooflines(report, m, hbm_gbs)
-    # dominant kernel = the family with the largest share of the step
-    dom = max(fam, key=lambda k: fam[k]["ms"])
-    d = fam[dom]
-    traffic = None
-    try:   # per-launch DRAM bytes from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(dom)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom + "*" if dom == "k_flux" else dom,
-                "achieved": d["achieved"], "peak": hbm_gbs,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": d["frac"],
-                "traffic": traffic,
-                "algorithmic_bytes_per_launch": d["bytes_per_launch"],
-                "avg_launch_ms": d["avg_launch_ms"],
-                "launches_per_step": d["launches"] / nprof,
-                "share_of_step": d["ms"] / total_prof_ms if total_prof_ms else None,
-                "note": "the flux kernels are bound by the FP64 pipe, not HBM "
-                        "(ncu: profiles/), so their HBM fraction is low by "
-                        "construction; see roofline_families for the "
-                        "memory-bound kernels"}
+    m = setup.n_local[0] + 2 * GHOST[0]
+    fam = family_rooflines(report, m, hbm_gbs) if name in ("ot", "turbulence") else {}
+    step_gbs = value * b_alg / 1e9 / world
+    # the path's roofline is the whole step against HBM
+    roofline = {"bound": "hbm", "kernel": "step (all kernels of one cycle)",
+                "achieved": step_gbs, "peak": hbm_gbs, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": step_gbs / hbm_gbs, "traffic": None,
+                "bytes_per_cell_update": b_alg,
+                "algorithmic_bytes_per_launch": b_alg * setup.cells,
+                "avg_launch_ms": elapsed_ms / args.steps,
+                "note": "per GPU; achieved = cell-updates/s x algorithmic bytes per "
+                        "cell-update (SURVEY 8d; a 'launch' = one step); traffic is "
+                        "not measured in this run (ncu per-kernel DRAM bytes: profiles/)"}
     roofline_families = {k: {"achieved": v["achieved"], "frac": v["frac"],
                              "avg_launch_ms": v["avg_launch_ms"],
+                             "algorithmic_bytes_per_launch": v["bytes_per_launch"],
                              "share_of_step": v["ms"] / total_prof_ms}
                          for k, v in sorted(fam.items())}
-    step_gbs = value * B_ALG_STEP / 1e9 / world
-    roofline_step = {"bound": "hbm", "bytes_per_cell_update": B_ALG_STEP,
-                     "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": step_gbs / hbm_gbs,
-                     "note": "per-GPU; 416 B = compulsory traffic of one MHD "
-                             "cell-update (SURVEY 8d); the path is bound by "
-                             "the FP64 pipe, see DESIGN.md"}
+    roofline_fp64 = fp64_roofline(name, value / world)
     kernels = {k: {"ms_per_step": ms / nprof, "launches_per_step": calls / nprof}
                for k, (ms, calls) in sorted(groups.items())}
 
     # ---- end-to-end through the C ABI with HOST (pinned) buffers ----------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, method, fields, n_local, width, world, dev)
+        e2e = run_e2e(args, setup, world, dev, pin_note)
+    n_local, width = setup.n_local, setup.width
+    setup.close()
+    del setup, method, block
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, short runs ---------------------
+    extras = {}
+    if not args.no_extras:
+        for other in ("turbulence", "ot_s4", "sod256", "fastwave64", "ot"):
+            if other == name or (world > 1 and not WORKLOADS[other]["multi_gpu"]):
+                continue
+            extras[other] = run_extra(other, args, rank, world, dev, stream,
+                                      sync_all, reduce_max, hbm_gbs)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu_baseline = run_cpu_sample(seconds_target=args.cpu_seconds,
-                                      block=args.cpu_block)
-        cpu_baseline = {k: cpu_baseline[k] for k in
-                        ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline = run_cpu_baseline(name, seconds_target=args.cpu_seconds,
+                                        block=args.cpu_block)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -451,54 +657,128 @@ def run_ours(args):
                 "ms_per_step": elapsed_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(size, world, grid),
+                "config": workload_config(name, size, world, grid, args.layout),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "roofline_families": roofline_families,
-                "roofline_step": roofline_step,
+                "roofline": roofline, "roofline_fp64": roofline_fp64,
+                "roofline_families": roofline_families,
                 "cpu_baseline": cpu_baseline,
+                "workloads": extras,
                 "compute_only_ms": compute_ms,
-                "compute_only_value": size ** 3 / (compute_ms * 1e-3),
-                "kernels": kernels, "last_dt": float(dt.item()),
-                "scratch_gb": method.scratch_bytes() / 1e9}
+                "compute_only_value": n_local[0] * n_local[1] * n_local[2] / (compute_ms * 1e-3),
+                "kernels": kernels, "last_dt": last_dt,
+                "scratch_gb": scratch_gb}
         print(json.dumps(line), flush=True)
-    method.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(args, method, fields, n_local, width, world, dev):
+def fp64_roofline(name, value_per_gpu):
+    """fp64 warp-instructions per second against the issue rate of the FP64
+    pipe. The instruction count per cell-update is the ncu opmix of the shipped
+    kernels (profiles/dp_inst.json, per workload; data dependent), not a live
+    measurement."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dp_inst.json")) as fh:
+            table = json.load(fh)
+        per32 = float(table[name]["dp_warp_inst_per_32_cell_updates"])
+        src = table[name].get("source")
+    except Exception:
+        return None
+    achieved = value_per_gpu / 32.0 * per32
+    return {"bound": "fp64", "achieved": achieved, "peak": FP64_WARP_INST_PER_S,
+            "unit": "fp64 warp-instructions/s", "frac": achieved / FP64_WARP_INST_PER_S,
+            "dp_warp_inst_per_32_cell_updates": per32, "source": src,
+            "note": "peak = 148 SMs x 4 sub-partitions x 1 DP warp-instruction per "
+                    "2 cycles x 1.965 GHz (the non-FMA arithmetic bit-parity needs "
+                    "counts one flop per lane per instruction)"}
+
+
+def run_extra(name, args, rank, world, dev, stream, sync_all, reduce_max, hbm_gbs):
+    """a short device-resident run of another BASELINE configuration"""
+    import torch
+    size = WORKLOADS[name].get("size", args.size)
+    try:
+        with torch.cuda.stream(stream):
+            setup = Setup(name, size, (rank, world), dev, args.layout)
+            if args.wavefront is not None:
+                setup.method.set_option("wavefront", args.wavefront)
+            steps = max(3, min(args.steps, 5))
+            ms, dt = timed_steps(setup, stream, steps, 3, sync_all,
+                                 overlap=not args.no_overlap)
+            ms = reduce_max(ms)
+            finite = bool(torch.isfinite(setup.fields["density"]).all())
+            value = setup.cells * world * steps / (ms * 1e-3)
+            out = {"value": value, "unit": UNIT, "ms_per_step": ms / steps,
+                   "steps": steps, "warmup": 3,
+                   "config": workload_config(name, size, world, setup.domain.grid,
+                                             args.layout),
+                   "roofline_frac": value / world * WORKLOADS[name]["bytes"] / 1e9 / hbm_gbs,
+                   "last_dt": float(dt.item()), "finite": finite}
+            setup.close()
+        del setup
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:   # an extra must never take the headline line down
+        return {"error": repr(exc)}
+
+
+def pin_rank_to_cores(local_rank, world):
+    """give every rank its own slice of the host cores (no migration of the
+    thread that feeds the copy engines); returns a note for the JSON line"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cores) < 2 * world:
+            return f"{len(cores)} cores, not pinned"
+        per = len(cores) // world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return f"rank pinned to {per} of {len(cores)} cores"
+    except Exception as exc:
+        return f"not pinned ({exc})"
+
+
+def run_e2e(args, setup, world, dev, pin_note):
     """Same metric through the C ABI with HOST buffers: every step copies the
-    block's fields pinned-host -> device, runs timestep + compute, and copies
-    the results back (all inside vlct_timestep / vlct_compute)."""
+    block's fields pinned-host -> device, runs compute + timestep, and copies
+    the results back, all inside the library's calls. Headline:
+    vlct_compute_and_timestep (one upload + one download per cycle); beside
+    it the two separate calls vlct_timestep + vlct_compute."""
     import torch
     import torch.distributed as dist
     from enzo_e_b200.method import EnzoMethodMHDVlct, Block
-    from enzo_e_b200 import problems
 
     host = {}
-    for k, v in fields.items():
+    for k, v in setup.fields.items():
         t = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
         t.copy_(v)
         host[k] = t
     torch.cuda.synchronize(dev)
     host_np = {k: v.numpy() for k, v in host.items()}
-    m2 = EnzoMethodMHDVlct(PARAMS)
-    hb = Block(host_np, n_local, GHOST, width)
+    w = setup.w
+    m2 = EnzoMethodMHDVlct(w["params"], n_passive=w["n_passive"])
+    if args.wavefront is not None:
+        m2.set_option("wavefront", args.wavefront)
+    hb = Block(host_np, setup.n_local, GHOST, setup.width, passive=setup.passive)
     steps = max(2, min(args.steps, 4))
-    cells = n_local[0] * n_local[1] * n_local[2] * world * steps
+    cells = setup.cells * world * steps
+    refresh_host = None   # the host code's own refresh is not part of the path
 
-    def timed(reuse):
-        m2.set_option("host_mirror_reuse", reuse)
-        for _ in range(1):
-            dt = m2.timestep(hb)
+    def timed(fused):
+        dt = m2.timestep(hb)
+        if fused:
+            dt = m2.compute_and_timestep(hb, dt)
+        else:
             m2.compute(hb, dt)
         if world > 1:
             dist.barrier()
         h2d0, d2h0 = m2.staged_bytes()
         t0 = time.perf_counter()
         for _ in range(steps):
-            dt = m2.timestep(hb)
-            m2.compute(hb, dt)
+            if fused:
+                dt = m2.compute_and_timestep(hb, dt)
+            else:
+                dt = m2.timestep(hb)
+                m2.compute(hb, dt)
         elapsed = time.perf_counter() - t0
         h2d1, d2h1 = m2.staged_bytes()
         t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
@@ -508,18 +788,24 @@ def run_e2e(args, method, fields, n_local, width, world, dev):
         return {"value": cells / elapsed, "unit": UNIT,
                 "h2d_bytes_per_step": (h2d1 - h2d0) // steps,
                 "d2h_bytes_per_step": (d2h1 - d2h0) // steps,
-                "steps": steps, "ms_per_step": 1e3 * elapsed / steps}
+                "steps": steps, "ms_per_step": 1e3 * elapsed / steps,
+                "pcie_gbs_h2d": (h2d1 - h2d0) / elapsed / 1e9,
+                "pcie_gbs_d2h": (d2h1 - d2h0) / elapsed / 1e9}
 
-    out = timed(0)
-    out["path"] = ("vlct_timestep + vlct_compute with mem_space=HOST (pinned host "
-                   "arrays; every call uploads its inputs and downloads its "
-                   "outputs, as a z-pass pipeline of H2D / kernels / D2H)")
-    # informational: the same loop with the caller's promise that nobody writes
-    # the fields between compute and the next timestep (Enzo-E's cycle order),
-    # so that timestep reuses the device copy compute left behind
-    reuse = timed(1)
-    reuse["path"] = "as e2e, option host_mirror_reuse = 1 (include/vlct.h)"
-    out["with_host_mirror_reuse"] = reuse
+    out = timed(True)
+    out["path"] = ("vlct_compute_and_timestep with mem_space=HOST (pinned host "
+                   "arrays): per cycle ONE upload of compute's inputs and ONE "
+                   "download of its outputs + pressure, as a z-pass pipeline of "
+                   "H2D / kernels / D2H; the CFL kernel of the next cycle runs on "
+                   "the device copy behind the update (include/vlct.h)")
+    two = timed(False)
+    two["path"] = ("vlct_timestep + vlct_compute as two calls (each uploads its "
+                   "inputs and downloads its outputs)")
+    out["two_calls"] = two
+    out["host_cores"] = pin_note
+    out["limiter"] = ("PCIe: both directions run concurrently at the rates in "
+                      "pcie_gbs_*; at N > 1 all ranks share one host memory system "
+                      "(every GPU of the box hangs off NUMA node 0)")
     m2.close()
     return out
 
@@ -530,16 +816,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ot", choices=sorted(WORKLOADS))
     ap.add_argument("--size", type=int, default=512,
-                    help="cells per axis per GPU")
+                    help="cells per axis per GPU (workloads without a fixed size)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--cpu-block", type=int, default=48)
-    ap.add_argument("--layout", default="slabs", choices=["slabs", "bricks"],
-                    help="N > 1: z slabs (1x1xN, default) or bricks (2x2x2 at N=8)")
+    ap.add_argument("--cpu-block", type=int, default=64)
+    ap.add_argument("--layout", default="bricks", choices=["slabs", "bricks"],
+                    help="N > 1: bricks (1x1x2, 1x2x2, 2x2x2; default) or z slabs (1x1xN)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: exchange ghosts before the update instead of under it")
+    ap.add_argument("--wavefront", type=int, default=None,
+                    help="override the handle option \"wavefront\" (0 = classic launches)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short runs of the other BASELINE configurations")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

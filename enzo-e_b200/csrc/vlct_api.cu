@@ -43,6 +43,7 @@ struct vlct_handle {
   unsigned long long* h_dt_bits = nullptr;   // pinned
   // device mirror of a HOST block (mem_space == VLCT_MEM_HOST)
   bool have_mirror = false;
+  Geom mirror_G{0, 0, 0};     // shape the mirror was allocated for
   vlct_block mirror;
   // option "host_mirror_reuse": after vlct_compute of a HOST block the mirror
   // holds exactly what was copied back; a vlct_timestep of the same block that
@@ -56,6 +57,7 @@ struct vlct_handle {
   // sub-batch overlap the kernels of another)
   vlct_block arena[2];
   int arena_capacity[2] = { 0, 0 };       // blocks each arena can hold
+  Geom arena_G[2] = { Geom{0, 0, 0}, Geom{0, 0, 0} };   // block shape of each arena
   std::vector<void*> arena_allocs[2];
   long long host_batch_blocks = 0;        // option: HOST sub-batch size, 0 = auto
   // option: how HOST batches cross PCIe. 0 = one cudaMemcpyBatchAsync per
@@ -103,6 +105,23 @@ int fail(vlct_handle* h, int code, const char* fmt, ...)
       return fail((h), VLCT_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
                   cudaGetErrorString(err__), __FILE__, __LINE__);            \
   } while (0)
+
+/// Every entry point runs on the handle's device, whatever device the calling
+/// thread has current (single-process multi-GPU hosts), and restores the
+/// caller's device on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device)
+  {
+    if (device < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != device) { cudaSetDevice(device); switched = true; }
+  }
+  ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 enum Pool { POOL_SCRATCH = 1, POOL_MIRROR = 0, POOL_ARENA = 2 /* + arena index */ };
 
@@ -202,6 +221,24 @@ int check_block(vlct_handle* h, const vlct_block* b, bool for_timestep)
     return fail(h, VLCT_ERR_INVALID_BLOCK,
                 "block must be three-dimensional (nx,ny,nz > 0); this "
                 "implementation supports rank 3 only");
+  if (b->gx < 0 || b->gy < 0 || b->gz < 0)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "negative ghost depth");
+  {
+    // the kernels count rows, columns and warps in 32 bits
+    const double cells = (double) (b->nx + 2 * b->gx + 1) * (b->ny + 2 * b->gy + 1) *
+                         (b->nz + 2 * b->gz + 1);
+    if (cells >= 2147483648.0)
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "block too large: %g cells incl. ghosts (limit 2^31)", cells);
+    // one shape per handle (EnzoMethodMHDVlct.cpp:236-246), also for the entry
+    // points that allocate no scratch themselves
+    const int mx = b->nx + 2 * b->gx, my = b->ny + 2 * b->gy, mz = b->nz + 2 * b->gz;
+    if (h->G.mx != 0 && (mx != h->G.mx || my != h->G.my || mz != h->G.mz))
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "all blocks handled by one handle must share one shape "
+                  "(first block was %dx%dx%d incl. ghosts, got %dx%dx%d)",
+                  h->G.mx, h->G.my, h->G.mz, mx, my, mz);
+  }
   if (!(b->dx > 0 && b->dy > 0 && b->dz > 0))
     return fail(h, VLCT_ERR_INVALID_BLOCK, "cell widths must be positive");
   const Params& P = h->P;
@@ -277,36 +314,61 @@ constexpr int kNumFields = (int) (sizeof(kFields) / sizeof(kFields[0]));
 size_t field_count(const Geom& G, int face)
 { return face < 0 ? cell_count(G) : face_count(G, face); }
 
+/// The device mirror of HOST blocks: allocated from the first HOST block, one
+/// shape per handle like the scratch. Entry points need different field sets
+/// (vlct_timestep may omit the face fields, vlct_compute may omit pressure):
+/// a field that a later block brings along and the mirror does not have yet is
+/// added then, so no kernel ever sees a NULL mirror pointer for a field its
+/// block supplies.
 int ensure_mirror(vlct_handle* h, const vlct_block* b, const Geom& G)
 {
-  if (h->have_mirror) return VLCT_OK;
-  h->mirror = *b;
+  if (h->have_mirror &&
+      (G.mx != h->mirror_G.mx || G.my != h->mirror_G.my || G.mz != h->mirror_G.mz))
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "all HOST blocks handled by one handle must share one shape "
+                "(the device mirror holds %dx%dx%d incl. ghosts, got %dx%dx%d)",
+                h->mirror_G.mx, h->mirror_G.my, h->mirror_G.mz, G.mx, G.my, G.mz);
+  const bool fresh = !h->have_mirror;
+  if (fresh) {
+    h->mirror = *b;
+    for (int f = 0; f < kNumFields; f++) h->mirror.*(kFields[f].member) = nullptr;
+    for (int s = 0; s < VLCT_MAX_PASSIVE; s++) h->mirror.passive[s] = nullptr;
+  }
+  // geometry and cell widths follow the current block
+  h->mirror.nx = b->nx; h->mirror.ny = b->ny; h->mirror.nz = b->nz;
+  h->mirror.gx = b->gx; h->mirror.gy = b->gy; h->mirror.gz = b->gz;
+  h->mirror.dx = b->dx; h->mirror.dy = b->dy; h->mirror.dz = b->dz;
   h->mirror.mem_space = VLCT_MEM_DEVICE;
+  h->mirror.stream = nullptr;
   int rc;
+  bool added = false;
   for (int f = 0; f < kNumFields; f++) {
-    h->mirror.*(kFields[f].member) = nullptr;
     if (b->*(kFields[f].member) == nullptr) continue;
+    if (h->mirror.*(kFields[f].member) != nullptr) continue;
     double* p;
     if ((rc = dev_alloc(h, &p, field_count(G, kFields[f].face), POOL_MIRROR)) != VLCT_OK)
       return rc;
     h->mirror.*(kFields[f].member) = p;
+    added = true;
   }
-  for (int s = 0; s < VLCT_MAX_PASSIVE; s++) {
-    h->mirror.passive[s] = nullptr;
-    if (s < h->P.nsc) {
-      double* p;
-      if ((rc = dev_alloc(h, &p, G.cells(), POOL_MIRROR)) != VLCT_OK) return rc;
-      h->mirror.passive[s] = p;
-    }
+  for (int s = 0; s < h->P.nsc; s++) {
+    if (h->mirror.passive[s] != nullptr) continue;
+    double* p;
+    if ((rc = dev_alloc(h, &p, G.cells(), POOL_MIRROR)) != VLCT_OK) return rc;
+    h->mirror.passive[s] = p;
+    added = true;
   }
   // the zero-fill above must not overtake the H2D copies on the work stream
-  CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
+  if (added) CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
+  if (added) h->mirror_is_current = false;
+  h->mirror_G = G;
   h->have_mirror = true;
   return VLCT_OK;
 }
 
 /// which fields one entry point reads (H2D) and writes (D2H)
-enum CopySet { COPY_COMPUTE_IN, COPY_COMPUTE_OUT, COPY_TIMESTEP_IN };
+enum CopySet { COPY_COMPUTE_IN, COPY_COMPUTE_OUT, COPY_TIMESTEP_IN,
+               COPY_FUSED_OUT /* compute's outputs + "pressure" */ };
 
 bool in_copy_set(const vlct_handle* h, double* vlct_block::*m, CopySet set)
 {
@@ -315,9 +377,10 @@ bool in_copy_set(const vlct_handle* h, double* vlct_block::*m, CopySet set)
   const bool accel = (m == &vlct_block::acceleration_x ||
                       m == &vlct_block::acceleration_y ||
                       m == &vlct_block::acceleration_z);
-  if (m == &vlct_block::pressure) return false;   // output of timestep only
+  if (m == &vlct_block::pressure) return set == COPY_FUSED_OUT;   // timestep's output
   switch (set) {
   case COPY_COMPUTE_IN:  return accel ? (h->cfg.has_acceleration != 0) : true;
+  case COPY_FUSED_OUT:
   case COPY_COMPUTE_OUT: return !accel;            // compute never writes them
   case COPY_TIMESTEP_IN: return !face && !accel;   // cell-centred state only
   }
@@ -544,7 +607,7 @@ void vlct_destroy(vlct_handle* h)
 {
   if (h == nullptr) return;
   if (h->device >= 0) {
-    cudaSetDevice(h->device);
+    DeviceGuard device_guard__(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (void* p : h->allocations) cudaFree(p);
     for (void* p : h->mirror_allocs) cudaFree(p);
@@ -587,9 +650,15 @@ int host_levels(const vlct_handle* h, const Geom& G)
 /// the device mirror on in_stream while the previous pass computes, and the
 /// levels a pass has finished are copied back on out_stream while the next
 /// one computes, so H2D, kernels and D2H overlap (PCIe is full duplex).
+int timestep_launch(vlct_handle* h, const vlct_block* db, const Geom& G,
+                    cudaStream_t st, ZClip zc = kNoClip, bool reset = true);
+
+/// fused_timestep: the CFL kernel of the NEXT cycle follows the update on every
+/// level a pass has finished (vlct_compute_and_timestep), before the level
+/// goes back to the host.
 int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* dev,
                       const Geom& G, double dt, const double* dt_dev,
-                      cudaStream_t st, int levels)
+                      cudaStream_t st, int levels, bool fused_timestep = false)
 {
   const bool staged = (host != nullptr);
   int rc;
@@ -615,16 +684,20 @@ int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* 
     }
     if ((rc = compute_on_device(h, dev, G, dt, dt_dev, st, prev, cut, first)) != VLCT_OK)
       return rc;
+    const int done = (cut.kind == CUT_END) ? cut.z : (1 << 30);
+    if (fused_timestep &&
+        (rc = timestep_launch(h, dev, G, st, ZClip{ downloaded, done }, first)) != VLCT_OK)
+      return rc;
     first = false;
     if (staged) {
       cudaEvent_t ev;
       if ((rc = record_event(h, st, &ev)) != VLCT_OK) return rc;
       CUDA_TRY(h, cudaStreamWaitEvent(h->out_stream, ev, 0));
-      const int done = (cut.kind == CUT_END) ? cut.z : (1 << 30);
-      if ((rc = mirror_copy(h, host, G, h->out_stream, false, COPY_COMPUTE_OUT,
+      if ((rc = mirror_copy(h, host, G, h->out_stream, false,
+                            fused_timestep ? COPY_FUSED_OUT : COPY_COMPUTE_OUT,
                             downloaded, done)) != VLCT_OK) return rc;
-      downloaded = done;
     }
+    downloaded = done;
     prev = cut;
   }
   if (staged) {
@@ -634,20 +707,41 @@ int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* 
   return VLCT_OK;
 }
 
-int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* dt_dev)
+/// dt_next != nullptr: vlct_compute_and_timestep
+int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* dt_dev,
+                  double* dt_next = nullptr)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   int rc = check_block(h, b, false);
   if (rc != VLCT_OK) return rc;
+  const bool fused = (dt_next != nullptr);
+  if (fused && b->pressure == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "\"pressure\" must be a permanent field");
   const Geom G = geom_of(b);
   if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
+  // the fused call ends like vlct_timestep: the minimum comes back to the host
+  auto finish_dt = [&](cudaStream_t st) -> int {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    double dt_min;
+    memcpy(&dt_min, h->h_dt_bits, sizeof(double));
+    *dt_next = dt_min * h->cfg.courant;   // cpp:585-587
+    return VLCT_OK;
+  };
   if (b->mem_space == VLCT_MEM_DEVICE) {
     cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
     if (h->device_pipeline_levels > 0 && h->cfg.time_scheme != VLCT_TIME_EULER)
-      return compute_in_passes(h, nullptr, b, G, dt, dt_dev, st,
-                               (int) h->device_pipeline_levels);
-    return compute_on_device(h, b, G, dt, dt_dev, st);
+      rc = compute_in_passes(h, nullptr, b, G, dt, dt_dev, st,
+                             (int) h->device_pipeline_levels, fused);
+    else {
+      rc = compute_on_device(h, b, G, dt, dt_dev, st);
+      if (rc == VLCT_OK && fused) rc = timestep_launch(h, b, G, st, kNoClip, true);
+    }
+    if (rc == VLCT_OK && fused) rc = finish_dt(st);
+    return rc;
   }
   if (dt_dev != nullptr)
     return fail(h, VLCT_ERR_INVALID_BLOCK,
@@ -657,13 +751,17 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
   if ((rc = ensure_mirror(h, b, G)) != VLCT_OK) return rc;
   h->mirror_is_current = false;
   if (const int levels = host_levels(h, G)) {
-    rc = compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels);
+    rc = compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels, fused);
   } else {
     if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
     if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
-    if ((rc = mirror_copy(h, b, G, st, false, COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+    if (fused && (rc = timestep_launch(h, &h->mirror, G, st, kNoClip, true)) != VLCT_OK)
+      return rc;
+    if ((rc = mirror_copy(h, b, G, st, false,
+                          fused ? COPY_FUSED_OUT : COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(st));
   }
+  if (rc == VLCT_OK && fused) rc = finish_dt(st);
   if (rc == VLCT_OK) {
     // every field timestep() reads was uploaded and/or written by this call
     h->mirror_is_current = true;
@@ -688,7 +786,7 @@ bool mirror_serves(const vlct_handle* h, const vlct_block* b)
 
 /// launches DE sync + pressure + CFL minimum on the block's stream
 int timestep_launch(vlct_handle* h, const vlct_block* db, const Geom& G,
-                    cudaStream_t st, ZClip zc = kNoClip, bool reset = true)
+                    cudaStream_t st, ZClip zc, bool reset)
 {
   const double width[3] = { db->dx, db->dy, db->dz };
   const State u = state_of(h, db);
@@ -746,6 +844,14 @@ extern "C" {
 int vlct_compute(vlct_handle* h, const vlct_block* b, double dt)
 { return compute_entry(h, b, dt, nullptr); }
 
+int vlct_compute_and_timestep(vlct_handle* h, const vlct_block* b, double dt,
+                              double* dt_next)
+{
+  if (h != nullptr && dt_next == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_next is NULL");
+  return compute_entry(h, b, dt, nullptr, dt_next);
+}
+
 int vlct_compute_dev(vlct_handle* h, const vlct_block* b, const double* dt_device)
 {
   if (h != nullptr && dt_device == nullptr)
@@ -756,6 +862,7 @@ int vlct_compute_dev(vlct_handle* h, const vlct_block* b, const double* dt_devic
 int vlct_timestep_dev(vlct_handle* h, const vlct_block* b, double* dt_device)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   if (dt_device == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device is NULL");
   int rc = check_block(h, b, true);
@@ -776,6 +883,7 @@ int vlct_timestep_dev(vlct_handle* h, const vlct_block* b, double* dt_device)
 int vlct_timestep(vlct_handle* h, const vlct_block* b, double* dt_out)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   if (dt_out == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_out is NULL");
   int rc = check_block(h, b, true);
@@ -839,6 +947,17 @@ int check_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
     return fail(h, VLCT_ERR_INVALID_BLOCK, "empty batch");
   int rc;
   const vlct_block& b0 = blocks[0];
+  if ((rc = check_block(h, &b0, for_timestep)) != VLCT_OK) return rc;
+  {
+    // a sub-batch is stacked along z: its cell count must fit 32 bits as well
+    const Geom G0 = geom_of(&b0);
+    long long cap = 65535 / (G0.mz + 1);
+    if (cap > h->batch_max_blocks) cap = h->batch_max_blocks;
+    if (cap > nblocks) cap = nblocks;
+    if ((double) G0.mx * G0.my * (double) (G0.mz + 1) * (double) cap >= 2147483648.0)
+      return fail(h, VLCT_ERR_INVALID_BLOCK,
+                  "batch too large: lower the option batch_max_blocks");
+  }
   for (int n = 0; n < nblocks; n++) {
     const vlct_block& b = blocks[n];
     if ((rc = check_block(h, &b, for_timestep)) != VLCT_OK) return rc;
@@ -860,7 +979,8 @@ int check_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
 int ensure_arena(vlct_handle* h, int a, const vlct_block& b0, const Geom& G)
 {
   vlct_block& arena = h->arena[a];
-  bool enough = (h->arena_capacity[a] >= G.nrep);
+  bool enough = (h->arena_capacity[a] >= G.nrep) && h->arena_G[a].mx == G.mx &&
+                h->arena_G[a].my == G.my && h->arena_G[a].mz == G.mz;
   for (int f = 0; enough && f < kNumFields; f++)
     if (b0.*(kFields[f].member) != nullptr && arena.*(kFields[f].member) == nullptr)
       enough = false;     // a field the arena was not built with
@@ -895,6 +1015,7 @@ int ensure_arena(vlct_handle* h, int a, const vlct_block& b0, const Geom& G)
   }
   CUDA_TRY(h, cudaStreamSynchronize(cudaStreamLegacy));
   h->arena_capacity[a] = G.nrep;
+  h->arena_G[a] = G;
   return VLCT_OK;
 }
 
@@ -1068,6 +1189,7 @@ int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
                           const vlct_face_fluxes* out)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (b == nullptr || out == nullptr)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "NULL argument to vlct_save_face_fluxes");
   if (h->P.mhd)   // EnzoMethodMHDVlct.cpp:137-141
@@ -1132,6 +1254,7 @@ int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
 int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   int rc = check_batch(h, blocks, nblocks, false);
   if (rc != VLCT_OK) return rc;
@@ -1204,6 +1327,7 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
                         double* dt_out)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   if (dt_out == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_out is NULL");
   int rc = check_batch(h, blocks, nblocks, true);
@@ -1264,6 +1388,7 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
 int vlct_host_register(vlct_handle* h, void* ptr, unsigned long long bytes)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (ptr == nullptr || bytes == 0)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_host_register: empty range");
   CUDA_TRY(h, cudaHostRegister(ptr, (size_t) bytes, cudaHostRegisterPortable |
@@ -1275,6 +1400,7 @@ int vlct_host_register(vlct_handle* h, void* ptr, unsigned long long bytes)
 int vlct_host_unregister(vlct_handle* h, void* ptr)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   auto it = h->registered.find(ptr);
   if (it == h->registered.end())
     return fail(h, VLCT_ERR_INVALID_BLOCK,
@@ -1298,6 +1424,7 @@ int vlct_host_unregister(vlct_handle* h, void* ptr)
 int vlct_set_option(vlct_handle* h, const char* key, long long value)
 {
   if (h == nullptr || key == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (strcmp(key, "host_pipeline_levels") == 0) {
     if (value < -1) return fail(h, VLCT_ERR_INVALID_CONFIG, "host_pipeline_levels >= -1");
     h->host_pipeline_levels = value;
@@ -1327,6 +1454,7 @@ int vlct_compute_dev_part(vlct_handle* h, const vlct_block* b,
                           const double* dt_device, int part, int z_lo, int z_hi)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   if (dt_device == nullptr) return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device is NULL");
   int rc = check_block(h, b, false);
@@ -1370,6 +1498,7 @@ long long vlct_staged_bytes(const vlct_handle* h, int direction)
 int vlct_synchronize(vlct_handle* h)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   CUDA_TRY(h, cudaDeviceSynchronize());
   return VLCT_OK;
 }
@@ -1378,6 +1507,7 @@ int vlct_synchronize(vlct_handle* h)
 int vlct_profile_enable(vlct_handle* h, int on)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   h->prof.collect();
   h->prof.enabled = (on != 0);
   return VLCT_OK;
@@ -1386,6 +1516,7 @@ int vlct_profile_enable(vlct_handle* h, int on)
 int vlct_profile_reset(vlct_handle* h)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   h->prof.reset();
   return VLCT_OK;
 }
@@ -1401,6 +1532,7 @@ int vlct_profile_get(vlct_handle* h, int index, char* name, int name_len,
                      double* total_ms, long long* calls)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   h->prof.collect();
   if (index < 0 || index >= (int) h->prof.names.size())
     return fail(h, VLCT_ERR_INTERNAL, "profile index out of range");
@@ -1434,6 +1566,7 @@ int collect_fields(vlct_handle* h, const vlct_block* b, const Geom& G,
 int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
     return fail(h, VLCT_ERR_INVALID_BLOCK,
                 "vlct_refresh_periodic needs a DEVICE block");
@@ -1465,6 +1598,7 @@ int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
 int vlct_boundary(vlct_handle* h, const vlct_block* b, int axis, int side, int type)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_boundary needs a DEVICE block");
   if (axis < 0 || axis > 2 || (side != 0 && side != 1) ||
@@ -1504,6 +1638,7 @@ int vlct_boundary_inflow(vlct_handle* h, const vlct_block* b, int axis, int side
                          const vlct_inflow_values* v)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "vlct_boundary_inflow needs a DEVICE block");
   if (axis < 0 || axis > 2 || (side != 0 && side != 1) || v == nullptr)
@@ -1566,6 +1701,7 @@ int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
               double* buffer, bool pack)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
+  DeviceGuard device_guard__(h->device);
   if (b == nullptr || b->mem_space != VLCT_MEM_DEVICE || axis < 0 || axis > 2 ||
       (side != 0 && side != 1) || buffer == nullptr)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "bad arguments to halo pack/unpack");

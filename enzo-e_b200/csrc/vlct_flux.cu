@@ -265,7 +265,8 @@ k_flux_x(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   const int nyb = box.hi[1] - box.lo[1];
   // rows of all stacked blocks (G.nrep = 1 for a single block)
   const unsigned nzs = (unsigned) (box.hi[2] - box.lo[2]) * (unsigned) G.nrep;
-  // (32-bit index arithmetic: the launcher checks that the counts fit)
+  // (32-bit index arithmetic: check_block / check_batch in vlct_api.cu refuse
+  // blocks and batches of 2^31 or more cells, so the counts fit)
   const unsigned nrows = (unsigned) nyb * nzs;
   const unsigned ngroups = (nrows + kXRows - 1) / kXRows;
   const unsigned gw = blockIdx.x * kXWarps + w;
@@ -504,11 +505,15 @@ void flux_go(const FluxLaunch& L)
     const unsigned gy = (unsigned) ((nf + chunk - 1) / chunk) *
                         (D == 2 ? (unsigned) L.G.nrep : 1u);
     // 4 resident blocks need 4 x (36 KB ring + 1 KB) of the SM's shared memory
-    static bool carveout_set = false;
-    if (!carveout_set) {
+    // (a per-device attribute: remembered per device, one handle = one device
+    // = one host thread at a time)
+    static bool carveout_set[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 0 || device >= 64 || !carveout_set[device]) {
       cudaFuncSetAttribute(k_flux_march<D, RECON, SOLVER, DE>,
                            cudaFuncAttributePreferredSharedMemoryCarveout, 75);
-      carveout_set = true;
+      if (device >= 0 && device < 64) carveout_set[device] = true;
     }
     k_flux_march<D, RECON, SOLVER, DE><<<dim3(gx, gy), kMarchThreads, 0, L.st>>>(
         L.P, L.G, L.cur, L.spec, L.bi, L.F, b, chunk);

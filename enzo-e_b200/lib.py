@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     "vlct_config_init", "vlct_config_set", "vlct_config_validate",
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
+    "vlct_compute_and_timestep",
     "vlct_compute_dev_part", "vlct_set_option",
     "vlct_compute_batch", "vlct_timestep_batch", "vlct_save_face_fluxes",
     "vlct_host_register", "vlct_host_unregister",
@@ -64,6 +65,7 @@ def load():
         "vlct_name": (C.c_char_p, []),
         "vlct_compute": (C.c_int, [C.c_void_p, blkp, C.c_double]),
         "vlct_timestep": (C.c_int, [C.c_void_p, blkp, dp]),
+        "vlct_compute_and_timestep": (C.c_int, [C.c_void_p, blkp, C.c_double, dp]),
         "vlct_timestep_dev": (C.c_int, [C.c_void_p, blkp, dp]),
         "vlct_compute_dev": (C.c_int, [C.c_void_p, blkp, dp]),
         "vlct_compute_dev_part": (C.c_int, [C.c_void_p, blkp, dp, C.c_int,

@@ -157,6 +157,17 @@ class EnzoMethodMHDVlct:
                                                float(dt)))
         block.compute_done()
 
+    def compute_and_timestep(self, block, dt=None):
+        """compute(block) followed by the timestep(block) of the next cycle in
+        one call (vlct_compute_and_timestep): one upload and one download per
+        cycle for HOST blocks. Returns the next dt."""
+        dt = block.dt if dt is None else dt
+        out = C.c_double(0.0)
+        self._check(self._lib.vlct_compute_and_timestep(
+            self._h, C.byref(block.c_block), float(dt), C.byref(out)))
+        block.compute_done()
+        return out.value
+
     def compute_part(self, block, dt, part, z_lo, z_hi):
         """One of the three parts of a step (vlct_compute_dev_part): the
         interior first, then the lower / upper rest once the z ghost levels

@@ -152,6 +152,95 @@ def hydro_blast(n_local, g, lower, width, device="cuda", gamma=5.0 / 3.0,
     return {k: v.contiguous() for k, v in f.items()}
 
 
+def turbulence_modes(seed=20240517, kmax=3, gamma=5.0 / 3.0, mach=0.5,
+                     rho0=1.0, p0=1.0):
+    """The Fourier modes of the decaying-turbulence velocity field (BASELINE
+    configs[3]): every integer wave vector of the half space with
+    1 <= |k| <= kmax gets a Gaussian amplitude vector, projected perpendicular
+    to k (solenoidal), and a uniform random phase, all drawn from
+    numpy.random.default_rng(seed) in a fixed order. The amplitudes are scaled
+    analytically (orthogonal modes: <v^2> = sum |a|^2 / 2) to an rms Mach
+    number `mach`, so that the field is a pure function of position and a brick
+    of a decomposed domain gets the values of the undivided one. Returns
+    (k [M,3] ints, a [M,3], phase [M]) as lists.
+
+    The reference's own generator (src/Enzo/initial/EnzoInitialTurbulence.cpp:
+    54-120 -> turboinit.F) is Fortran and cannot be built here; only the
+    spectrum shape (low-k solenoidal modes, fixed Mach number) is kept."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    ks = []
+    for kz in range(-kmax, kmax + 1):
+        for ky in range(-kmax, kmax + 1):
+            for kx in range(-kmax, kmax + 1):
+                k2 = kx * kx + ky * ky + kz * kz
+                if k2 < 1 or k2 > kmax * kmax:
+                    continue
+                # one of every +-k pair: first non-zero of (kz, ky, kx) positive
+                lead = kz if kz != 0 else (ky if ky != 0 else kx)
+                if lead < 0:
+                    continue
+                ks.append((kx, ky, kz))
+    k = np.array(ks, dtype=np.float64)
+    a = rng.standard_normal(k.shape)
+    phase = rng.uniform(0.0, 2.0 * math.pi, size=len(ks))
+    khat = k / np.sqrt((k * k).sum(axis=1, keepdims=True))
+    a = a - khat * (a * khat).sum(axis=1, keepdims=True)
+    # Kolmogorov-like weighting |k|^(-11/6) of the mode amplitudes
+    a = a * ((k * k).sum(axis=1, keepdims=True)) ** (-11.0 / 12.0)
+    cs2 = gamma * p0 / rho0
+    scale = math.sqrt((mach * mach * cs2) / (0.5 * float((a * a).sum())))
+    a = a * scale
+    return ks, a.tolist(), phase.tolist()
+
+
+def turbulence(n_local, g, lower, width, global_n, device="cuda",
+               gamma=5.0 / 3.0, seed=20240517, mach=0.5, beta=2.0, n_passive=0):
+    """Decaying MHD turbulence (BASELINE configs[3]): rho = 1, p = 1, a uniform
+    field B = (0, 0, B0) with plasma beta = 2 p / B0^2, and a solenoidal
+    velocity field of low-k Fourier modes (turbulence_modes). Cell positions
+    come from the global cell index wrapped into the periodic domain of
+    `global_n` cells, so ghost cells hold exactly the values of their periodic
+    images and every brick of a decomposition the values of the undivided
+    domain. Genuinely three-dimensional: every sweep direction sees all HLLD
+    regions."""
+    shape = tuple(n_local[ax] + 2 * g[ax] for ax in (2, 1, 0))
+    mz, my, mx = shape
+    pos = []
+    for ax in range(3):
+        m = n_local[ax] + 2 * g[ax]
+        off = round(lower[ax] / width[ax])
+        idx = torch.arange(m, dtype=torch.float64, device=device) - g[ax] + off
+        idx = torch.remainder(idx, float(global_n[ax]))
+        pos.append((0.5 + idx) / float(global_n[ax]))        # in [0, 1)
+    X = pos[0].view(1, 1, mx)
+    Y = pos[1].view(1, my, 1)
+    Z = pos[2].view(mz, 1, 1)
+    ks, amp, phase = turbulence_modes(seed, gamma=gamma, mach=mach)
+    v = [torch.zeros(shape, dtype=torch.float64, device=device) for _ in range(3)]
+    two_pi = 2.0 * math.pi
+    for (kx, ky, kz), a, ph in zip(ks, amp, phase):
+        c = torch.cos(two_pi * (kx * X + ky * Y + kz * Z) + ph)
+        for comp in range(3):
+            v[comp] += a[comp] * c
+        del c
+    f = {"density": torch.ones(shape, dtype=torch.float64, device=device)}
+    for comp, name in enumerate("xyz"):
+        f["velocity_" + name] = v[comp]
+    b0 = math.sqrt(2.0 * 1.0 / beta)
+    f["bfieldi_x"] = torch.zeros((mz, my, mx + 1), dtype=torch.float64, device=device)
+    f["bfieldi_y"] = torch.zeros((mz, my + 1, mx), dtype=torch.float64, device=device)
+    f["bfieldi_z"] = torch.full((mz + 1, my, mx), b0, dtype=torch.float64, device=device)
+    _center_b(f)
+    ke = 0.5 * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    f["total_energy"] = 1.0 / (gamma - 1.0) + ke + 0.5 * b0 * b0
+    f["pressure"] = torch.zeros(shape, dtype=torch.float64, device=device)
+    for s in range(n_passive):
+        f[f"passive_{s}"] = (f["density"] * (0.5 + 0.4 * torch.sin(
+            two_pi * ((s + 1) * X + Y + Z)))).expand(shape).contiguous()
+    return {k: t.contiguous() for k, t in f.items()}
+
+
 # ---------------------------------------------------------------------------
 # the reference's answer-test problems, generated in device memory
 # ---------------------------------------------------------------------------

@@ -205,6 +205,27 @@ enum { VLCT_PART_INTERIOR = 0, VLCT_PART_LOWER = 1, VLCT_PART_UPPER = 2 };
 int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
                           const double *dt_device, int part, int z_lo, int z_hi);
 
+/* compute(block) and the timestep(block) of the cycle that follows, in ONE
+ * call. In Enzo-E's cycle the stopping phase calls Method::timestep on every
+ * block right after the compute phase (src/Cello/control_compute.cpp:42-157 ->
+ * control_stopping.cpp:44-142), on exactly the fields compute left behind. For
+ * a VLCT_MEM_HOST block two separate calls move the cell-centred state across
+ * PCIe twice (compute downloads it, timestep uploads it again). Here the CFL
+ * kernel (EnzoMethodMHDVlct.cpp:551-588: dual-energy sync, "pressure" field,
+ * minimum over all cells incl. ghost zones, times courant) runs on the device
+ * copy right behind the update, z pass by z pass inside the staging pipeline,
+ * and "pressure" plus the (dual-energy-synced) energies come back with the
+ * other fields: one upload and one download per cycle. The result -- all
+ * fields, "pressure", *dt_next -- is bit for bit what vlct_compute followed by
+ * vlct_timestep on the same block leaves (tests/test_gpu_fused_timestep.py).
+ * block->pressure must be non-NULL. The reference-side adapter
+ * (integration/EnzoMethodMHDVlctGpu.cpp) calls this from compute() and hands
+ * the cached value to the timestep() that follows when it is the last Method
+ * touching the fields. Two-stage "vl" and single-stage "euler" schemes, HOST
+ * and DEVICE blocks. */
+int vlct_compute_and_timestep(vlct_handle *h, const vlct_block *block, double dt,
+                              double *dt_next);
+
 /* Flux-correction output:
  * EnzoMethodMHDVlct::save_fluxes_for_corrections_
  * (src/Enzo/hydro-mhd/EnzoMethodMHDVlct.cpp:250-330, called for the final

@@ -26,6 +26,10 @@ def main():
     # the update (device-resident dt); "slabs": z slabs instead of bricks
     mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
     overlap = "overlap" in mode
+    # "ot": the z-extruded Orszag-Tang vortex; "turbulence": a flow that varies
+    # along all three axes (problems.turbulence), so that the x, y and z
+    # exchanges, edges and corners all carry distinct data
+    problem = sys.argv[3] if len(sys.argv) > 3 else "ot"
     n_scalars = 1
     params = {"mhd_choice": "constrained_transport", "riemann_solver": "hlld",
               "reconstruct_method": "plm", "theta_limiter": 1.5,
@@ -41,8 +45,12 @@ def main():
     passive = tuple(f"passive_{k}" for k in range(n_scalars))
 
     def run(domain, n, lower, overlap=False):
-        f = problems.orszag_tang(n, g, lower, width, device=dev,
-                                 n_passive=n_scalars)
+        if problem == "turbulence":
+            f = problems.turbulence(n, g, lower, width, N, device=dev,
+                                    n_passive=n_scalars)
+        else:
+            f = problems.orszag_tang(n, g, lower, width, device=dev,
+                                     n_passive=n_scalars)
         m = EnzoMethodMHDVlct(params, n_passive=n_scalars)
         blk = Block(f, n, g, width, passive=passive)
         dts = []
@@ -94,7 +102,7 @@ def main():
                     print(f"MISMATCH {name} rank {r}: max diff {diff:.3e}")
                     ok = False
         print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAIL", "world", world, "grid",
-              dom.grid, "dts", dts)
+              dom.grid, "mode", mode, "problem", problem, "dts", dts, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -29,6 +29,32 @@ CASES = {
                                      accel=True, dual_energy=True, eta=0.0),
 }
 
+# Floors that really fire on the random state (density 1 +- 0.1 noise, pressure
+# 0.6 (1 +- 0.1 noise)): the reconstructed-state floors
+# (EnzoReconstructorPLM.hpp:166-248), the density floor of the update
+# (EnzoIntegrationQuanUpdate.cpp:183-238) and the energy floor with and
+# without dual energy (EnzoPhysicsFluidProps.cpp:162-290). Same values as the
+# oracle's own pinned case (tests/test_oracle_golden.py: mhd_hlld_floors).
+FLOOR_CASES = {
+    "mhd_hlld_plm_floors": dict(riemann="hlld", recon="plm", mhd=True,
+                                dfloor=0.95, pfloor=0.55),
+    "mhd_hlld_nn_floors": dict(riemann="hlld", recon="nn", mhd=True,
+                               dfloor=0.95, pfloor=0.55),
+    "mhd_hlle_athena_floors_scalars": dict(riemann="hlle", recon="plm_athena",
+                                           mhd=True, dfloor=0.97, pfloor=0.58,
+                                           n_passive=2),
+    "mhd_hlld_plm_de_floors": dict(riemann="hlld", recon="plm", mhd=True,
+                                   dual_energy=True, dfloor=0.95, pfloor=0.55),
+    "hd_hllc_plm_de_floors": dict(riemann="hllc", recon="plm", mhd=False,
+                                  dual_energy=True, gamma=1.4, dfloor=0.95,
+                                  pfloor=0.55),
+    "hd_hllc_plm_floors": dict(riemann="hllc", recon="plm", mhd=False,
+                               dfloor=0.95, pfloor=0.55),
+    "hd_hllc_euler_floors": dict(riemann="hllc", recon="plm", mhd=False,
+                                 time_scheme="euler", courant=0.5, dfloor=0.95,
+                                 pfloor=0.55),
+}
+
 
 def run_cpu(cfg, host, n, g, d, nsteps, kind="oracle"):
     f = copy_state(host)
@@ -128,5 +154,60 @@ def test_against_compiled_reference():
     host = random_state(cfg, n, g, seed=5)
     want, dts_want = run_cpu(cfg, host, n, g, d, 2, kind="ref")
     got, dts_got, _ = run_gpu(cfg, host, n, g, d, 2, True)
+    assert dts_got == dts_want
+    assert all(bit_equal(want, got).values())
+
+
+def _eint_floor_hits(cfg, f, g):
+    """cells of the active zone whose thermal energy sits exactly on the floor
+    pressure_floor / ((gamma - 1) rho) (FluidProps.cpp:204-205, 262-266)"""
+    sl = (slice(g[2], -g[2]), slice(g[1], -g[1]), slice(g[0], -g[0]))
+    rho = f["density"][sl]
+    inv_gm1 = 1.0 / (cfg.gamma - 1.0)
+    eint_floor = cfg.pressure_floor * inv_gm1 * (1.0 / rho)
+    if cfg.dual_energy:
+        return int(np.sum(f["internal_energy"][sl] == eint_floor))
+    nt = 0.5 * (f["velocity_x"][sl] * f["velocity_x"][sl]
+                + f["velocity_y"][sl] * f["velocity_y"][sl]
+                + f["velocity_z"][sl] * f["velocity_z"][sl])
+    if cfg.mhd_choice == 1:
+        b2 = (f["bfield_x"][sl] * f["bfield_x"][sl] + f["bfield_y"][sl] * f["bfield_y"][sl]
+              + f["bfield_z"][sl] * f["bfield_z"][sl])
+        nt = nt + 0.5 * b2 * (1.0 / rho)
+    return int(np.sum(f["total_energy"][sl] == eint_floor + nt))
+
+
+@pytest.mark.parametrize("name", sorted(FLOOR_CASES))
+@pytest.mark.parametrize("kind", ["oracle", "ref"])
+def test_active_floors_bit_exact(name, kind):
+    """GPU vs the oracle AND vs the compiled reference with floors that fire:
+    density floor, reconstructed-state floors and the energy floor (with and
+    without dual energy) -- the floor branches must actually be taken."""
+    if kind == "ref" and not oracle.have_ref():
+        pytest.skip("oracle/_ref/libvlct_ref.so not available on this box")
+    cfg = make_config(**FLOOR_CASES[name])
+    n, g, d = (20, 12, 10), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=21)
+    nsteps = 3
+    want, dts_want = run_cpu(cfg, host, n, g, d, nsteps, kind=kind)
+    got, dts_got, _ = run_gpu(cfg, host, n, g, d, nsteps, True)
+    assert dts_got == dts_want
+    eq = bit_equal(want, got)
+    bad = {k: max_abs_diff(want, got)[k] for k, ok in eq.items() if not ok}
+    assert not bad, f"fields differ from the {kind}: {bad}"
+    # the floors fired, on the device
+    act = got["density"][g[2]:-g[2], g[1]:-g[1], g[0]:-g[0]]
+    assert np.min(act) >= cfg.density_floor
+    assert np.any(act == cfg.density_floor), "density floor never fired"
+    assert _eint_floor_hits(cfg, got, g) > 0, "energy floor never fired"
+
+
+@pytest.mark.parametrize("name", ["mhd_hlld_plm_floors", "hd_hllc_plm_de_floors"])
+def test_active_floors_host_blocks(name):
+    cfg = make_config(**FLOOR_CASES[name])
+    n, g, d = (20, 12, 10), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=22)
+    want, dts_want = run_cpu(cfg, host, n, g, d, 2)
+    got, dts_got, _ = run_gpu(cfg, host, n, g, d, 2, False)
     assert dts_got == dts_want
     assert all(bit_equal(want, got).values())
