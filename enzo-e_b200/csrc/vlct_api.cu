@@ -34,6 +34,9 @@ struct vlct_handle {
   // options (vlct_set_option)
   long long host_pipeline_levels = -1;   // -1 auto, 0 off, n > 0: n z levels per pass
   long long device_pipeline_levels = 0;  // test hook: run DEVICE steps in passes too
+  // measurement hook (scripts/gpu_power.py): bit k set = launch kernel family k
+  // of a step (KernelId order). Anything but "all" leaves garbage in the fields.
+  long long debug_kernel_mask = -1;
   Geom G{0, 0, 0};
   Scratch S;
   std::vector<void*> allocations;
@@ -519,20 +522,26 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
 
     const LaunchCtx ctx{ st, &h->launches, &h->prof };
     const int row = final_stage ? 1 : 0;
-    launch_primitives(ctx, P, G, cur, h->S, stale, pass_clip(zlo, zhi, row, K_SCAL));
+    const long long mask = h->debug_kernel_mask;
+    const ZClip nothing{ 0, 0 };
+    if (mask & (1 << K_SCAL))
+      launch_primitives(ctx, P, G, cur, h->S, stale, pass_clip(zlo, zhi, row, K_SCAL));
     const int cs = stale + immediate_staling(recon);
     for (int dim = 0; dim < 3; dim++)
-      launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs,
-                  pass_clip(zlo, zhi, row, dim == 2 ? K_FLUX_Z : K_FLUX_XY));
+      if (mask & (1 << (dim == 2 ? K_FLUX_Z : K_FLUX_XY)))
+        launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs,
+                    pass_clip(zlo, zhi, row, dim == 2 ? K_FLUX_Z : K_FLUX_XY));
     if (P.mhd)
       launch_ct(ctx, P, G, cur, h->S, bi, bi_out, step_params, cs,
-                pass_clip(zlo, zhi, row, K_EDGE), pass_clip(zlo, zhi, row, K_FACE));
+                (mask & (1 << K_EDGE)) ? pass_clip(zlo, zhi, row, K_EDGE) : nothing,
+                (mask & (1 << K_FACE)) ? pass_clip(zlo, zhi, row, K_FACE) : nothing);
     // gravity: full step only, i.e. stage index 1
     // (EnzoMHDIntegratorStageCommands.cpp:181,279)
     const bool gravity = (stage == 1) && h->cfg.has_acceleration &&
                          accel[0] != nullptr;
-    launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
-                  step_params, cs, pass_clip(zlo, zhi, row, K_UPDATE));
+    if (mask & (1 << K_UPDATE))
+      launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
+                    step_params, cs, pass_clip(zlo, zhi, row, K_UPDATE));
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -1441,6 +1450,8 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
   } else if (strcmp(key, "batch_max_blocks") == 0) {
     if (value < 1) return fail(h, VLCT_ERR_INVALID_CONFIG, "batch_max_blocks >= 1");
     h->batch_max_blocks = value;
+  } else if (strcmp(key, "debug_kernel_mask") == 0) {
+    h->debug_kernel_mask = value;
   } else if (strcmp(key, "device_pipeline_levels") == 0) {
     if (value < 0) return fail(h, VLCT_ERR_INVALID_CONFIG, "device_pipeline_levels >= 0");
     h->device_pipeline_levels = value;
