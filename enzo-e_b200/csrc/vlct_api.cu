@@ -1260,13 +1260,33 @@ int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
   return VLCT_OK;
 }
 
-int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt)
+}  // extern "C"
+
+namespace {
+/// vlct_compute_batch; with dt_next != nullptr vlct_compute_and_timestep_batch:
+/// the CFL kernel follows the update of every sub-batch on its stacked arrays
+/// and "pressure" (+ the dual-energy-synced energies) come back with the rest
+int compute_batch_impl(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt,
+                       double* dt_next)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
   DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   int rc = check_batch(h, blocks, nblocks, false);
   if (rc != VLCT_OK) return rc;
+  const bool fused = (dt_next != nullptr);
+  if (fused && blocks[0].pressure == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "\"pressure\" must be a permanent field");
+  const CopySet out_set = fused ? COPY_FUSED_OUT : COPY_COMPUTE_OUT;
+  auto finish_dt = [&](cudaStream_t st) -> int {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_dt_bits, h->d_dt_bits, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    double dt_min;
+    memcpy(&dt_min, h->h_dt_bits, sizeof(double));
+    *dt_next = dt_min * h->cfg.courant;
+    return VLCT_OK;
+  };
   const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
   cudaStream_t st = (!host && blocks[0].stream) ? (cudaStream_t) blocks[0].stream
                                                  : h->own_stream;
@@ -1281,11 +1301,13 @@ int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, do
       if ((rc = batch_copy(h, 0, blocks, first, nb, nblocks, G, st, true,
                            COPY_COMPUTE_IN)) != VLCT_OK) return rc;
       if ((rc = compute_on_device(h, &h->arena[0], G, dt, nullptr, st)) != VLCT_OK) return rc;
+      if (fused && (rc = timestep_launch(h, &h->arena[0], G, st, kNoClip, first == 0)) != VLCT_OK)
+        return rc;
       if ((rc = batch_copy(h, 0, blocks, first, nb, nblocks, G, st, false,
-                           COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+                           out_set)) != VLCT_OK) return rc;
       // (stream order protects the arena between consecutive sub-batches)
     }
-    return VLCT_OK;
+    return fused ? finish_dt(st) : VLCT_OK;
   }
   // HOST blocks: a pipeline over sub-batches with two arenas -- the H2D copies
   // of sub-batch s+1 (in_stream), the kernels of sub-batch s (st) and the D2H
@@ -1321,16 +1343,33 @@ int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, do
     if ((rc = record_event(h, h->in_stream, &ev)) != VLCT_OK) return rc;
     CUDA_TRY(h, cudaStreamWaitEvent(st, ev, 0));
     if ((rc = compute_on_device(h, &h->arena[a], G, dt, nullptr, st)) != VLCT_OK) return rc;
+    if (fused && (rc = timestep_launch(h, &h->arena[a], G, st, kNoClip, first == 0)) != VLCT_OK)
+      return rc;
     if ((rc = record_event(h, st, &ev)) != VLCT_OK) return rc;
     CUDA_TRY(h, cudaStreamWaitEvent(h->out_stream, ev, 0));
     if ((rc = batch_copy(h, a, blocks, first, nb, nblocks, G, h->out_stream, false,
-                         COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
+                         out_set)) != VLCT_OK) return rc;
     if ((rc = record_event(h, h->out_stream, &downloaded[a])) != VLCT_OK) return rc;
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->out_stream));
   CUDA_TRY(h, cudaStreamSynchronize(st));
-  return VLCT_OK;
+  return fused ? finish_dt(st) : VLCT_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int vlct_compute_batch(vlct_handle* h, const vlct_block* blocks, int nblocks, double dt)
+{ return compute_batch_impl(h, blocks, nblocks, dt, nullptr); }
+
+int vlct_compute_and_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
+                                    double dt, double* dt_next)
+{
+  if (h != nullptr && dt_next == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_next is NULL");
+  return compute_batch_impl(h, blocks, nblocks, dt, dt_next);
+}
+
 
 int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
                         double* dt_out)

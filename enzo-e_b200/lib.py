@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "vlct_config_init", "vlct_config_set", "vlct_config_validate",
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
-    "vlct_compute_and_timestep",
+    "vlct_compute_and_timestep", "vlct_compute_and_timestep_batch",
     "vlct_compute_dev_part", "vlct_set_option",
     "vlct_compute_batch", "vlct_timestep_batch", "vlct_save_face_fluxes",
     "vlct_host_register", "vlct_host_unregister",
@@ -73,6 +73,8 @@ def load():
         "vlct_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "vlct_compute_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_double]),
         "vlct_timestep_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, dp]),
+        "vlct_compute_and_timestep_batch": (C.c_int, [C.c_void_p, blkp, C.c_int,
+                                                      C.c_double, dp]),
         "vlct_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ulonglong]),
         "vlct_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
         "vlct_save_face_fluxes": (C.c_int, [C.c_void_p, blkp,

@@ -225,6 +225,17 @@ class EnzoMethodMHDVlct:
         for b in blocks:
             b.compute_done()
 
+    def compute_and_timestep_batch(self, blocks, dt):
+        """compute_batch followed by timestep_batch in one call
+        (vlct_compute_and_timestep_batch); returns the next dt."""
+        arr = self._block_array(blocks)
+        out = C.c_double(0.0)
+        self._check(self._lib.vlct_compute_and_timestep_batch(
+            self._h, arr, len(blocks), float(dt), C.byref(out)))
+        for b in blocks:
+            b.compute_done()
+        return out.value
+
     def timestep_batch(self, blocks):
         """min over the blocks of timestep(block); fills every "pressure"."""
         arr = self._block_array(blocks)

@@ -270,6 +270,13 @@ int vlct_compute_batch(vlct_handle *h, const vlct_block *blocks, int nblocks,
                        double dt);
 int vlct_timestep_batch(vlct_handle *h, const vlct_block *blocks, int nblocks,
                         double *dt_out);
+/* vlct_compute_batch followed by vlct_timestep_batch on the same blocks in one
+ * call (see vlct_compute_and_timestep): the CFL kernel runs on each sub-batch's
+ * stacked device arrays right behind the update; *dt_next is the minimum over
+ * the batch; every block's "pressure" is filled. One upload and one download
+ * per cycle for HOST blocks. */
+int vlct_compute_and_timestep_batch(vlct_handle *h, const vlct_block *blocks,
+                                    int nblocks, double dt, double *dt_next);
 
 /* Pinning of host field memory. Staging of VLCT_MEM_HOST blocks is fastest
  * from page-locked memory: the copies of the single-block pipeline and of the

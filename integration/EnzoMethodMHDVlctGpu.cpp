@@ -4,6 +4,7 @@
 #include "Enzo/enzo.hpp"
 #include "EnzoMethodMHDVlctGpu.hpp"
 
+#include <cstdio>
 #include <cstring>
 
 //----------------------------------------------------------------------
@@ -30,22 +31,37 @@ static void set_key_(vlct_config* cfg, const char* key, const std::string& val)
 EnzoMethodMHDVlctGpu::EnzoMethodMHDVlctGpu(ParameterGroup p,
                                            bool store_fluxes_for_corrections)
   : Method(), handle_(nullptr), passive_names_(),
-    store_fluxes_for_corrections_(store_fluxes_for_corrections)
+    store_fluxes_for_corrections_(store_fluxes_for_corrections),
+    batch_blocks_(true), fused_timestep_(false)
 {
   vlct_config_init(&config_);
 
   // Method:mhd_vlct:* (cpp:38-101): forward whatever the user wrote; the
-  // library applies the reference's defaults and error messages
-  static const char* const keys[] = {
-    "mhd_choice", "riemann_solver", "reconstruct_method", "theta_limiter",
-    "time_scheme", "courant",
+  // library applies the reference's defaults and error messages. Like the
+  // reference (cpp:42-43) a parameter counts as defined when
+  // ParameterGroup::param() finds it; values are read with value_string /
+  // value_float.
+  auto is_defined = [&](const char* key) -> bool { return p.param(key) != nullptr; };
+  static const char* const string_keys[] = {
+    "mhd_choice", "riemann_solver", "reconstruct_method", "time_scheme",
     "half_dt_reconstruct_method", "full_dt_reconstruct_method" };
-  for (const char* key : keys) {
-    const std::string* val = p.param(key);
-    if (val != nullptr) {
-      set_key_(&config_, (std::string("Method:mhd_vlct:") + key).c_str(), *val);
+  for (const char* key : string_keys) {
+    if (is_defined(key)) {
+      set_key_(&config_, (std::string("Method:mhd_vlct:") + key).c_str(),
+               p.value_string(key, ""));
     }
   }
+  static const char* const float_keys[] = { "theta_limiter", "courant" };
+  for (const char* key : float_keys) {
+    if (is_defined(key)) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%.17g", p.value_float(key, 0.));
+      set_key_(&config_, (std::string("Method:mhd_vlct:") + key).c_str(), buf);
+    }
+  }
+  // keys of this binding only (no counterpart in the reference)
+  batch_blocks_ = p.value_logical("gpu_batch_blocks", true);
+  fused_timestep_ = p.value_logical("gpu_fused_timestep", false);
 
   // Physics:fluid_props (what EnzoMHDIntegratorStageCommands reads through
   // enzo::fluid_props(), EnzoMHDIntegratorStageCommands.cpp:18-64)
@@ -89,6 +105,34 @@ EnzoMethodMHDVlctGpu::EnzoMethodMHDVlctGpu(ParameterGroup p,
   ASSERT("EnzoMethodMHDVlctGpu", "\"pressure\" must be a permanent field",
          field_descr->is_field("pressure"));
 
+  // every field handed to the library is fp64 with one common ghost depth
+  // (bind_block_ passes a single (gx, gy, gz) and raw double pointers)
+  {
+    static const char* const names[] = {
+      "density", "velocity_x", "velocity_y", "velocity_z", "total_energy",
+      "internal_energy", "bfield_x", "bfield_y", "bfield_z", "bfieldi_x",
+      "bfieldi_y", "bfieldi_z", "pressure", "acceleration_x", "acceleration_y",
+      "acceleration_z" };
+    std::vector<std::string> all(names, names + sizeof(names) / sizeof(names[0]));
+    all.insert(all.end(), passive_names_.begin(), passive_names_.end());
+    int g0[3] = { -1, -1, -1 };
+    for (const std::string& field_name : all) {
+      if (!field_descr->is_field(field_name)) continue;
+      const int id = field_descr->field_id(field_name);
+      const int prec = field_descr->precision(id);
+      ASSERT1("EnzoMethodMHDVlctGpu", "field \"%s\" must be double precision",
+              field_name.c_str(),
+              prec == precision_double ||
+              (prec == precision_default && sizeof(enzo_float) == sizeof(double)));
+      int g[3];
+      field_descr->ghost_depth(id, &g[0], &g[1], &g[2]);
+      if (g0[0] < 0) { g0[0] = g[0]; g0[1] = g[1]; g0[2] = g[2]; }
+      ASSERT1("EnzoMethodMHDVlctGpu",
+              "field \"%s\" must have the ghost depth of \"density\"",
+              field_name.c_str(), g[0] == g0[0] && g[1] == g0[1] && g[2] == g0[2]);
+    }
+  }
+
   create_handle_();
   this->set_courant(config_.courant < 0
                     ? (config_.time_scheme == VLCT_TIME_VL ? 0.3 : 1.0)
@@ -112,6 +156,10 @@ void EnzoMethodMHDVlctGpu::create_handle_()
 
 EnzoMethodMHDVlctGpu::~EnzoMethodMHDVlctGpu()
 {
+  if (!queue_.empty()) {
+    WARNING1("EnzoMethodMHDVlctGpu::~EnzoMethodMHDVlctGpu",
+             "%d queued blocks were never advanced", (int) queue_.size());
+  }
   vlct_destroy(handle_);
 }
 
@@ -124,7 +172,16 @@ void EnzoMethodMHDVlctGpu::pup(PUP::er& p)
   PUParray(p, reinterpret_cast<char*>(&config_), sizeof(vlct_config));
   p | passive_names_;
   p | store_fluxes_for_corrections_;
-  if (p.isUnpacking()) create_handle_();
+  p | batch_blocks_;
+  p | fused_timestep_;
+  // the queue and the cached timesteps live within one compute phase resp.
+  // one cycle; Charm++ migrates / checkpoints Methods between cycles
+  ASSERT("EnzoMethodMHDVlctGpu::pup", "pup() with blocks still queued",
+         queue_.empty());
+  if (p.isUnpacking()) {
+    cached_dt_.clear();
+    create_handle_();          // the library handle (device scratch) is rebuilt
+  }
 }
 
 //----------------------------------------------------------------------
@@ -236,23 +293,102 @@ void EnzoMethodMHDVlctGpu::save_fluxes_for_corrections_(Block* block,
 
 //----------------------------------------------------------------------
 
+void EnzoMethodMHDVlctGpu::compute_one_(Block* block) throw()
+{
+  vlct_block b;
+  bind_block_(block, &b);
+  int rc;
+  if (fused_timestep_ && !store_fluxes_for_corrections_) {
+    double dt_next = 0.;
+    rc = vlct_compute_and_timestep(handle_, &b, block->dt(), &dt_next);
+    for (std::size_t i = 0; i < cached_dt_.size();) {       // one entry per block
+      if (cached_dt_[i].block == block) cached_dt_.erase(cached_dt_.begin() + i);
+      else i++;
+    }
+    cached_dt_.push_back(CachedDt{ block, block->cycle() + 1, dt_next });
+  } else {
+    rc = vlct_compute(handle_, &b, block->dt());
+  }
+  check_status_(rc, handle_, "EnzoMethodMHDVlctGpu::compute");
+  if (store_fluxes_for_corrections_) save_fluxes_for_corrections_(block, b);  // cpp:480-490
+}
+
+//----------------------------------------------------------------------
+
 void EnzoMethodMHDVlctGpu::compute(Block* block) throw()
 {
   if (store_fluxes_for_corrections_) allocate_FC_flux_buffer_(block);   // cpp:362
-  if (block->is_leaf()) {           // cpp:364
-    vlct_block b;
-    bind_block_(block, &b);
-    const int rc = vlct_compute(handle_, &b, block->dt());
-    check_status_(rc, handle_, "EnzoMethodMHDVlctGpu::compute");
-    if (store_fluxes_for_corrections_) save_fluxes_for_corrections_(block, b);  // cpp:480-490
+
+  // Cello calls compute() once per block of this process, block after block
+  // (src/Cello/control_compute.cpp:72-112), and a block only moves on when it
+  // reports compute_done(). Entry methods run to completion, so with several
+  // blocks per process the calls can be gathered: the blocks are queued, the
+  // call for the process's last block advances them all in ONE set of kernel
+  // launches (vlct_compute_batch) and then every block reports compute_done().
+  // No block needs another block's compute_done() to reach its own compute()
+  // (the refresh that precedes compute() only needs the neighbours' data of the
+  // previous phase), so nothing can deadlock on the delay.
+  const std::size_t expected = cello::simulation()->hierarchy()->num_blocks();
+  const bool batching = batch_blocks_ && expected > 1 && !store_fluxes_for_corrections_;
+  if (!batching) {
+    if (block->is_leaf()) compute_one_(block);       // cpp:364
+    block->compute_done();                           // cpp:499
+    return;
   }
-  block->compute_done();            // cpp:499
+  if (queue_.empty()) cached_dt_.clear();            // a new compute phase
+  queue_.push_back(Queued{ block, block->is_leaf() });
+  if (queue_.size() >= expected) flush_queue_();
+}
+
+//----------------------------------------------------------------------
+
+void EnzoMethodMHDVlctGpu::flush_queue_() throw()
+{
+  // group the leaf blocks by (dt, cell widths): blocks of one refinement level
+  std::vector<char> done(queue_.size(), 0);
+  for (std::size_t first = 0; first < queue_.size(); first++) {
+    if (done[first] || !queue_[first].leaf) continue;
+    std::vector<vlct_block> batch;
+    std::vector<Block*> members;
+    vlct_block b0;
+    bind_block_(queue_[first].block, &b0);
+    const double dt0 = queue_[first].block->dt();
+    for (std::size_t i = first; i < queue_.size(); i++) {
+      if (done[i] || !queue_[i].leaf) continue;
+      vlct_block b;
+      bind_block_(queue_[i].block, &b);
+      if (queue_[i].block->dt() != dt0 || b.dx != b0.dx || b.dy != b0.dy || b.dz != b0.dz)
+        continue;
+      batch.push_back(b);
+      members.push_back(queue_[i].block);
+      done[i] = 1;
+    }
+    int rc;
+    if (fused_timestep_) {
+      // the batch minimum serves every member: Cello min-reduces the blocks'
+      // timesteps anyway (src/Cello/control_stopping.cpp:96-142)
+      double dt_next = 0.;
+      rc = vlct_compute_and_timestep_batch(handle_, batch.data(), (int) batch.size(),
+                                           dt0, &dt_next);
+      for (Block* member : members)
+        cached_dt_.push_back(CachedDt{ member, member->cycle() + 1, dt_next });
+    } else {
+      rc = vlct_compute_batch(handle_, batch.data(), (int) batch.size(), dt0);
+    }
+    check_status_(rc, handle_, "EnzoMethodMHDVlctGpu::compute (batch)");
+  }
+  // every block of the process moves on (cpp:499), in the order Cello called
+  std::vector<Queued> queued;
+  queued.swap(queue_);          // compute_done() may re-enter compute()
+  for (const Queued& q : queued) q.block->compute_done();
 }
 
 //----------------------------------------------------------------------
 
 double EnzoMethodMHDVlctGpu::timestep(Block* block) throw()
 {
+  for (const CachedDt& c : cached_dt_)
+    if (c.block == block && c.cycle == block->cycle()) return c.dt;
   vlct_block b;
   bind_block_(block, &b);
   double dt = 0.;

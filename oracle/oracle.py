@@ -104,14 +104,26 @@ def numpy_block(fields, n, g, d, passive=()):
 class CpuMethod:
     """A CPU `EnzoMethodMHDVlct` (oracle restatement or compiled reference)."""
 
-    def __init__(self, cfg, ghost=(3, 3, 3), kind="oracle", store_fluxes=False):
+    def __init__(self, cfg, ghost=(3, 3, 3), kind="oracle", store_fluxes=False,
+                 gpu_batch_blocks=None, gpu_fused_timestep=None):
         """store_fluxes: construct the reference Method ("ref" / "adapter")
         with store_fluxes_for_corrections = true (the oracle restatement
-        always keeps its flux arrays)"""
+        always keeps its flux arrays). gpu_batch_blocks / gpu_fused_timestep:
+        the two parameter keys of the GPU binding ("adapter" only)."""
         self.kind = kind
         self.cfg = cfg
         (self._lib, create, self._destroy, self._compute,
          self._timestep) = _load(kind)
+        if gpu_batch_blocks is not None or gpu_fused_timestep is not None:
+            assert kind == "adapter" and not store_fluxes
+            fn = self._lib.vlct_adapter_create_opts
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.POINTER(abi.VlctConfig)] + [C.c_int] * 5
+
+            def create(cfgp, gx, gy, gz):
+                as_int = lambda v: -1 if v is None else int(bool(v))  # noqa: E731
+                return fn(cfgp, gx, gy, gz, as_int(gpu_batch_blocks),
+                          as_int(gpu_fused_timestep))
         if store_fluxes and kind != "oracle":
             pfx = {"ref": "vlct_ref", "adapter": "vlct_adapter"}[kind]
             create = getattr(self._lib, pfx + "_create_fc")
@@ -171,6 +183,53 @@ class CpuMethod:
         if rc != 0:
             raise RuntimeError(f"vlct_oracle_face_fluxes failed ({rc})")
         return out
+
+    # -- the GPU binding driven like a process with several blocks ---------
+    def _block_array(self, blks):
+        arr = (abi.VlctBlock * len(blks))()
+        for i, b in enumerate(blks):
+            arr[i] = b
+        return arr
+
+    def compute_many(self, blks, dt, cycle=0):
+        """Method::compute on one block after the other, as Cello's compute
+        phase does on a process owning all of them. Returns how many blocks
+        had not yet reported compute_done() when the last call began."""
+        assert self.kind == "adapter"
+        fn = self._lib.vlct_adapter_compute_many
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_int, C.c_double,
+                       C.c_int, C.POINTER(C.c_int)]
+        deferred = C.c_int(0)
+        rc = fn(self._h, self._block_array(blks), len(blks), float(dt), int(cycle),
+                C.byref(deferred))
+        if rc != 0:
+            raise RuntimeError(f"adapter: compute_many failed ({rc})")
+        return deferred.value
+
+    def timestep_many(self, blks, cycle=0):
+        assert self.kind == "adapter"
+        fn = self._lib.vlct_adapter_timestep_many
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock), C.c_int, C.c_int,
+                       C.POINTER(C.c_double)]
+        out = (C.c_double * len(blks))()
+        rc = fn(self._h, self._block_array(blks), len(blks), int(cycle), out)
+        if rc != 0:
+            raise RuntimeError(f"adapter: timestep_many failed ({rc})")
+        return list(out)
+
+    def pup_roundtrip(self):
+        """pack the Method with a PUP::er, rebuild it through the migration
+        constructor + unpack; returns the packed size in bytes"""
+        assert self.kind == "adapter"
+        fn = self._lib.vlct_adapter_pup_roundtrip
+        fn.restype = C.c_longlong
+        fn.argtypes = [C.c_void_p]
+        size = fn(self._h)
+        if size <= 0:
+            raise RuntimeError(f"adapter: pup round trip failed ({size})")
+        return size
 
     def timestep(self, blk):
         out = C.c_double(0.0)

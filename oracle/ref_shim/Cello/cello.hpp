@@ -329,6 +329,7 @@ public:
   void compute_done() { compute_done_count++; }
   void initial_done() {}
   void set_dt(double dt) { dt_ = dt; }
+  void set_cycle(int cycle) { cycle_ = cycle; }
   Data data_;
   double dt_, time_;
   int cycle_;
@@ -344,9 +345,22 @@ public:
   void add_field(int) {}
 };
 
+/// src/Cello/mesh_Hierarchy.hpp:178-179: blocks on this process
+class Hierarchy {
+public:
+  Hierarchy() : num_blocks_(1) {}
+  size_t num_blocks() const throw() { return num_blocks_; }
+  void set_num_blocks(size_t n) { num_blocks_ = n; }
+private:
+  size_t num_blocks_;
+};
+
 class Simulation {
 public:
   void refresh_set_name(int, const std::string&) {}
+  Hierarchy* hierarchy() const throw() { return const_cast<Hierarchy*>(&hierarchy_); }
+private:
+  Hierarchy hierarchy_;
 };
 
 class Monitor {
@@ -486,8 +500,6 @@ public:
   void evaluate(T*, double, int, int, double*, int, int, double*, int, int,
                 double*) const {}
 };
-
-class Hierarchy;
 
 /// src/Cello/problem_Initial.hpp: only what an Initial subclass needs to compile
 class Initial : public PUP::able {

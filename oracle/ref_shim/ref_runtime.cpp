@@ -106,6 +106,9 @@ struct RefContext {
 struct RefHandle {
   RefContext* ctx;
   ShimMethod* method;
+  // blocks of the *_many entry points: they live as long as the handle, like
+  // Cello's blocks live across cycles (the adapter keys its cache on Block*)
+  std::vector<std::unique_ptr<EnzoBlock>> blocks;
   // flux-correction output of the last compute: [field slot][axis][face]
   bool store_fluxes = false;
   std::vector<double> saved[6 + VLCT_MAX_PASSIVE][3][2];
@@ -185,7 +188,7 @@ void bind_block(RefHandle* h, EnzoBlock& blk, const vlct_block* b) {
 extern "C" {
 
 static void* create_(const vlct_config* cfg, int gx, int gy, int gz,
-                     bool store_fluxes)
+                     bool store_fluxes, int gpu_batch = -1, int gpu_fused = -1)
 {
   std::lock_guard<std::mutex> lock(g_mutex);
   RefContext* c = nullptr;
@@ -266,6 +269,9 @@ static void* create_(const vlct_config* cfg, int gx, int gy, int gz,
   if (cfg->mhd_choice != VLCT_MHD_UNSET)
     p.set("mhd_choice", mhd ? "constrained_transport" : "no_bfield");
   if (cfg->courant >= 0) p.set("courant", fmt_double(cfg->courant));
+  // keys of the GPU binding only (integration/EnzoMethodMHDVlctGpu.hpp)
+  if (gpu_batch >= 0) p.set("gpu_batch_blocks", gpu_batch ? "true" : "false");
+  if (gpu_fused >= 0) p.set("gpu_fused_timestep", gpu_fused ? "true" : "false");
 
   h->store_fluxes = store_fluxes;
   h->method = new ShimMethod(p, store_fluxes);
@@ -445,6 +451,87 @@ int vlct_ref_boundary(void* handle, const vlct_block* b, int axis, int side, int
                                                       : boundary_type_reflecting);
   boundary.enforce(&blk, side == 0 ? face_lower : face_upper, (axis_enum) axis);
   return 0;
+}
+#endif
+
+#ifdef VLCT_SHIM_GPU_ADAPTER
+/// the adapter constructed with its own two keys set
+void* vlct_adapter_create_opts(const vlct_config* cfg, int gx, int gy, int gz,
+                               int gpu_batch_blocks, int gpu_fused_timestep)
+{ return create_(cfg, gx, gy, gz, false, gpu_batch_blocks, gpu_fused_timestep); }
+
+static void bind_many(RefHandle* h, const vlct_block* blocks, int n, int cycle)
+{
+  while ((int) h->blocks.size() < n)
+    h->blocks.emplace_back(new EnzoBlock(&h->ctx->descr));
+  for (int i = 0; i < n; i++) {
+    bind_block(h, *h->blocks[i], &blocks[i]);
+    h->blocks[i]->set_cycle(cycle);
+  }
+  g_simulation.hierarchy()->set_num_blocks((size_t) n);
+}
+
+/// The compute phase of one cycle the way Cello runs it on a process with n
+/// blocks: Method::compute(block) for one block after the other
+/// (src/Cello/control_compute.cpp:72-112). Returns 0 if every block reported
+/// compute_done() exactly once by the end; *deferred = how many blocks had NOT
+/// reported it when the last call began (n - 1 when the adapter batches).
+int vlct_adapter_compute_many(void* handle, const vlct_block* blocks, int n, double dt,
+                              int cycle, int* deferred)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  bind_many(h, blocks, n, cycle);
+  for (int i = 0; i < n; i++) {
+    h->blocks[i]->set_dt(dt);
+    h->blocks[i]->compute_done_count = 0;
+  }
+  int not_done = 0;
+  for (int i = 0; i < n; i++) {
+    if (i == n - 1)
+      for (int j = 0; j < n - 1; j++) not_done += (h->blocks[j]->compute_done_count == 0);
+    h->method->compute(h->blocks[i].get());
+  }
+  if (deferred) *deferred = not_done;
+  g_simulation.hierarchy()->set_num_blocks(1);
+  for (int i = 0; i < n; i++)
+    if (h->blocks[i]->compute_done_count != 1) return 1;
+  return h->method->queued_blocks() == 0 ? 0 : 2;
+}
+
+/// Method::timestep on the same n blocks (stopping phase of cycle `cycle`)
+int vlct_adapter_timestep_many(void* handle, const vlct_block* blocks, int n, int cycle,
+                               double* dts)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  bind_many(h, blocks, n, cycle);
+  g_simulation.hierarchy()->set_num_blocks(1);
+  for (int i = 0; i < n; i++) dts[i] = h->method->timestep(h->blocks[i].get());
+  return 0;
+}
+
+/// Charm++ migration / checkpoint of the Method: size, pack, construct a new
+/// object with the migration constructor, unpack into it, delete the old one
+/// (EnzoMethodMHDVlct.cpp:170-197, hpp:102-112). Returns the packed size.
+long long vlct_adapter_pup_roundtrip(void* handle)
+{
+  RefHandle* h = static_cast<RefHandle*>(handle);
+  activate(h);
+  std::vector<char> buffer;
+  PUP::er sizer(PUP::er::SIZING, &buffer);
+  h->method->pup(sizer);
+  PUP::er packer(PUP::er::PACKING, &buffer);
+  h->method->pup(packer);
+  if (buffer.size() != sizer.size()) return -1;
+  CkMigrateMessage msg;
+  ShimMethod* fresh = new ShimMethod(&msg);
+  PUP::er unpacker(PUP::er::UNPACKING, &buffer);
+  fresh->pup(unpacker);
+  if (unpacker.size() != buffer.size()) { delete fresh; return -2; }
+  delete h->method;
+  h->method = fresh;
+  return (long long) buffer.size();
 }
 #endif
 
