@@ -86,6 +86,9 @@ k_specific_scalars(const int nsc, const typename GeomFor<STACKED>::type G,
 //   identify_upwind :170-216, compute_center_efield :267-292,
 //   compute_edge_ :384-457 (negate_Ej = true), update_bfield :617-687
 // ---------------------------------------------------------------------------
+#ifndef VLCT_EDGE_MINBLOCKS
+#define VLCT_EDGE_MINBLOCKS 4
+#endif
 struct EdgeArgs {
   const double* v[3];
   const double* b[3];
@@ -142,6 +145,92 @@ __device__ __forceinline__ void edge_component(const GEOM& G, const EdgeArgs& A,
   A.edge[D][c] = 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
 }
 
+#ifndef VLCT_EDGE_V1
+/// one edge value from its twelve inputs (compute_edge_, CT.cpp:384-457, with
+/// negate_Ej = true): operand order as in the reference
+__device__ __forceinline__ double
+edge_value(double Ec, double Ec_jp1, double Ec_kp1, double Ec_jkp1, double Ej,
+           double Ej_kp1, double Ek, double Ek_jp1, double Wj, double Wj_kp1,
+           double Wk, double Wk_jp1)
+{
+  const double dEdj_r = Wk_jp1 * (Ec_jp1 + Ej) + (1 - Wk_jp1) * (Ec_jkp1 + Ej_kp1);
+  const double dEdj_l = Wk * (-Ej - Ec) + (1 - Wk) * (-Ej_kp1 - Ec_kp1);
+  const double dEdk_r = Wj_kp1 * (Ec_kp1 - Ek) + (1 - Wj_kp1) * (Ec_jkp1 - Ek_jp1);
+  const double dEdk_l = Wj * (Ek - Ec) + (1 - Wj) * (Ek_jp1 - Ec_jp1);
+  double Ej_sum = Ej + Ej_kp1;
+  Ej_sum *= -1;
+  const double Ek_sum = Ek + Ek_jp1;
+  return 0.25 * (Ej_sum + Ek_sum + (dEdj_l - dEdj_r) + (dEdk_l - dEdk_r));
+}
+
+// All three components of the edge E of one cell in one pass. The components
+// read v and B on seven cells of the cell's 2x2x2 cube (0, +x, +y, +z, +y+z,
+// +z+x, +x+y) and the density flux of every sweep on three: each value is
+// loaded once (57 loads where three separate passes issue 72), every array is
+// addressed from one pointer at the cell (the +x neighbours are immediate
+// offsets), and nothing branches: a thread on the lowest layer of a
+// component's box evaluates that component too and only skips its store. The
+// kernel is bound by instruction issue under the board's power cap, not by
+// HBM (profiles/r2b_power_per_kernel_family.jsonl), so instructions are what
+// counts.
+template <bool STACKED>
+__global__ void __launch_bounds__(kBlock, VLCT_EDGE_MINBLOCKS)
+k_edge_efield(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const Box box)
+{
+  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
+  const ptrdiff_t Y = (ptrdiff_t) G.mx, Z = (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
+  const size_t c = cidx(G, k, j, i);
+  const double* const vx = A.v[0] + c; const double* const vy = A.v[1] + c;
+  const double* const vz = A.v[2] + c; const double* const bx = A.b[0] + c;
+  const double* const by = A.b[1] + c; const double* const bz = A.b[2] + c;
+  // cell-centred E_d = -v_j B_k + v_k B_j  (compute_center_efield, CT.cpp:267-292)
+#define VLCT_EX(o) (-__ldg(vy + (o)) * __ldg(bz + (o)) + __ldg(vz + (o)) * __ldg(by + (o)))
+#define VLCT_EY(o) (-__ldg(vz + (o)) * __ldg(bx + (o)) + __ldg(vx + (o)) * __ldg(bz + (o)))
+#define VLCT_EZ(o) (-__ldg(vx + (o)) * __ldg(by + (o)) + __ldg(vy + (o)) * __ldg(bx + (o)))
+  // upwind weights from the density fluxes (identify_upwind, CT.cpp:170-216)
+  const double* const rx = A.frho[0] + c;
+  const double* const ry = A.frho[1] + c;
+  const double* const rz = A.frho[2] + c;
+  const double wx0 = upwind_weight(__ldg(rx)), wxY = upwind_weight(__ldg(rx + Y)),
+               wxZ = upwind_weight(__ldg(rx + Z));
+  const double wy0 = upwind_weight(__ldg(ry)), wyZ = upwind_weight(__ldg(ry + Z)),
+               wyX = upwind_weight(__ldg(ry + 1));
+  const double wz0 = upwind_weight(__ldg(rz)), wzX = upwind_weight(__ldg(rz + 1)),
+               wzY = upwind_weight(__ldg(rz + Y));
+  const bool in_x = (i < box.hi[0]), in_y = (j < box.hi[1]), in_z = (kl < box.hi[2]);
+  (void) in_x; (void) in_y; (void) in_z;   // (the launch box is the union: always true)
+  {
+    // x component: (j, k) = (y, z); E_x on y-faces is -F_y(B_z), on z-faces +F_z(B_y)
+    const double* const Fj = A.fb[1][2] + c;
+    const double* const Fk = A.fb[2][1] + c;
+    const double e = edge_value(VLCT_EX(0), VLCT_EX(Y), VLCT_EX(Z), VLCT_EX(Y + Z),
+                                __ldg(Fj), __ldg(Fj + Z), __ldg(Fk), __ldg(Fk + Y),
+                                wy0, wyZ, wz0, wzY);
+    if (i >= A.box[0].lo[0]) A.edge[0][c] = e;
+  }
+  {
+    // y component: (j, k) = (z, x)
+    const double* const Fj = A.fb[2][0] + c;
+    const double* const Fk = A.fb[0][2] + c;
+    const double e = edge_value(VLCT_EY(0), VLCT_EY(Z), VLCT_EY(1), VLCT_EY(Z + 1),
+                                __ldg(Fj), __ldg(Fj + 1), __ldg(Fk), __ldg(Fk + Z),
+                                wz0, wzX, wx0, wxZ);
+    if (j >= A.box[1].lo[1]) A.edge[1][c] = e;
+  }
+  {
+    // z component: (j, k) = (x, y)
+    const double* const Fj = A.fb[0][1] + c;
+    const double* const Fk = A.fb[1][0] + c;
+    const double e = edge_value(VLCT_EZ(0), VLCT_EZ(1), VLCT_EZ(Y), VLCT_EZ(Y + 1),
+                                __ldg(Fj), __ldg(Fj + Y), __ldg(Fk), __ldg(Fk + 1),
+                                wx0, wxY, wy0, wyX);
+    if (kl >= A.box[2].lo[2]) A.edge[2][c] = e;
+  }
+#undef VLCT_EX
+#undef VLCT_EY
+#undef VLCT_EZ
+}
+#else
 // (40 registers = 6 blocks of 256 threads per SM; measured faster than 5 blocks
 // at 42-44 registers, 4.4 vs 5.1 ms at 512^3, and than 8 blocks at 32)
 template <bool STACKED>
@@ -153,6 +242,7 @@ k_edge_efield(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const B
   edge_component<1>(G, A, kl, k, j, i);
   edge_component<2>(G, A, kl, k, j, i);
 }
+#endif
 
 struct FaceArgs {
   const double* edge[3];

@@ -37,14 +37,17 @@ def main():
               "Physics:fluid_props:floors:density": 1e-200,
               "Physics:fluid_props:floors:pressure": 1e-200}
     from enzo_e_b200.domain import proc_grid
-    dom = Domain(rank, world, grid=proc_grid(world, slabs="slabs" in mode))
+    grid = proc_grid(world, slabs="slabs" in mode)
+    if os.environ.get("VLCT_TEST_GRID"):      # e.g. "2,1,1": split along x only
+        grid = tuple(int(v) for v in os.environ["VLCT_TEST_GRID"].split(","))
+    dom = Domain(rank, world, grid=grid)
     g = (3, 3, 3)
     n_local = (24, 20, 16)
     N = tuple(n_local[a] * dom.grid[a] for a in range(3))
     width = tuple(1.0 / N[a] for a in range(3))
     passive = tuple(f"passive_{k}" for k in range(n_scalars))
 
-    def run(domain, n, lower, overlap=False):
+    def run(domain, n, lower, overlap=False, impose_dts=None):
         if problem == "turbulence":
             f = problems.turbulence(n, g, lower, width, N, device=dev,
                                     n_passive=n_scalars)
@@ -54,16 +57,18 @@ def main():
         m = EnzoMethodMHDVlct(params, n_passive=n_scalars)
         blk = Block(f, n, g, width, passive=passive)
         dts = []
-        for _ in range(nsteps):
+        for step in range(nsteps):
             if overlap:
                 dt = domain.global_dt(m.timestep_dev(blk), dev)
                 domain.step(m, blk, dt)
                 dts.append(dt.clone())
             else:
                 dt = domain.global_dt(m.timestep(blk), dev)
+                dts.append(dt)
+                if impose_dts is not None:
+                    dt = impose_dts[step]
                 domain.refresh(m, blk)
                 m.compute(blk, dt)
-                dts.append(dt)
         m.synchronize()
         torch.cuda.synchronize()
         assert blk.compute_done_count == nsteps
@@ -81,10 +86,23 @@ def main():
         if rank == 0:
             f[name] = parts
     if rank == 0:
+        # The single block advances with the decomposed run's timesteps. Its own
+        # CFL values are only reported: like the reference's
+        # (EnzoMHDIntegratorStageCommands.cpp:336,361) the minimum runs over the
+        # ghost zones too, which after a compute still hold the PREVIOUS state
+        # (hydro ghosts are never updated), so every brick boundary adds
+        # old-state cells to the minimum and the value depends on the
+        # decomposition whenever the limiting cell of the old state sits within
+        # three cells of one (seen with the turbulence problem on 2x2x2 bricks;
+        # the field update itself is decomposition invariant, which is what this
+        # test pins).
         single = Domain(0, 1)
-        fs, dts_s = run(single, N, (0.0, 0.0, 0.0))
+        fs, dts_s = run(single, N, (0.0, 0.0, 0.0), impose_dts=dts)
         if dts != dts_s:
-            print("dt sequences differ", dts, dts_s)
+            print("note: CFL over stale ghost zones differs between the "
+                  "decompositions:", dts, "vs single block", dts_s, flush=True)
+        if dts[0] != dts_s[0]:
+            print("first timestep (fresh ghost zones) differs", dts[0], dts_s[0])
             ok = False
         for name in names:
             face = {"bfieldi_x": 0, "bfieldi_y": 1, "bfieldi_z": 2}.get(name, -1)
@@ -98,8 +116,12 @@ def main():
                     lo = g[ax] + c[ax] * n_local[ax]
                     sl_glob.append(slice(lo, lo + ext))
                 if not torch.equal(part[tuple(sl_loc)], fs[name][tuple(sl_glob)]):
-                    diff = (part[tuple(sl_loc)] - fs[name][tuple(sl_glob)]).abs().max().item()
-                    print(f"MISMATCH {name} rank {r}: max diff {diff:.3e}")
+                    delta = (part[tuple(sl_loc)] - fs[name][tuple(sl_glob)]).abs()
+                    diff = delta.max().item()
+                    where = torch.nonzero(delta > 0)
+                    print(f"MISMATCH {name} rank {r} coords {c}: max diff {diff:.3e}, "
+                          f"{where.shape[0]} entries, first (z,y,x) {where[0].tolist()} "
+                          f"last {where[-1].tolist()} of {list(delta.shape)}")
                     ok = False
         print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAIL", "world", world, "grid",
               dom.grid, "mode", mode, "problem", problem, "dts", dts, flush=True)
