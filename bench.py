@@ -197,7 +197,7 @@ def workload_config(name, size, world, grid, layout):
             "gamma": w["params"]["Physics:fluid_props:eos:gamma"],
             "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} {layout}",
             "algorithmic_bytes_per_cell_update": w["bytes"],
-            "step": "timestep + dt min-reduce + ghost refresh + compute (dt device-resident: vlct_timestep_dev / vlct_compute_dev; with a z split the z ghost exchange overlaps the interior update)",
+            "step": "ghost refresh + compute + the next cycle's timestep (folded into the last update kernel: vlct_compute_and_timestep_dev) + its min-reduce over ranks; dt stays on the device; with a z split the z ghost exchange overlaps the interior update",
             "l2_policy": "inputs (>=1.1 GB per field at 512^3, 143 MB at 256^3) exceed the 126 MB L2"
                          if n[0] * n[1] * n[2] >= 256 ** 3 else
                          "L2 flushed between timed steps (a 256 MB buffer is rewritten)"}
@@ -406,13 +406,16 @@ FAMILIES = {
                "units": lambda m, name: ((m - 5) * (m - 4) ** 2 if name.endswith("plm")
                                          else (m - 1) * m * m)},
     # per cell: 15 fluxes + 3 face B + 5 start-of-step fields in, 8 fields out
-    "k_update": {"doubles": 31, "units": lambda m, name: (m - 2) ** 3},
+    # (+ "pressure" out for k_update_cfl, the update that also does the CFL work)
+    "k_update": {"doubles": 31, "units": lambda m, name: (m - 2) ** 3 * (
+        32.0 / 31.0 if name.endswith("cfl") else 1.0)},
     # per cell: v, B (6) + 6 B-fluxes + 3 density fluxes in, 3 edge E out
     "k_edge_efield": {"doubles": 18, "units": lambda m, name: (m - 2) ** 3},
     # per cell: 3 edge E + 3 face B in, 3 face B out
     "k_face_bfield": {"doubles": 9, "units": lambda m, name: (m - 2) ** 3},
-    # per cell: 8 fields in, pressure out
-    "k_timestep": {"doubles": 9, "units": lambda m, name: m ** 3},
+    # per cell: 8 fields in, pressure out (k_timestep_shell: the ghost shell only)
+    "k_timestep": {"doubles": 9, "units": lambda m, name: (
+        m ** 3 - (m - 6) ** 3 if name.endswith("shell") else m ** 3)},
 }
 
 
@@ -467,6 +470,9 @@ class Setup:
                            passive=self.passive)   # torch's current stream
         assert self.block.stream_is_current
         self.dt_dev = torch.empty(1, dtype=torch.float64, device=dev)
+        self.dt_next = torch.empty(1, dtype=torch.float64, device=dev)
+        self.primed = False
+        self.fold = True       # fold the next cycle's timestep into the update
         self.dev = dev
         self.cells = self.n_local[0] * self.n_local[1] * self.n_local[2]
         # small blocks fit the L2: flush it between timed steps
@@ -479,11 +485,26 @@ class Setup:
         # cycles queue back to back, nothing waits for the host
         if self.flush is not None:
             self.flush.add_(1.0)
-        dt = self.method.timestep_dev(self.block, out=self.dt_dev)
-        dt = self.domain.global_dt(dt, self.dev)
+        if not self.fold:
+            dt = self.method.timestep_dev(self.block, out=self.dt_dev)
+            dt = self.domain.global_dt(dt, self.dev)
+            self.domain.step(self.method, self.block, dt, overlap=overlap)
+            return dt
+        # Enzo-E's cycle is timestep -> refresh -> compute; the timestep of the
+        # NEXT cycle only needs what compute leaves behind, so it is evaluated
+        # inside the last update kernel (vlct_compute_and_timestep_dev). One
+        # cycle = refresh + compute + next timestep + its min-reduction.
+        if not self.primed:
+            dt = self.method.timestep_dev(self.block, out=self.dt_dev)
+            self.domain.global_dt(dt, self.dev)
+            self.primed = True
+        dt = self.dt_dev
         # refresh + compute; with a z split the z exchange runs under the
         # interior part of the update (Domain.step)
-        self.domain.step(self.method, self.block, dt, overlap=overlap)
+        self.domain.step(self.method, self.block, dt, overlap=overlap,
+                         dt_next=self.dt_next)
+        self.domain.global_dt(self.dt_next, self.dev)
+        self.dt_dev, self.dt_next = self.dt_next, self.dt_dev
         return dt
 
     def close(self):
@@ -562,8 +583,7 @@ def run_ours(args):
         setup = Setup(name, size, (rank, world), dev, args.layout)
         method, block, domain = setup.method, setup.block, setup.domain
         grid = domain.grid
-        if args.wavefront is not None:
-            method.set_option("wavefront", args.wavefront)
+        setup.fold = not args.no_fold
         overlap = not args.no_overlap
 
         for _ in range(args.warmup):
@@ -700,8 +720,7 @@ def run_extra(name, args, rank, world, dev, stream, sync_all, reduce_max, hbm_gb
     try:
         with torch.cuda.stream(stream):
             setup = Setup(name, size, (rank, world), dev, args.layout)
-            if args.wavefront is not None:
-                setup.method.set_option("wavefront", args.wavefront)
+            setup.fold = not args.no_fold
             steps = max(3, min(args.steps, 5))
             ms, dt = timed_steps(setup, stream, steps, 3, sync_all,
                                  overlap=not args.no_overlap)
@@ -756,8 +775,6 @@ def run_e2e(args, setup, world, dev, pin_note):
     host_np = {k: v.numpy() for k, v in host.items()}
     w = setup.w
     m2 = EnzoMethodMHDVlct(w["params"], n_passive=w["n_passive"])
-    if args.wavefront is not None:
-        m2.set_option("wavefront", args.wavefront)
     hb = Block(host_np, setup.n_local, GHOST, setup.width, passive=setup.passive)
     steps = max(2, min(args.steps, 4))
     cells = setup.cells * world * steps
@@ -825,8 +842,9 @@ def main():
                     help="N > 1: bricks (1x1x2, 1x2x2, 2x2x2; default) or z slabs (1x1xN)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: exchange ghosts before the update instead of under it")
-    ap.add_argument("--wavefront", type=int, default=None,
-                    help="override the handle option \"wavefront\" (0 = classic launches)")
+    ap.add_argument("--no-fold", action="store_true",
+                    help="separate timestep kernel every cycle instead of the CFL "
+                         "work folded into the last update (vlct_compute_and_timestep_dev)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true",

@@ -26,7 +26,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 BOUNDARY = {"outflow": 0, "reflecting": 1}
 PART_INTERIOR, PART_LOWER, PART_UPPER = 0, 1, 2
 # input levels an interior part reads below z_lo / beyond z_hi (vlct.h)
-PART_REACH_BELOW, PART_REACH_ABOVE = 4, 6
+PART_REACH_BELOW, PART_REACH_ABOVE = 5, 6
 
 _DP = C.POINTER(C.c_double)
 

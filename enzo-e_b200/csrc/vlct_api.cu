@@ -185,9 +185,10 @@ int alloc_scratch(vlct_handle* h, const Geom& G)
       if (d != 2) ALLOC(F.bz, n);
     }
     if (P.de) { ALLOC(F.eint, n); ALLOC(F.vbar, n); }
-    for (int s = 0; s < P.nsc; s++) ALLOC(F.sc[s], n);
+    for (int s = 0; s < P.nsc_flux; s++) ALLOC(F.sc[s], n);
   }
-  for (int s = 0; s < P.nsc; s++) ALLOC(S.prim_sc[s], n);
+  for (int stage = 0; stage < (two_stage ? 2 : 1); stage++)
+    for (int s = 0; s < P.nsc; s++) ALLOC(S.prim_sc[stage][s], n);
   if (P.mhd) for (int d = 0; d < 3; d++) ALLOC(S.edge[d], n);
 #undef ALLOC
   // dev_alloc's memsets run on the legacy default stream; the kernels run on a
@@ -454,7 +455,9 @@ int immediate_staling(int recon) { return recon == VLCT_RECON_NN ? 0 : 1; }
 //   FLUX_Z(f)  <- stage input / SCAL f-1..f+2 (PLM; f..f+1 with NN), z-face f+1
 //   EDGE(k)    <- FLUX_XY k..k+1, FLUX_Z k, stage input k..k+1
 //   FACE(k)    <- EDGE k-1..k
-//   UPDATE(k)  <- FLUX_XY k, FLUX_Z k-1..k, FACE k..k+1
+//   UPDATE(k)  <- FLUX_XY k, FLUX_Z k-1..k, FACE k..k+1, SCAL k-2..k+2 (passive
+//                 scalars without flux arrays: the update reconstructs them
+//                 itself; each stage has its own SCAL arrays)
 // and the second stage's input is the first stage's UPDATE / FACE output.
 //   an END cut at z   : the pass covers indices below  z + kEndLag[stage][kernel]
 //   a START cut at z  : the pass covers indices from   z - kStartLag[stage][kernel]
@@ -472,10 +475,10 @@ struct ZCut { int kind; int z; };
 //                                   SCAL XY  Z  EDGE FACE UPDATE
 const int kEndLag[2][K_COUNT]   = { { 6,  6,  5,  5,  5,  4 },     // first of two stages
                                     { 3,  2,  1,  1,  1,  0 } };   // last stage
-const int kStartLag[2][K_COUNT] = { { 4,  4,  4,  4,  3,  3 },
+const int kStartLag[2][K_COUNT] = { { 5,  4,  4,  4,  3,  3 },
                                     { 2,  1,  1,  1,  0,  0 } };
 /// input levels a pass needs beyond an END cut / before a START cut
-constexpr int kEndReach = 6, kStartReach = 4;
+constexpr int kEndReach = 6, kStartReach = 5;
 
 int cut_index(const ZCut& c, int row, KernelId id)
 { return (c.kind == CUT_END) ? c.z + kEndLag[row][id] : c.z - kStartLag[row][id]; }
@@ -491,10 +494,14 @@ ZClip pass_clip(const ZCut& lo, const ZCut& hi, int row, KernelId id)
 
 /// the stage loop of EnzoMethodMHDVlct::compute on device pointers, restricted
 /// to the pass between two cuts (CUT_NONE on both sides = the whole block)
+/// fold_cfl: the last stage's update also evaluates the next cycle's
+/// timestep() (launch_update / CflFold): "pressure" is written and the CFL
+/// minimum of the levels this pass finishes is folded into h->d_dt_bits (reset
+/// by the pass that sets the step parameters, i.e. the first one of a step).
 int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
                       double dt, const double* dt_dev, cudaStream_t st,
                       ZCut zlo = ZCut{ CUT_NONE, 0 }, ZCut zhi = ZCut{ CUT_NONE, 0 },
-                      bool set_step_params = true)
+                      bool set_step_params = true, bool fold_cfl = false)
 {
   const Params& P = h->P;
   const State ext = state_of(h, b);
@@ -509,6 +516,14 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
   if (set_step_params)
     launch_step_params(LaunchCtx{ st, &h->launches, &h->prof }, dt_dev, dt, nstages,
                        width, h->d_step);
+  if (fold_cfl && G.nrep != 1)
+    return fail(h, VLCT_ERR_INTERNAL, "the CFL fold handles single blocks only");
+  if (fold_cfl && set_step_params)
+    launch_timestep_reset(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits);
+  CflFold cfl;
+  cfl.pressure = b->pressure;
+  cfl.dt_bits = h->d_dt_bits;
+  cfl.width[0] = b->dx; cfl.width[1] = b->dy; cfl.width[2] = b->dz;
   int stale = 0;
   for (int stage = 0; stage < nstages; stage++) {
     const bool final_stage = (stage + 1) == nstages;
@@ -525,11 +540,12 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     const long long mask = h->debug_kernel_mask;
     const ZClip nothing{ 0, 0 };
     if (mask & (1 << K_SCAL))
-      launch_primitives(ctx, P, G, cur, h->S, stale, pass_clip(zlo, zhi, row, K_SCAL));
+      launch_primitives(ctx, P, G, cur, h->S, stage, stale,
+                        pass_clip(zlo, zhi, row, K_SCAL));
     const int cs = stale + immediate_staling(recon);
     for (int dim = 0; dim < 3; dim++)
       if (mask & (1 << (dim == 2 ? K_FLUX_Z : K_FLUX_XY)))
-        launch_flux(ctx, P, G, dim, recon, cur, h->S, bi_cur, cs,
+        launch_flux(ctx, P, G, dim, recon, cur, h->S, stage, bi_cur, cs,
                     pass_clip(zlo, zhi, row, dim == 2 ? K_FLUX_Z : K_FLUX_XY));
     if (P.mhd)
       launch_ct(ctx, P, G, cur, h->S, bi, bi_out, step_params, cs,
@@ -541,7 +557,8 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
                          accel[0] != nullptr;
     if (mask & (1 << K_UPDATE))
       launch_update(ctx, P, G, ext, cur, out, h->S, bi_out, accel, gravity,
-                    step_params, cs, pass_clip(zlo, zhi, row, K_UPDATE));
+                    step_params, stage, recon, cs, pass_clip(zlo, zhi, row, K_UPDATE),
+                    (fold_cfl && final_stage) ? &cfl : nullptr);
     stale += total_staling(recon);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -600,6 +617,7 @@ int vlct_create(const vlct_config* cfg, vlct_handle** out)
     P.igm1 = one / gm1;
   }
   P.nsc = cfg->n_passive;
+  P.nsc_flux = 0;          // option "scalar_flux_arrays"
   P.riemann = cfg->riemann_solver;
   P.recon = cfg->reconstruct_method;
 
@@ -691,12 +709,10 @@ int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* 
       // nothing new below the cut yet: keep uploading
       if (cut.z <= (prev.kind == CUT_END ? prev.z : 0)) continue;
     }
-    if ((rc = compute_on_device(h, dev, G, dt, dt_dev, st, prev, cut, first)) != VLCT_OK)
+    if ((rc = compute_on_device(h, dev, G, dt, dt_dev, st, prev, cut, first,
+                                fused_timestep)) != VLCT_OK)
       return rc;
     const int done = (cut.kind == CUT_END) ? cut.z : (1 << 30);
-    if (fused_timestep &&
-        (rc = timestep_launch(h, dev, G, st, ZClip{ downloaded, done }, first)) != VLCT_OK)
-      return rc;
     first = false;
     if (staged) {
       cudaEvent_t ev;
@@ -718,16 +734,19 @@ int compute_in_passes(vlct_handle* h, const vlct_block* host, const vlct_block* 
 
 /// dt_next != nullptr: vlct_compute_and_timestep
 int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* dt_dev,
-                  double* dt_next = nullptr)
+                  double* dt_next = nullptr, double* dt_next_dev = nullptr)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
   DeviceGuard device_guard__(h->device);
   if (h->device < 0) return fail(h, VLCT_ERR_NO_DEVICE, "handle has no device");
   int rc = check_block(h, b, false);
   if (rc != VLCT_OK) return rc;
-  const bool fused = (dt_next != nullptr);
+  const bool fused = (dt_next != nullptr || dt_next_dev != nullptr);
   if (fused && b->pressure == nullptr)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "\"pressure\" must be a permanent field");
+  if (dt_next_dev != nullptr && b->mem_space != VLCT_MEM_DEVICE)
+    return fail(h, VLCT_ERR_INVALID_BLOCK,
+                "vlct_compute_and_timestep_dev needs a block in device memory");
   const Geom G = geom_of(b);
   if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
   // the fused call ends like vlct_timestep: the minimum comes back to the host
@@ -745,11 +764,17 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
     if (h->device_pipeline_levels > 0 && h->cfg.time_scheme != VLCT_TIME_EULER)
       rc = compute_in_passes(h, nullptr, b, G, dt, dt_dev, st,
                              (int) h->device_pipeline_levels, fused);
-    else {
-      rc = compute_on_device(h, b, G, dt, dt_dev, st);
-      if (rc == VLCT_OK && fused) rc = timestep_launch(h, b, G, st, kNoClip, true);
+    else
+      rc = compute_on_device(h, b, G, dt, dt_dev, st, ZCut{ CUT_NONE, 0 },
+                             ZCut{ CUT_NONE, 0 }, true, fused);
+    if (rc == VLCT_OK && dt_next_dev != nullptr) {
+      // courant * minimum, left on the device: nothing waits for the host
+      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+                       h->cfg.courant, dt_next_dev);
+      CUDA_TRY(h, cudaGetLastError());
+    } else if (rc == VLCT_OK && fused) {
+      rc = finish_dt(st);
     }
-    if (rc == VLCT_OK && fused) rc = finish_dt(st);
     return rc;
   }
   if (dt_dev != nullptr)
@@ -763,9 +788,8 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
     rc = compute_in_passes(h, b, &h->mirror, G, dt, nullptr, st, levels, fused);
   } else {
     if ((rc = mirror_copy(h, b, G, st, true, COPY_COMPUTE_IN)) != VLCT_OK) return rc;
-    if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st)) != VLCT_OK) return rc;
-    if (fused && (rc = timestep_launch(h, &h->mirror, G, st, kNoClip, true)) != VLCT_OK)
-      return rc;
+    if ((rc = compute_on_device(h, &h->mirror, G, dt, nullptr, st, ZCut{ CUT_NONE, 0 },
+                                ZCut{ CUT_NONE, 0 }, true, fused)) != VLCT_OK) return rc;
     if ((rc = mirror_copy(h, b, G, st, false,
                           fused ? COPY_FUSED_OUT : COPY_COMPUTE_OUT)) != VLCT_OK) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -859,6 +883,14 @@ int vlct_compute_and_timestep(vlct_handle* h, const vlct_block* b, double dt,
   if (h != nullptr && dt_next == nullptr)
     return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_next is NULL");
   return compute_entry(h, b, dt, nullptr, dt_next);
+}
+
+int vlct_compute_and_timestep_dev(vlct_handle* h, const vlct_block* b,
+                                  const double* dt_device, double* dt_next_device)
+{
+  if (h != nullptr && (dt_device == nullptr || dt_next_device == nullptr))
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_device / dt_next_device is NULL");
+  return compute_entry(h, b, 0.0, dt_device, nullptr, dt_next_device);
 }
 
 int vlct_compute_dev(vlct_handle* h, const vlct_block* b, const double* dt_device)
@@ -1234,7 +1266,15 @@ int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
     const FluxSet& F = h->S.flux[d];
     const double* arrays[VLCT_FLUX_FIELDS] = { F.rho, F.mx_, F.my_, F.mz_, F.e,
                                                h->P.de ? F.eint : nullptr };
-    for (int s = 0; s < h->P.nsc; s++) arrays[6 + s] = F.sc[s];
+    if (h->P.nsc > 0 && h->P.nsc_flux == 0) {
+      for (int s = 0; s < h->P.nsc; s++)
+        for (int side = 0; side < 2; side++)
+          if (out->face[d][side][6 + s] != nullptr)
+            return fail(h, VLCT_ERR_INVALID_CONFIG,
+                        "passive-scalar face fluxes need the option "
+                        "\"scalar_flux_arrays\" = 1 (set before vlct_compute)");
+    }
+    for (int s = 0; s < h->P.nsc_flux; s++) arrays[6 + s] = F.sc[s];
     const int a0 = (d == 0) ? 1 : 0, a1 = (d == 2) ? 1 : 2;
     const size_t cnt = (size_t) n[a0] * n[a1];
     for (int f = 0; f < 6 + h->P.nsc; f++) {
@@ -1489,6 +1529,20 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
   } else if (strcmp(key, "batch_max_blocks") == 0) {
     if (value < 1) return fail(h, VLCT_ERR_INVALID_CONFIG, "batch_max_blocks >= 1");
     h->batch_max_blocks = value;
+  } else if (strcmp(key, "scalar_flux_arrays") == 0) {
+    const int want = (value != 0) ? h->P.nsc : 0;
+    if (want != h->P.nsc_flux) {
+      h->P.nsc_flux = want;
+      if (h->G.mx != 0) {      // the scratch layout changes: rebuild it lazily
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        for (void* p : h->allocations) cudaFree(p);
+        h->allocations.clear();
+        h->scratch_bytes = 0;
+        h->G = Geom{0, 0, 0};
+        h->scratch_levels = 0;
+        h->stepped = false;
+      }
+    }
   } else if (strcmp(key, "debug_kernel_mask") == 0) {
     h->debug_kernel_mask = value;
   } else if (strcmp(key, "device_pipeline_levels") == 0) {
@@ -1500,8 +1554,33 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
   return VLCT_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int compute_dev_part(vlct_handle* h, const vlct_block* b, const double* dt_device,
+                     int part, int z_lo, int z_hi, double* dt_next_device);
+}
+
+extern "C" {
+
 int vlct_compute_dev_part(vlct_handle* h, const vlct_block* b,
                           const double* dt_device, int part, int z_lo, int z_hi)
+{ return compute_dev_part(h, b, dt_device, part, z_lo, z_hi, nullptr); }
+
+int vlct_compute_and_timestep_dev_part(vlct_handle* h, const vlct_block* b,
+                                       const double* dt_device, int part, int z_lo,
+                                       int z_hi, double* dt_next_device)
+{
+  if (h != nullptr && dt_next_device == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "dt_next_device is NULL");
+  return compute_dev_part(h, b, dt_device, part, z_lo, z_hi, dt_next_device);
+}
+
+}  // extern "C"
+
+namespace {
+int compute_dev_part(vlct_handle* h, const vlct_block* b, const double* dt_device,
+                     int part, int z_lo, int z_hi, double* dt_next_device)
 {
   if (h == nullptr) return VLCT_ERR_INVALID_CONFIG;
   DeviceGuard device_guard__(h->device);
@@ -1524,14 +1603,32 @@ int vlct_compute_dev_part(vlct_handle* h, const vlct_block* b,
                 z_lo, z_hi, kStartReach, kEndReach);
   if ((rc = ensure_scratch(h, G)) != VLCT_OK) return rc;
   cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
+  const bool fold = (dt_next_device != nullptr);
+  if (fold && b->pressure == nullptr)
+    return fail(h, VLCT_ERR_INVALID_BLOCK, "\"pressure\" must be a permanent field");
   const ZCut none{ CUT_NONE, 0 }, start{ CUT_START, z_lo }, end{ CUT_END, z_hi };
   switch (part) {
-  case VLCT_PART_INTERIOR: return compute_on_device(h, b, G, 0.0, dt_device, st, start, end, true);
-  case VLCT_PART_LOWER:    return compute_on_device(h, b, G, 0.0, dt_device, st, none, start, false);
-  case VLCT_PART_UPPER:    return compute_on_device(h, b, G, 0.0, dt_device, st, end, none, false);
+  case VLCT_PART_INTERIOR:
+    return compute_on_device(h, b, G, 0.0, dt_device, st, start, end, true, fold);
+  case VLCT_PART_LOWER:
+    return compute_on_device(h, b, G, 0.0, dt_device, st, none, start, false, fold);
+  case VLCT_PART_UPPER:
+    rc = compute_on_device(h, b, G, 0.0, dt_device, st, end, none, false, fold);
+    if (rc == VLCT_OK && fold) {
+      // the three parts are done (INTERIOR, LOWER, UPPER, in this order): the
+      // minimum is complete
+      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+                       h->cfg.courant, dt_next_device);
+      CUDA_TRY(h, cudaGetLastError());
+    }
+    return rc;
   default: return fail(h, VLCT_ERR_INVALID_BLOCK, "unknown part %d", part);
   }
 }
+}  // namespace
+
+extern "C" {
+
 
 const char* vlct_last_error(const vlct_handle* h)
 { return h ? h->last_error.c_str() : "NULL handle"; }

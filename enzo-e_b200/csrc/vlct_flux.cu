@@ -160,7 +160,7 @@ solve_and_store(const Params& P, const double* wl_, const double* wr_,
     F.eint[c] = f.eint;
     F.vbar[c] = f.vbar;
   }
-  for (int s = 0; s < P.nsc; s++) {
+  for (int s = 0; s < P.nsc_flux; s++) {
     double sl, sr;
     recon_pair<RECON>(spec.p[s], c, sd, P.theta, sl, sr);
     F.sc[s][c] = passive_flux(sl, sr, f.rho);
@@ -550,14 +550,14 @@ void flux_recon(const FluxLaunch& L, int recon, int solver, bool de)
 }  // namespace
 
 void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
-                 int recon, const State& cur, const Scratch& S,
+                 int recon, const State& cur, const Scratch& S, int stage,
                  const FaceB& bi_cur, int cs, ZClip zc)
 {
   // non-stale faces: [cs, f-cs) on every axis of the face-shaped array
   Box box = full_box(G, cs);
   box.hi[dim] -= 1;
   if (!clip_z(box, zc)) return;
-  FluxLaunch L{ ctx.st, P, G, cur, scalar_ptrs(S.prim_sc, P.nsc),
+  FluxLaunch L{ ctx.st, P, G, cur, scalar_ptrs(S.prim_sc[stage], P.nsc_flux),
                 P.mhd ? bi_cur.bi[dim] : nullptr, S.flux[dim], box };
   const bool de = P.de != 0;
   static const char* const names[2][3] = {

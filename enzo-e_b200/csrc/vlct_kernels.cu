@@ -297,6 +297,18 @@ struct UpdateArgs {
   const double* sp;          // dt/dx, dt/dy, dt/dz, dt of the stage
   int gravity;
   Box inner;                 // [s+1, m-s-1)^3: conserved update + floors
+  // passive scalars without flux arrays (Params::nsc_flux == 0): specific
+  // scalars of the stage's input state, the stage's reconstruction
+  const double* spec[kMaxPassive];
+  int recon;
+  int scalars_elsewhere;     // 1: k_scalar_update advances the scalars (single block)
+  // CFL fold (last stage of vlct_compute_and_timestep*): the timestep() of the
+  // NEXT cycle is evaluated on the freshly updated cells while they are still
+  // in registers; the cells this kernel does not update go through
+  // k_timestep_boxes
+  double* pressure;          // the "pressure" field (written for every updated cell)
+  unsigned long long* dt_bits;
+  double dx, dy, dz;
 };
 
 template <bool DE, bool MHD>
@@ -334,17 +346,84 @@ floor_energy_and_sync(const Params& P, double rho, double vx, double vy,
   }
 }
 
-template <bool MHD, bool DE, bool STACKED>
+/// What EnzoMethodMHDVlct::timestep does with one cell
+/// (EnzoMethodMHDVlct.cpp:551-588, EnzoMHDIntegratorStageCommands.cpp:299-366):
+/// dual-energy sync (rewrites etot / eint), pressure, local CFL limit.
+template <bool MHD, bool DE>
+__device__ __forceinline__ double
+timestep_of_cell(const Params& P, double rho, double vx, double vy, double vz,
+                 double bx, double by, double bz, double& etot, double& eint,
+                 double dx, double dy, double dz, double& p)
+{
+  if (DE) {
+    floor_energy_and_sync<true, MHD>(P, rho, vx, vy, vz, bx, by, bz, etot, eint);
+    p = (P.gamma - 1.0) * rho * eint;
+  } else {
+    const double ke = 0.5 * (vx * vx + vy * vy + vz * vz);
+    double me_den = 0.;
+    if (MHD) me_den = 0.5 * (bx * bx + by * by + bz * bz);
+    p = (P.gamma - 1.0) * (rho * (etot - ke) - me_den);
+  }
+  double cs;
+  ExactOps op;   // HBM-bound kernels: the built-in operators are fine here
+  if (MHD) cs = eos_cfast_max(op, P.gamma, rho, p, bx, by, bz);
+  else     cs = sqrt(eos_cs2(op, P.gamma, rho, p));
+  return min3(dx / (fabs(vx) + cs), dy / (fabs(vy) + cs), dz / (fabs(vz) + cs));
+}
+
+/// minimum over the block (warp shuffles, then one atomicMin per block).
+/// Non-negative doubles order like their bit patterns; NaNs compare above +inf
+/// and so never win, which matches std::min(dtBaryons, local_dt) keeping the
+/// old value. Every thread of the block must call this.
+__device__ __forceinline__ void block_min_to(unsigned long long* dt_bits, double local_min)
+{
+  unsigned long long bits = (unsigned long long) __double_as_longlong(local_min);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
+    bits = (other < bits) ? other : bits;
+  }
+  __shared__ unsigned long long warp_min[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_min[warp] = bits;
+  __syncthreads();
+  if (warp == 0) {
+    bits = (lane < (int) ((blockDim.x + 31) >> 5)) ? warp_min[lane]
+                                                     : 0x7fefffffffffffffULL;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
+      bits = (other < bits) ? other : bits;
+    }
+    if (lane == 0) atomicMin(dt_bits, bits);
+  }
+}
+
+// SCAL: the kernel advances the passive scalars itself (stacked batches, or
+// scalar flux arrays); otherwise k_scalar_update does, or there are none --
+// and the scalar code with its registers is compiled out
+template <bool MHD, bool DE, bool STACKED, bool CFL, bool SCAL>
 __global__ void __launch_bounds__(kBlock)
 k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateArgs A,
          const Box box)
 {
-  VLCT_THREAD_IN_BOX(G, box, i, j, kl, k);
+  // (with the CFL fold every thread of the block reaches the block-wide
+  // minimum at the end, so nothing returns early)
+  const unsigned nxb = box.hi[0] - box.lo[0];
+  const unsigned t = blockIdx.x * kBlock + threadIdx.x;
+  bool active = t < nxb * (unsigned) (box.hi[1] - box.lo[1]);
+  if (!CFL && !active) return;
+  const int i = box.lo[0] + (int) (t % nxb);
+  const int j = active ? box.lo[1] + (int) (t / nxb) : box.lo[1];
+  int kl, k;
+  if constexpr (STACKED) unstack(G, box, blockIdx.y, kl, k);
+  else kl = k = box.lo[2] + (int) blockIdx.y;
   const size_t c = cidx(G, k, j, i);
   const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
+  double local_dt = DBL_MAX;
 
   double bx = 0., by = 0., bz = 0.;
-  if (MHD) {
+  if (MHD && active) {
     bx = 0.5 * (__ldg(A.bi_out[0] + fidx(G, 0, k, j, i)) +
                 __ldg(A.bi_out[0] + fidx(G, 0, k, j, i + 1)));
     by = 0.5 * (__ldg(A.bi_out[1] + fidx(G, 1, k, j, i)) +
@@ -358,11 +437,14 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
 
   const Box& in = A.inner;
   if (i < in.lo[0] || i >= in.hi[0] || j < in.lo[1] || j >= in.hi[1] ||
-      kl < in.lo[2] || kl >= in.hi[2]) return;
+      kl < in.lo[2] || kl >= in.hi[2]) active = false;
+  if (!CFL && !active) return;
 
+  if (active) {
   const double dtd[3] = { __ldg(A.sp), __ldg(A.sp + 1), __ldg(A.sp + 2) };
   // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
   double d_rho = 0., d_mx = 0., d_my = 0., d_mz = 0., d_e = 0., d_eint = 0.;
+  double frho_c[3], frho_l[3];   // density fluxes (the scalars' upwinding needs them)
   double p_floored = 0.;
   if (DE) {
     // cell-centred primitive pressure of the current stage
@@ -375,7 +457,9 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
     const FluxSet& F = A.flux[d];
     const size_t l = c - st[d];
     const double dtdx = dtd[d];
-    d_rho -= dtdx * (__ldg(F.rho + c) - __ldg(F.rho + l));
+    frho_c[d] = __ldg(F.rho + c);
+    frho_l[d] = __ldg(F.rho + l);
+    d_rho -= dtdx * (frho_c[d] - frho_l[d]);
     d_mx -= dtdx * (__ldg(F.mx_ + c) - __ldg(F.mx_ + l));
     d_my -= dtdx * (__ldg(F.my_ + c) - __ldg(F.my_ + l));
     d_mz -= dtdx * (__ldg(F.mz_ + c) - __ldg(F.mz_ + l));
@@ -400,14 +484,61 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
   }
 
   // passive scalars (conserved form)
-  for (int s = 0; s < P.nsc; s++) {
-    double d_s = 0.;
+  if (!SCAL) {
+    // none, or k_scalar_update (a z-marching kernel of its own) does them
+  } else if (P.nsc_flux > 0) {
+    for (int s = 0; s < P.nsc; s++) {
+      double d_s = 0.;
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      const double* Fs = A.flux[d].sc[s];
-      d_s -= dtd[d] * (__ldg(Fs + c) - __ldg(Fs + c - st[d]));
+      for (int d = 0; d < 3; d++) {
+        const double* Fs = A.flux[d].sc[s];
+        d_s -= dtd[d] * (__ldg(Fs + c) - __ldg(Fs + c - st[d]));
+      }
+      A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
     }
-    A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
+  } else {
+    // The scalar fluxes through the cell's two faces per direction, formed
+    // here as the sweeps would (reconstruct the specific scalar on both sides
+    // of a face, upwind by the sign of the density flux, times the density
+    // flux: EnzoReconstructor*, riemann/EnzoRiemannUtils.hpp:224-249,267-314)
+    // instead of being written by three sweeps and read back: 13 specific
+    // values (mostly L1 / L2 hits) replace 3 stores and 6 loads per scalar,
+    // and the sweeps carry no scalar work at all. Same expressions, same bits.
+    const bool nn = (A.recon == VLCT_RECON_NN);
+    const bool athena = (A.recon == VLCT_RECON_PLM_ATHENA);
+    for (int s = 0; s < P.nsc; s++) {
+      const double* const q = A.spec[s] + c;
+      const double w0 = __ldg(q);
+      double d_s = 0.;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const ptrdiff_t sd = st[d];
+        const double wm1 = __ldg(q - sd), wp1 = __ldg(q + sd);
+        double sl_c, sr_c, sl_l, sr_l;   // L / R states at the upper and the lower face
+        if (nn) {
+          sl_l = wm1; sr_l = w0; sl_c = w0; sr_c = wp1;
+        } else {
+          const double wm2 = __ldg(q - 2 * sd), wp2 = __ldg(q + 2 * sd);
+          double dm, d0, dp;
+          if (athena) {
+            dm = limiter_athena(wm2, wm1, w0);
+            d0 = limiter_athena(wm1, w0, wp1);
+            dp = limiter_athena(w0, wp1, wp2);
+          } else {
+            dm = limiter_enzo(wm2, wm1, w0, P.theta);
+            d0 = limiter_enzo(wm1, w0, wp1, P.theta);
+            dp = limiter_enzo(w0, wp1, wp2, P.theta);
+          }
+          sl_l = wm1 + dm * 0.5;
+          sr_l = w0 - d0 * 0.5;
+          sl_c = w0 + d0 * 0.5;
+          sr_c = wp1 - dp * 0.5;
+        }
+        d_s -= dtd[d] * (passive_flux(sl_c, sr_c, frho_c[d]) -
+                         passive_flux(sl_l, sr_l, frho_l[d]));
+      }
+      A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
+    }
   }
 
   double new_rho = old_rho + d_rho;
@@ -422,18 +553,163 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
 
   floor_energy_and_sync<DE, MHD>(P, new_rho, vx, vy, vz, bx, by, bz, etot, eint);
 
+  if (CFL) {
+    // timestep() of the next cycle on this cell: a second dual-energy sync
+    // (what timestep() does to the field compute() left), "pressure", CFL
+    double p;
+    local_dt = timestep_of_cell<MHD, DE>(P, new_rho, vx, vy, vz, bx, by, bz, etot, eint,
+                                         A.dx, A.dy, A.dz, p);
+    A.pressure[c] = p;
+  }
+
   A.out.rho[c] = new_rho;
   A.out.vx[c] = vx;
   A.out.vy[c] = vy;
   A.out.vz[c] = vz;
   A.out.etot[c] = etot;
   if (DE) A.out.eint[c] = eint;
+  }
+  if (CFL) block_min_to(A.dt_bits, local_dt);
+}
+
+// ---------------------------------------------------------------------------
+// passive scalars without flux arrays, single block: one thread = one scalar
+// of one (x, y) column, marching along z
+// ---------------------------------------------------------------------------
+// Per face the sweeps of the reference reconstruct the specific scalar on both
+// sides, upwind by the sign of the density flux and multiply by it
+// (EnzoReconstructor*, riemann/EnzoRiemannUtils.hpp:224-249,267-314), and the
+// update takes the divergence of those fluxes (EnzoIntegrationQuanUpdate.cpp).
+// Here a thread does exactly that for the six faces of its cell, level after
+// level: the five z neighbours and the z slopes roll through registers (each
+// specific value crosses L2 once for the z direction, each z slope is evaluated
+// once), the x neighbours are L1 hits, the y neighbours L1 / L2 hits, and the
+// four blocks that work on the four scalars of a tile run side by side, so the
+// density fluxes they share are L2 hits. Nothing but the scalars' own arrays
+// and the density fluxes is touched: 3 + 3/nsc doubles per scalar and cell,
+// where flux arrays written by the sweeps cost 14. Same expressions in the
+// same order as the sweeps + update: bit-identical.
+struct ScalarArgs {
+  const double* spec[kMaxPassive];   // specific scalars of the stage's input
+  const double* u0[kMaxPassive];     // conserved scalars at the start of the step
+  double* out[kMaxPassive];
+  const double* frho[3];             // density fluxes of the three sweeps
+  const double* sp;                  // dt/dx, dt/dy, dt/dz of the stage
+  double theta;
+  int nsc;
+};
+constexpr int kScalarRows = 4;       // 32 x 4 columns per block
+
+template <int RECON>
+__device__ __forceinline__ double scalar_slope(double a, double b, double c, double theta)
+{ return limited_slope<RECON>(a, b, c, theta); }
+
+template <int RECON>
+__global__ void __launch_bounds__(32 * kScalarRows)
+k_scalar_update(const __grid_constant__ ScalarArgs A, const GeomLite G, const Box box,
+                const int chunk)
+{
+  constexpr bool PLM = (RECON != RECON_NN);
+  const int s = (int) (blockIdx.x % (unsigned) A.nsc);
+  const int i = box.lo[0] + (int) (blockIdx.x / (unsigned) A.nsc) * 32 + (int) (threadIdx.x & 31);
+  const int j = box.lo[1] + (int) blockIdx.y * kScalarRows + (int) (threadIdx.x >> 5);
+  if (i >= box.hi[0] || j >= box.hi[1]) return;
+  const int k0 = box.lo[2] + (int) blockIdx.z * chunk;
+  const int k1 = min(k0 + chunk, box.hi[2]);
+  const ptrdiff_t Y = (ptrdiff_t) G.mx, Z = (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
+  const double theta = A.theta;
+  const double dtdx = __ldg(A.sp), dtdy = __ldg(A.sp + 1), dtdz = __ldg(A.sp + 2);
+  size_t c = cidx(G, k0, j, i);
+  const double* __restrict__ q = A.spec[s];
+  const double* __restrict__ u0 = A.u0[s];
+  double* __restrict__ out = A.out[s];
+  const double* __restrict__ fx = A.frho[0];
+  const double* __restrict__ fy = A.frho[1];
+  const double* __restrict__ fz = A.frho[2];
+
+  // the z window: values at k-2 .. k+1, slopes at k-1 and k, flux at the lower face
+  double wm2 = 0., wm1 = __ldg(q + c - Z), w0 = __ldg(q + c), wp1 = __ldg(q + c + Z);
+  double dm = 0., d0 = 0.;
+  if (PLM) {
+    wm2 = __ldg(q + c - 2 * Z);
+    dm = scalar_slope<RECON>(wm2, wm1, w0, theta);
+    d0 = scalar_slope<RECON>(wm1, w0, wp1, theta);
+  }
+  double fz_l = __ldg(fz + c - Z);
+#pragma unroll 1
+  for (int k = k0; k < k1; k++, c += Z) {
+    double d_s = 0.;
+    {   // x faces
+      const double xm1 = __ldg(q + c - 1), xp1 = __ldg(q + c + 1);
+      double sl_l = xm1, sr_l = w0, sl_c = w0, sr_c = xp1;
+      if (PLM) {
+        const double xm2 = __ldg(q + c - 2), xp2 = __ldg(q + c + 2);
+        const double a = scalar_slope<RECON>(xm2, xm1, w0, theta);
+        const double b = scalar_slope<RECON>(xm1, w0, xp1, theta);
+        const double e = scalar_slope<RECON>(w0, xp1, xp2, theta);
+        sl_l = xm1 + a * 0.5; sr_l = w0 - b * 0.5;
+        sl_c = w0 + b * 0.5;  sr_c = xp1 - e * 0.5;
+      }
+      d_s -= dtdx * (passive_flux(sl_c, sr_c, __ldg(fx + c)) -
+                     passive_flux(sl_l, sr_l, __ldg(fx + c - 1)));
+    }
+    {   // y faces
+      const double ym1 = __ldg(q + c - Y), yp1 = __ldg(q + c + Y);
+      double sl_l = ym1, sr_l = w0, sl_c = w0, sr_c = yp1;
+      if (PLM) {
+        const double ym2 = __ldg(q + c - 2 * Y), yp2 = __ldg(q + c + 2 * Y);
+        const double a = scalar_slope<RECON>(ym2, ym1, w0, theta);
+        const double b = scalar_slope<RECON>(ym1, w0, yp1, theta);
+        const double e = scalar_slope<RECON>(w0, yp1, yp2, theta);
+        sl_l = ym1 + a * 0.5; sr_l = w0 - b * 0.5;
+        sl_c = w0 + b * 0.5;  sr_c = yp1 - e * 0.5;
+      }
+      d_s -= dtdy * (passive_flux(sl_c, sr_c, __ldg(fy + c)) -
+                     passive_flux(sl_l, sr_l, __ldg(fy + c - Y)));
+    }
+    double wp2 = 0., dp = 0.;
+    {   // z faces: the window
+      double sl_l = wm1, sr_l = w0, sl_c = w0, sr_c = wp1;
+      if (PLM) {
+        wp2 = __ldg(q + c + 2 * Z);
+        dp = scalar_slope<RECON>(w0, wp1, wp2, theta);
+        sl_l = wm1 + dm * 0.5; sr_l = w0 - d0 * 0.5;
+        sl_c = w0 + d0 * 0.5;  sr_c = wp1 - dp * 0.5;
+      }
+      const double fz_c = __ldg(fz + c);
+      d_s -= dtdz * (passive_flux(sl_c, sr_c, fz_c) - passive_flux(sl_l, sr_l, fz_l));
+      fz_l = fz_c;
+    }
+    out[c] = __ldg(u0 + c) + d_s;
+    // roll
+    wm2 = wm1; wm1 = w0; w0 = wp1;
+    if (PLM) { wp1 = wp2; dm = d0; d0 = dp; }
+    else if (k + 1 < k1) wp1 = __ldg(q + c + 2 * Z);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // timestep: hydro-mhd/EnzoMethodMHDVlct.cpp:551-588,
 //           hydro-mhd/EnzoMHDIntegratorStageCommands.cpp:299-366
 // ---------------------------------------------------------------------------
+template <bool MHD, bool DE>
+__device__ __forceinline__ double timestep_cell_at(const Params& P, const State& u,
+                                                   double* pressure, size_t c,
+                                                   double dx, double dy, double dz)
+{
+  const double rho = u.rho[c];
+  const double vx = u.vx[c], vy = u.vy[c], vz = u.vz[c];
+  double bx = 0., by = 0., bz = 0.;
+  if (MHD) { bx = u.bx[c]; by = u.by[c]; bz = u.bz[c]; }
+  double etot = u.etot[c], eint = 0., p;
+  if (DE) eint = u.eint[c];
+  const double local_dt = timestep_of_cell<MHD, DE>(P, rho, vx, vy, vz, bx, by, bz, etot,
+                                                    eint, dx, dy, dz, p);
+  if (DE) { u.etot[c] = etot; u.eint[c] = eint; }
+  pressure[c] = p;
+  return local_dt;
+}
+
 template <bool MHD, bool DE>
 __global__ void __launch_bounds__(256)
 k_timestep(const Params P, const Geom G, const State u, double* pressure,
@@ -445,56 +721,35 @@ k_timestep(const Params P, const Geom G, const State u, double* pressure,
   const size_t n = c_end + shift;
   double local_min = DBL_MAX;
   for (size_t c = c_begin + shift + (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-       c < n; c += (size_t) gridDim.x * blockDim.x) {
-    const double rho = u.rho[c];
-    const double vx = u.vx[c], vy = u.vy[c], vz = u.vz[c];
-    double bx = 0., by = 0., bz = 0.;
-    if (MHD) { bx = u.bx[c]; by = u.by[c]; bz = u.bz[c]; }
-    double p;
-    if (DE) {
-      double etot = u.etot[c], eint = u.eint[c];
-      floor_energy_and_sync<true, MHD>(P, rho, vx, vy, vz, bx, by, bz, etot, eint);
-      u.etot[c] = etot;
-      u.eint[c] = eint;
-      p = (P.gamma - 1.0) * rho * eint;
-    } else {
-      const double ke = 0.5 * (vx * vx + vy * vy + vz * vz);
-      double me_den = 0.;
-      if (MHD) me_den = 0.5 * (bx * bx + by * by + bz * bz);
-      p = (P.gamma - 1.0) * (rho * (u.etot[c] - ke) - me_den);
-    }
-    pressure[c] = p;
-    double cs;
-    ExactOps op;   // HBM-bound kernel: the built-in operators are fine here
-    if (MHD) cs = eos_cfast_max(op, P.gamma, rho, p, bx, by, bz);
-    else     cs = sqrt(eos_cs2(op, P.gamma, rho, p));
-    const double local_dt = min3(dx / (fabs(vx) + cs), dy / (fabs(vy) + cs),
-                                 dz / (fabs(vz) + cs));
-    local_min = std_min(local_min, local_dt);
+       c < n; c += (size_t) gridDim.x * blockDim.x)
+    local_min = std_min(local_min,
+                        timestep_cell_at<MHD, DE>(P, u, pressure, c, dx, dy, dz));
+  block_min_to(dt_bits, local_min);
+}
+
+/// the same over a list of boxes (blockIdx.y = box): the cells a CFL-folding
+/// update kernel did not touch -- the ghost shell around its inner box
+struct BoxList { Box b[6]; int count; };
+
+template <bool MHD, bool DE>
+__global__ void __launch_bounds__(256)
+k_timestep_boxes(const Params P, const GeomLite G, const State u, double* pressure,
+                 double dx, double dy, double dz, unsigned long long* dt_bits,
+                 const __grid_constant__ BoxList L)
+{
+  const Box& b = L.b[blockIdx.y];
+  const size_t nx = (size_t) (b.hi[0] - b.lo[0]), ny = (size_t) (b.hi[1] - b.lo[1]);
+  const size_t total = nx * ny * (size_t) (b.hi[2] - b.lo[2]);
+  double local_min = DBL_MAX;
+  for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t) gridDim.x * blockDim.x) {
+    const int i = b.lo[0] + (int) (t % nx);
+    const int j = b.lo[1] + (int) ((t / nx) % ny);
+    const int k = b.lo[2] + (int) (t / (nx * ny));
+    local_min = std_min(local_min, timestep_cell_at<MHD, DE>(P, u, pressure,
+                                                             cidx(G, k, j, i), dx, dy, dz));
   }
-  // warp-shuffle min, then one atomic per block. Non-negative doubles order
-  // like their bit patterns; NaNs compare above +inf and so never win, which
-  // matches std::min(dtBaryons, local_dt) keeping the old value.
-  unsigned long long bits = (unsigned long long) __double_as_longlong(local_min);
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
-    bits = (other < bits) ? other : bits;
-  }
-  __shared__ unsigned long long warp_min[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) warp_min[warp] = bits;
-  __syncthreads();
-  if (warp == 0) {
-    bits = (lane < (int) (blockDim.x >> 5)) ? warp_min[lane]
-                                            : 0x7fefffffffffffffULL;
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) {
-      const unsigned long long other = __shfl_down_sync(0xffffffffu, bits, off);
-      bits = (other < bits) ? other : bits;
-    }
-    if (lane == 0) atomicMin(dt_bits, bits);
-  }
+  block_min_to(dt_bits, local_min);
 }
 
 __global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
@@ -713,7 +968,7 @@ void Profiler::reset()
 // launchers
 // ---------------------------------------------------------------------------
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale, ZClip zc)
+                       const State& cur, const Scratch& S, int stage, int stale, ZClip zc)
 {
   if (P.nsc == 0) return;   // pressure is computed inside the flux kernels
   Box box = full_box(G, stale);
@@ -721,10 +976,10 @@ void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
   ScopedLaunch sl(ctx, "k_specific_scalars");
   if (G.nrep > 1)
     k_specific_scalars<true><<<grid_for(G, box), kBlock, 0, ctx.st>>>(
-        P.nsc, G, cur, scalar_ptrs(S.prim_sc, P.nsc), box);
+        P.nsc, G, cur, scalar_ptrs(S.prim_sc[stage], P.nsc), box);
   else
     k_specific_scalars<false><<<grid_for(G, box), kBlock, 0, ctx.st>>>(
-        P.nsc, lite(G), cur, scalar_ptrs(S.prim_sc, P.nsc), box);
+        P.nsc, lite(G), cur, scalar_ptrs(S.prim_sc[stage], P.nsc), box);
 }
 
 void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
@@ -786,7 +1041,8 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
                    const double* accel[3], bool gravity,
-                   const double* step_params, int s, ZClip zc)
+                   const double* step_params, int stage, int recon, int s, ZClip zc,
+                   const CflFold* cfl)
 {
   cudaStream_t st = ctx.st;
   UpdateArgs A;
@@ -801,24 +1057,113 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
   A.sp = step_params;
   A.gravity = gravity ? 1 : 0;
   A.inner = full_box(G, s + 1);
+  for (int n = 0; n < kMaxPassive; n++) A.spec[n] = (n < P.nsc) ? S.prim_sc[stage][n] : nullptr;
+  A.recon = recon;
+  // single blocks: the scalars get a z-marching kernel of their own
+  const bool scalar_kernel = (P.nsc > 0 && P.nsc_flux == 0 && G.nrep == 1);
+  A.scalars_elsewhere = scalar_kernel ? 1 : 0;
+  if (scalar_kernel) {
+    Box sbox = A.inner;
+    if (clip_z(sbox, zc)) {
+      ScalarArgs SA;
+      for (int n = 0; n < kMaxPassive; n++) {
+        SA.spec[n] = (n < P.nsc) ? S.prim_sc[stage][n] : nullptr;
+        SA.u0[n] = (n < P.nsc) ? u0.sc[n] : nullptr;
+        SA.out[n] = (n < P.nsc) ? out.sc[n] : nullptr;
+      }
+      for (int d = 0; d < 3; d++) SA.frho[d] = S.flux[d].rho;
+      SA.sp = step_params;
+      SA.theta = P.theta;
+      SA.nsc = P.nsc;
+      const int nz = sbox.hi[2] - sbox.lo[2];
+      int chunk = 64;
+      if (nz < 2 * chunk) chunk = nz;
+      const dim3 sgrid((unsigned) ((sbox.hi[0] - sbox.lo[0] + 31) / 32) * (unsigned) P.nsc,
+                       (unsigned) ((sbox.hi[1] - sbox.lo[1] + kScalarRows - 1) / kScalarRows),
+                       (unsigned) ((nz + chunk - 1) / chunk));
+      ScopedLaunch sl(ctx, recon == VLCT_RECON_NN ? "k_scalar_update_nn"
+                                                  : "k_scalar_update_plm");
+      const int threads = 32 * kScalarRows;
+      if (recon == VLCT_RECON_NN)
+        k_scalar_update<RECON_NN><<<sgrid, threads, 0, st>>>(SA, lite(G), sbox, chunk);
+      else if (recon == VLCT_RECON_PLM_ATHENA)
+        k_scalar_update<RECON_PLM_ATHENA><<<sgrid, threads, 0, st>>>(SA, lite(G), sbox, chunk);
+      else
+        k_scalar_update<RECON_PLM_ENZO><<<sgrid, threads, 0, st>>>(SA, lite(G), sbox, chunk);
+    }
+  }
+  A.pressure = cfl ? cfl->pressure : nullptr;
+  A.dt_bits = cfl ? cfl->dt_bits : nullptr;
+  A.dx = cfl ? cfl->width[0] : 0.; A.dy = cfl ? cfl->width[1] : 0.;
+  A.dz = cfl ? cfl->width[2] : 0.;
   // with CT the centred B is rewritten on the whole [s, m-s)^3 region
   Box box = P.mhd ? full_box(G, s) : A.inner;
-  if (!clip_z(box, zc)) return;
-  const int block = kBlock; const dim3 grid = grid_for(G, box);
-  ScopedLaunch sl(ctx, "k_update");
-#define VLCT_UPDATE(MHD_, DE_)                                                   \
+  if (clip_z(box, zc)) {
+    const int block = kBlock; const dim3 grid = grid_for(G, box);
+    ScopedLaunch sl(ctx, cfl ? "k_update_cfl" : "k_update");
+    const bool in_kernel_scalars = (P.nsc > 0 && !scalar_kernel);
+#define VLCT_UPDATE3(MHD_, DE_, CFL_, SCAL_)                                      \
   do {                                                                          \
-    if (G.nrep > 1) k_update<MHD_, DE_, true><<<grid, block, 0, st>>>(P, G, A, box);  \
-    else            k_update<MHD_, DE_, false><<<grid, block, 0, st>>>(P, lite(G), A, box); \
+    if (G.nrep > 1) k_update<MHD_, DE_, true, CFL_, SCAL_><<<grid, block, 0, st>>>(P, G, A, box);  \
+    else            k_update<MHD_, DE_, false, CFL_, SCAL_><<<grid, block, 0, st>>>(P, lite(G), A, box); \
   } while (0)
-  if (P.mhd) {
-    if (P.de) VLCT_UPDATE(true, true);
-    else      VLCT_UPDATE(true, false);
-  } else {
-    if (P.de) VLCT_UPDATE(false, true);
-    else      VLCT_UPDATE(false, false);
-  }
+#define VLCT_UPDATE2(MHD_, DE_, CFL_)                                             \
+  do { if (in_kernel_scalars) VLCT_UPDATE3(MHD_, DE_, CFL_, true);              \
+       else VLCT_UPDATE3(MHD_, DE_, CFL_, false); } while (0)
+#define VLCT_UPDATE(MHD_, DE_)                                                   \
+  do { if (cfl) VLCT_UPDATE2(MHD_, DE_, true); else VLCT_UPDATE2(MHD_, DE_, false); } while (0)
+    if (P.mhd) {
+      if (P.de) VLCT_UPDATE(true, true);
+      else      VLCT_UPDATE(true, false);
+    } else {
+      if (P.de) VLCT_UPDATE(false, true);
+      else      VLCT_UPDATE(false, false);
+    }
 #undef VLCT_UPDATE
+#undef VLCT_UPDATE2
+#undef VLCT_UPDATE3
+  }
+  if (cfl == nullptr) return;
+  // the cells of the levels [zc.lo, zc.hi) outside the inner box: up to six
+  // slabs (whole levels below / above, then y slabs, then x slabs)
+  const Box& in = A.inner;
+  const int zlo = zc.lo < 0 ? 0 : zc.lo, zhi = zc.hi > G.mz ? G.mz : zc.hi;
+  if (zhi <= zlo) return;
+  BoxList L;
+  L.count = 0;
+  auto add = [&](int x0, int x1, int y0, int y1, int z0, int z1) {
+    if (z0 < zlo) z0 = zlo;
+    if (z1 > zhi) z1 = zhi;
+    if (x1 <= x0 || y1 <= y0 || z1 <= z0) return;
+    Box b;
+    b.lo[0] = x0; b.hi[0] = x1; b.lo[1] = y0; b.hi[1] = y1; b.lo[2] = z0; b.hi[2] = z1;
+    L.b[L.count++] = b;
+  };
+  add(0, G.mx, 0, G.my, 0, in.lo[2]);
+  add(0, G.mx, 0, G.my, in.hi[2], G.mz);
+  add(0, G.mx, 0, in.lo[1], in.lo[2], in.hi[2]);
+  add(0, G.mx, in.hi[1], G.my, in.lo[2], in.hi[2]);
+  add(0, in.lo[0], in.lo[1], in.hi[1], in.lo[2], in.hi[2]);
+  add(in.hi[0], G.mx, in.lo[1], in.hi[1], in.lo[2], in.hi[2]);
+  if (L.count == 0) return;
+  size_t largest = 0;
+  for (int n = 0; n < L.count; n++) {
+    const Box& b = L.b[n];
+    const size_t cnt = (size_t) (b.hi[0] - b.lo[0]) * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    if (cnt > largest) largest = cnt;
+  }
+  int blocks_x = (int) ((largest + 255) / 256);
+  if (blocks_x > 148 * 4) blocks_x = 148 * 4;
+  const dim3 grid(blocks_x, L.count, 1);
+  const State u = out;
+  ScopedLaunch sl(ctx, "k_timestep_shell");
+  if (P.mhd) {
+    if (P.de) k_timestep_boxes<true, true><<<grid, 256, 0, st>>>(P, lite(G), u, cfl->pressure, cfl->width[0], cfl->width[1], cfl->width[2], cfl->dt_bits, L);
+    else      k_timestep_boxes<true, false><<<grid, 256, 0, st>>>(P, lite(G), u, cfl->pressure, cfl->width[0], cfl->width[1], cfl->width[2], cfl->dt_bits, L);
+  } else {
+    if (P.de) k_timestep_boxes<false, true><<<grid, 256, 0, st>>>(P, lite(G), u, cfl->pressure, cfl->width[0], cfl->width[1], cfl->width[2], cfl->dt_bits, L);
+    else      k_timestep_boxes<false, false><<<grid, 256, 0, st>>>(P, lite(G), u, cfl->pressure, cfl->width[0], cfl->width[1], cfl->width[2], cfl->dt_bits, L);
+  }
 }
 
 void launch_timestep_reset(const LaunchCtx& ctx, unsigned long long* dt_bits)

@@ -58,6 +58,12 @@ struct Params {
   double ggm1;          // (double)(float)(gamma*(gamma-1)), FluidProps.cpp:234
   double igm1;          // 1. / (gamma - 1.), HLLD.hpp:66 (IEEE, host-side)
   int nsc;
+  // Passive-scalar fluxes: by default they are never materialised -- the
+  // update kernel forms the two face fluxes of a cell per direction itself
+  // from the specific scalars and the density fluxes (same expressions, same
+  // bits). nsc_flux = nsc brings back the flux arrays written by the sweeps
+  // (handle option "scalar_flux_arrays"), which vlct_save_face_fluxes needs.
+  int nsc_flux;
   int mhd, de;
   int riemann, recon;
 };
@@ -66,7 +72,9 @@ struct Scratch {
   State temp;           // temp_integration_map
   FaceB tbi;            // temp_bfieldi_l_
   FluxSet flux[3];
-  double *prim_sc[kMaxPassive]; // specific passive scalars
+  // specific passive scalars of each stage's input state (one set per stage:
+  // the update of a stage reads them two levels behind the sweeps)
+  double *prim_sc[2][kMaxPassive];
   double *edge[3];      // edge-centred E (cell strides)
 };
 
@@ -107,12 +115,12 @@ constexpr ZClip kNoClip{ -(1 << 30), 1 << 30 };
 /// specific passive scalars over [s, m-s)^3 (no-op without scalars; the
 /// primitive pressure is computed on the fly by the flux kernels)
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
-                       const State& cur, const Scratch& S, int stale,
+                       const State& cur, const Scratch& S, int stage, int stale,
                        ZClip zc = kNoClip);
 
 /// reconstruct -> fix longitudinal B -> Riemann -> passive fluxes along dim
 void launch_flux(const LaunchCtx& ctx, const Params& P, const Geom& G, int dim,
-                 int recon, const State& cur, const Scratch& S,
+                 int recon, const State& cur, const Scratch& S, int stage,
                  const FaceB& bi_cur, int cur_stale, ZClip zc = kNoClip);
 
 /// constrained transport: edge E, face-B update
@@ -122,12 +130,24 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
                const FaceB& bi_out, const double* step_params, int stale,
                ZClip z_edge = kNoClip, ZClip z_face = kNoClip);
 
+/// CFL fold: the update of the LAST stage also evaluates the timestep() of the
+/// next cycle -- dual-energy sync, "pressure", CFL minimum into *dt_bits (see
+/// launch_timestep) -- on the cells it updates, from registers; the other cells
+/// of the clipped levels (the ghost shell, which compute() never updates) go
+/// through a small second launch. Single blocks only (Geom::nrep == 1).
+struct CflFold {
+  double* pressure;
+  unsigned long long* dt_bits;
+  double width[3];
+};
+
 /// centred B + flux divergence + sources + conserved update + floors/sync
 void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
                    const State& u0, const State& cur, const State& out,
                    const Scratch& S, const FaceB& bi_out,
                    const double* accel[3], bool gravity,
-                   const double* step_params, int stale, ZClip zc = kNoClip);
+                   const double* step_params, int stage, int recon, int stale,
+                   ZClip zc = kNoClip, const CflFold* cfl = nullptr);
 
 /// the per-stage constants of a step from a host or device dt (see k_step_params)
 void launch_step_params(const LaunchCtx& ctx, const double* dt_dev, double dt_host,

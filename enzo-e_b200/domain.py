@@ -211,10 +211,13 @@ class Domain:
         if self.boundaries:
             self.apply_boundaries(method, block, *pending[6])
 
-    def step(self, method, block, dt, overlap=True):
+    def step(self, method, block, dt, overlap=True, dt_next=None):
         """refresh + compute of one cycle (dt: device-resident, already
         reduced over ranks). With overlap the z exchange runs under the
-        interior part of the update."""
+        interior part of the update. dt_next (one-element fp64 CUDA tensor):
+        also evaluate this block's timestep of the NEXT cycle, folded into the
+        update (vlct_compute_and_timestep_dev[_part]); the caller min-reduces
+        it over the ranks (global_dt)."""
         from . import abi
         mz = block.n[2] + 2 * block.g[2]
         z_lo = block.g[2] + abi.PART_REACH_BELOW
@@ -225,12 +228,15 @@ class Domain:
                      and getattr(block, "stream_is_current", False))
         pending = self.refresh(method, block, defer_z=can_split)
         if pending is None:
-            method.compute(block, dt)
+            if dt_next is not None:
+                method.compute_and_timestep_dev(block, dt, out=dt_next)
+            else:
+                method.compute(block, dt)
             return
-        method.compute_part(block, dt, abi.PART_INTERIOR, z_lo, z_hi)
+        method.compute_part(block, dt, abi.PART_INTERIOR, z_lo, z_hi, dt_next)
         self.refresh_finish(method, block, pending)
-        method.compute_part(block, dt, abi.PART_LOWER, z_lo, z_hi)
-        method.compute_part(block, dt, abi.PART_UPPER, z_lo, z_hi)
+        method.compute_part(block, dt, abi.PART_LOWER, z_lo, z_hi, dt_next)
+        method.compute_part(block, dt, abi.PART_UPPER, z_lo, z_hi, dt_next)
         block.compute_done()
 
     def global_dt(self, dt, device=None):

@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     "vlct_create", "vlct_destroy", "vlct_name", "vlct_compute",
     "vlct_timestep", "vlct_timestep_dev", "vlct_compute_dev",
     "vlct_compute_and_timestep", "vlct_compute_and_timestep_batch",
+    "vlct_compute_and_timestep_dev", "vlct_compute_and_timestep_dev_part",
     "vlct_compute_dev_part", "vlct_set_option",
     "vlct_compute_batch", "vlct_timestep_batch", "vlct_save_face_fluxes",
     "vlct_host_register", "vlct_host_unregister",
@@ -70,6 +71,9 @@ def load():
         "vlct_compute_dev": (C.c_int, [C.c_void_p, blkp, dp]),
         "vlct_compute_dev_part": (C.c_int, [C.c_void_p, blkp, dp, C.c_int,
                                             C.c_int, C.c_int]),
+        "vlct_compute_and_timestep_dev": (C.c_int, [C.c_void_p, blkp, dp, dp]),
+        "vlct_compute_and_timestep_dev_part": (C.c_int, [C.c_void_p, blkp, dp, C.c_int,
+                                                         C.c_int, C.c_int, dp]),
         "vlct_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
         "vlct_compute_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, C.c_double]),
         "vlct_timestep_batch": (C.c_int, [C.c_void_p, blkp, C.c_int, dp]),

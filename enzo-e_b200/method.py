@@ -168,11 +168,31 @@ class EnzoMethodMHDVlct:
         block.compute_done()
         return out.value
 
-    def compute_part(self, block, dt, part, z_lo, z_hi):
+    def compute_and_timestep_dev(self, block, dt, out=None):
+        """compute(block) + the next cycle's timestep with both values on the
+        device (vlct_compute_and_timestep_dev); dt, out: one-element fp64 CUDA
+        tensors (out may be dt itself). Asynchronous."""
+        import torch
+        if out is None:
+            out = torch.empty(1, dtype=torch.float64, device=dt.device)
+        self._check(self._lib.vlct_compute_and_timestep_dev(
+            self._h, C.byref(block.c_block),
+            C.cast(dt.data_ptr(), C.POINTER(C.c_double)),
+            C.cast(out.data_ptr(), C.POINTER(C.c_double))))
+        block.compute_done()
+        return out
+
+    def compute_part(self, block, dt, part, z_lo, z_hi, dt_next=None):
         """One of the three parts of a step (vlct_compute_dev_part): the
         interior first, then the lower / upper rest once the z ghost levels
         have arrived. dt: one-element fp64 CUDA tensor. The caller calls
         block.compute_done() after the last part."""
+        if dt_next is not None:     # with the next cycle's timestep folded in
+            self._check(self._lib.vlct_compute_and_timestep_dev_part(
+                self._h, C.byref(block.c_block),
+                C.cast(dt.data_ptr(), C.POINTER(C.c_double)), part, z_lo, z_hi,
+                C.cast(dt_next.data_ptr(), C.POINTER(C.c_double))))
+            return
         self._check(self._lib.vlct_compute_dev_part(
             self._h, C.byref(block.c_block),
             C.cast(dt.data_ptr(), C.POINTER(C.c_double)), part, z_lo, z_hi))

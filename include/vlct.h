@@ -190,9 +190,9 @@ int vlct_compute_dev(vlct_handle *h, const vlct_block *block,
  * src/Cello/control_refresh.cpp:243-359; with one large block per GPU the
  * overlap has to happen inside the block):
  *   VLCT_PART_INTERIOR  everything that can be computed from the cell levels
- *                       z_lo-4 .. z_hi+5 alone (z in ghost-including indices),
+ *                       z_lo-5 .. z_hi+5 alone (z in ghost-including indices),
  *                       i.e. without the z ghost levels when
- *                       gz+4 <= z_lo < z_hi <= mz-gz-6;
+ *                       gz+5 <= z_lo < z_hi <= mz-gz-6;
  *   VLCT_PART_LOWER / VLCT_PART_UPPER  the rest, below / above it; these read
  *                       the z ghost levels and may be issued in either order
  *                       once the exchange has delivered them.
@@ -204,6 +204,13 @@ int vlct_compute_dev(vlct_handle *h, const vlct_block *block,
 enum { VLCT_PART_INTERIOR = 0, VLCT_PART_LOWER = 1, VLCT_PART_UPPER = 2 };
 int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
                           const double *dt_device, int part, int z_lo, int z_hi);
+/* The three parts with the next cycle's timestep folded in (see
+ * vlct_compute_and_timestep_dev): every part adds the CFL minimum of the levels
+ * it finishes; issue INTERIOR first and UPPER last -- UPPER completes the
+ * minimum and writes courant * min to *dt_next_device. */
+int vlct_compute_and_timestep_dev_part(vlct_handle *h, const vlct_block *block,
+                                       const double *dt_device, int part, int z_lo,
+                                       int z_hi, double *dt_next_device);
 
 /* compute(block) and the timestep(block) of the cycle that follows, in ONE
  * call. In Enzo-E's cycle the stopping phase calls Method::timestep on every
@@ -225,6 +232,15 @@ int vlct_compute_dev_part(vlct_handle *h, const vlct_block *block,
  * and DEVICE blocks. */
 int vlct_compute_and_timestep(vlct_handle *h, const vlct_block *block, double dt,
                               double *dt_next);
+/* The same with both timesteps in device memory (DEVICE blocks): nothing waits
+ * for the host, cycles queue back to back. For a single block the CFL work is
+ * folded into the last stage's update kernel -- the freshly updated cells are
+ * still in registers, so the separate pass over eight fields that
+ * vlct_timestep_dev makes disappears -- plus one small launch for the ghost
+ * shell that compute never updates. dt_next_device may alias dt_device (dt is
+ * latched by the first kernel of the step). */
+int vlct_compute_and_timestep_dev(vlct_handle *h, const vlct_block *block,
+                                  const double *dt_device, double *dt_next_device);
 
 /* Flux-correction output:
  * EnzoMethodMHDVlct::save_fluxes_for_corrections_
@@ -292,6 +308,14 @@ int vlct_host_register(vlct_handle *h, void *ptr, unsigned long long bytes);
 int vlct_host_unregister(vlct_handle *h, void *ptr);
 
 /* Tuning knobs of a handle (none changes any result bit):
+ *   "scalar_flux_arrays" (0 = off, default) Passive-scalar fluxes are normally
+ *        never stored: the update kernel forms the fluxes through a cell's
+ *        faces itself from the specific scalars and the density fluxes (the
+ *        sweeps then carry no scalar work and three arrays per scalar are
+ *        neither written nor read). 1 brings the flux arrays back;
+ *        vlct_save_face_fluxes needs that for its passive-scalar slots. Set it
+ *        before the first vlct_compute of the handle (setting it later
+ *        rebuilds the scratch).
  *   "host_mirror_reuse"  (0 = off, default) A PROMISE BY THE CALLER: between
  *        vlct_compute of a VLCT_MEM_HOST block and the vlct_timestep of the
  *        same block that follows it, nobody writes the block's fields. That is

@@ -150,6 +150,11 @@ void EnzoMethodMHDVlctGpu::create_handle_()
 {
   const int rc = vlct_create(&config_, &handle_);
   check_status_(rc, handle_, "EnzoMethodMHDVlctGpu");
+  if (store_fluxes_for_corrections_ && config_.n_passive > 0) {
+    // FluxData wants the passive scalars' face fluxes, too
+    check_status_(vlct_set_option(handle_, "scalar_flux_arrays", 1), handle_,
+                  "EnzoMethodMHDVlctGpu");
+  }
 }
 
 //----------------------------------------------------------------------

@@ -50,6 +50,7 @@ def main():
     from enzo_e_b200.method import EnzoMethodMHDVlct, Block
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 4.0
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     dev = torch.device("cuda", 0)
     n, width = (size,) * 3, (1.0 / size,) * 3
     stream = torch.cuda.Stream(device=dev)
@@ -62,6 +63,8 @@ def main():
         block = Block(fields, n, GHOST, width)
         dt = torch.full((1,), 1e-5, dtype=torch.float64, device=dev)
         for name, mask in families.items():
+            if only is not None and name not in only:
+                continue
             saved = {k: v.clone() for k, v in fields.items()} if name == "all" else None
             method.set_option("debug_kernel_mask", mask)
             for _ in range(3):

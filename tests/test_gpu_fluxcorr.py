@@ -32,6 +32,9 @@ def test_face_fluxes_match_oracle(name, where):
     cpu.close()
 
     method = EnzoMethodMHDVlct(config=cfg)
+    if cfg.n_passive:
+        # the scalars' face fluxes only exist with their flux arrays
+        method.set_option("scalar_flux_arrays", 1)
     if where == "device":
         fields = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
     else:
@@ -69,4 +72,22 @@ def test_face_fluxes_need_hydro_and_a_compute():
     method.compute(block, method.timestep(block))
     with pytest.raises(VlctError):          # "only supported in hydro-mode"
         method.save_face_fluxes(block)
+    method.close()
+
+
+def test_scalar_face_fluxes_need_their_flux_arrays():
+    """by default passive-scalar fluxes are never stored (the update kernel
+    forms them itself); asking for them without the option is refused"""
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    from enzo_e_b200.lib import VlctError
+    cfg = make_config(riemann="hllc", recon="plm", mhd=False, n_passive=2)
+    n, g, d = (10, 8, 8), (3, 3, 3), (0.1, 0.1, 0.1)
+    host = random_state(cfg, n, g, seed=3)
+    method = EnzoMethodMHDVlct(config=cfg)
+    block = Block(host, n, g, d, passive=passive_names(cfg))
+    method.compute(block, 1e-3)
+    with pytest.raises(VlctError, match="scalar_flux_arrays"):
+        method.save_face_fluxes(block)
+    hydro_only = method.save_face_fluxes(block, n_fields=6)    # fine without
+    assert len(hydro_only) > 0
     method.close()

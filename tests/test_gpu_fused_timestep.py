@@ -110,3 +110,70 @@ def test_mirror_grows_with_the_field_set_and_checks_shape():
     with pytest.raises(VlctError, match="share one shape"):
         method.timestep(Block(other, (10, 10, 8), g, d))
     method.close()
+
+
+@pytest.mark.parametrize("name", ["mhd_hlld_plm", "mhd_hlld_athena_de_scalars",
+                                  "hd_hllc_plm_de", "mhd_hlld_floors_de"])
+@pytest.mark.parametrize("how", ["whole", "parts", "passes"])
+def test_device_resident_fold_equals_compute_then_timestep(name, how):
+    """vlct_compute_and_timestep_dev / _dev_part: dt in, next dt out, both on
+    the device; the CFL work rides on the last update kernel (+ a ghost-shell
+    launch). Fields, "pressure" and every dt equal the oracle's
+    compute() -> timestep() sequence bit for bit -- as one step, as the three
+    parts of the overlapped step, and as z passes."""
+    import torch
+    from enzo_e_b200 import abi
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**CASES[name])
+    n, g, d = (20, 12, 26), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=10)
+    nsteps = 3
+    want, dts_want = reference_run(cfg, host, n, g, d, nsteps)
+    method = EnzoMethodMHDVlct(config=cfg)
+    if how == "passes":
+        method.set_option("device_pipeline_levels", 5)
+    f = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+    block = Block(f, n, g, d, passive=passive_names(cfg))
+    dt = method.timestep_dev(block)
+    dts = [dt.clone()]
+    zr = (10, 17)
+    for _ in range(nsteps):
+        nxt = torch.empty_like(dt)
+        if how == "parts":
+            for part in (abi.PART_INTERIOR, abi.PART_LOWER, abi.PART_UPPER):
+                method.compute_part(block, dt, part, *zr, dt_next=nxt)
+        else:
+            method.compute_and_timestep_dev(block, dt, out=nxt)
+        dt = nxt
+        dts.append(dt.clone())
+    method.synchronize()
+    torch.cuda.synchronize()
+    assert [float(t.item()) for t in dts] == dts_want
+    got = {k: v.cpu().numpy() for k, v in f.items()}
+    method.close()
+    eq = bit_equal(want, got)
+    bad = {k: max_abs_diff(want, got)[k] for k, ok in eq.items() if not ok}
+    assert not bad, bad
+
+
+def test_fold_may_write_dt_in_place():
+    """dt_next_device may alias dt_device"""
+    import torch
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**CASES["mhd_hlld_plm"])
+    n, g, d = (16, 12, 10), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=12)
+    want, dts_want = reference_run(cfg, host, n, g, d, 2)
+    method = EnzoMethodMHDVlct(config=cfg)
+    f = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+    block = Block(f, n, g, d)
+    dt = method.timestep_dev(block)
+    seen = [float(dt.item())]
+    for _ in range(2):
+        method.compute_and_timestep_dev(block, dt, out=dt)
+        method.synchronize()
+        seen.append(float(dt.item()))
+    assert seen == dts_want
+    got = {k: v.cpu().numpy() for k, v in f.items()}
+    method.close()
+    assert all(bit_equal(want, got).values())

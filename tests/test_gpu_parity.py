@@ -211,3 +211,35 @@ def test_active_floors_host_blocks(name):
     got, dts_got, _ = run_gpu(cfg, host, n, g, d, 2, False)
     assert dts_got == dts_want
     assert all(bit_equal(want, got).values())
+
+
+@pytest.mark.parametrize("name", ["mhd_hlld_plm_scalars", "mhd_hlle_nn_de_scalar",
+                                  "hd_hllc_plm_de_scalars",
+                                  "mhd_hlle_athena_floors_scalars"])
+def test_scalar_flux_arrays_option_is_bit_neutral(name):
+    """Passive scalars two ways: fluxes formed inside the update kernel
+    (default) and flux arrays written by the sweeps (option
+    "scalar_flux_arrays"); both equal the oracle bit for bit."""
+    import torch
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**{**CASES, **FLOOR_CASES}[name])
+    n, g, d = (20, 12, 10), (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=31)
+    want, dts_want = run_cpu(cfg, host, n, g, d, 3)
+    for option in (0, 1):
+        method = EnzoMethodMHDVlct(config=cfg)
+        method.set_option("scalar_flux_arrays", option)
+        f = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+        block = Block(f, n, g, d, passive=passive_names(cfg))
+        dts = []
+        for step in range(3):
+            if step == 2:      # switching later rebuilds the scratch
+                method.set_option("scalar_flux_arrays", 1 - option)
+            dt = method.timestep(block)
+            method.compute(block, dt)
+            dts.append(dt)
+        method.synchronize()
+        got = {k: v.cpu().numpy() for k, v in f.items()}
+        method.close()
+        assert dts == dts_want
+        assert all(bit_equal(want, got).values()), option

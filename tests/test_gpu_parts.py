@@ -95,7 +95,7 @@ def test_host_pipeline_euler_is_one_shot():
 
 
 @pytest.mark.parametrize("name", PASS_CASES)
-@pytest.mark.parametrize("zr", [(7, 8), (7, 21), (10, 15), (12, 13)])
+@pytest.mark.parametrize("zr", [(8, 9), (8, 21), (10, 15), (12, 13)])
 @pytest.mark.parametrize("upper_first", [False, True])
 def test_three_parts_bit_exact(name, zr, upper_first):
     """interior, then lower / upper in either order == the whole step"""
