@@ -238,7 +238,10 @@ __device__ __forceinline__ void ring_cell(const Params& P, const double* slot,
 #define VLCT_FLUX_MARCH_PLM_MINBLOCKS 3
 #endif
 constexpr int kXWarps = 4;
-constexpr int kXRows = 8;        // rows a warp walks through, one after another
+#ifndef VLCT_XROWS
+#define VLCT_XROWS 8
+#endif
+constexpr int kXRows = VLCT_XROWS;   // rows a warp walks through, one after another
 
 template <int RECON, int SOLVER, bool DE>
 __global__ void __launch_bounds__(kXWarps * 32, VLCT_FLUX_X_MINBLOCKS)
