@@ -402,8 +402,11 @@ __device__ __forceinline__ void block_min_to(unsigned long long* dt_bits, double
 // SCAL: the kernel advances the passive scalars itself (stacked batches, or
 // scalar flux arrays); otherwise k_scalar_update does, or there are none --
 // and the scalar code with its registers is compiled out
+#ifndef VLCT_UPDATE_MINBLOCKS
+#define VLCT_UPDATE_MINBLOCKS 4
+#endif
 template <bool MHD, bool DE, bool STACKED, bool CFL, bool SCAL>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, SCAL ? 2 : VLCT_UPDATE_MINBLOCKS)
 k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateArgs A,
          const Box box)
 {
@@ -444,7 +447,8 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
   const double dtd[3] = { __ldg(A.sp), __ldg(A.sp + 1), __ldg(A.sp + 2) };
   // accumulate dU = 0 - sum_d dt/dx_d (F_{c+1/2} - F_{c-1/2}) in x,y,z order
   double d_rho = 0., d_mx = 0., d_my = 0., d_mz = 0., d_e = 0., d_eint = 0.;
-  double frho_c[3], frho_l[3];   // density fluxes (the scalars' upwinding needs them)
+  // density fluxes: kept only where this kernel upwinds the scalars itself
+  double frho_c[SCAL ? 3 : 1], frho_l[SCAL ? 3 : 1];
   double p_floored = 0.;
   if (DE) {
     // cell-centred primitive pressure of the current stage
@@ -457,9 +461,9 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
     const FluxSet& F = A.flux[d];
     const size_t l = c - st[d];
     const double dtdx = dtd[d];
-    frho_c[d] = __ldg(F.rho + c);
-    frho_l[d] = __ldg(F.rho + l);
-    d_rho -= dtdx * (frho_c[d] - frho_l[d]);
+    const double fr_c = __ldg(F.rho + c), fr_l = __ldg(F.rho + l);
+    if (SCAL) { frho_c[SCAL ? d : 0] = fr_c; frho_l[SCAL ? d : 0] = fr_l; }
+    d_rho -= dtdx * (fr_c - fr_l);
     d_mx -= dtdx * (__ldg(F.mx_ + c) - __ldg(F.mx_ + l));
     d_my -= dtdx * (__ldg(F.my_ + c) - __ldg(F.my_ + l));
     d_mz -= dtdx * (__ldg(F.mz_ + c) - __ldg(F.mz_ + l));
@@ -534,8 +538,8 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
           sl_c = w0 + d0 * 0.5;
           sr_c = wp1 - dp * 0.5;
         }
-        d_s -= dtd[d] * (passive_flux(sl_c, sr_c, frho_c[d]) -
-                         passive_flux(sl_l, sr_l, frho_l[d]));
+        d_s -= dtd[d] * (passive_flux(sl_c, sr_c, frho_c[SCAL ? d : 0]) -
+                         passive_flux(sl_l, sr_l, frho_l[SCAL ? d : 0]));
       }
       A.out.sc[s][c] = __ldg(A.u0.sc[s] + c) + d_s;
     }
