@@ -430,16 +430,83 @@ def shock_tube(n_local, g, lower, width, setup="rj2a", aligned_ax=0, device="cud
     return {k: v.contiguous() for k, v in f.items()}
 
 
+def cloud_perturbation_waves(nwaves, seed, min_lambda, max_lambda):
+    """The plane waves of EnzoInitialCloud's density perturbation
+    (WavePerturbation, src/Enzo/initial/EnzoInitialCloud.cpp:86-119): drawn on
+    the host from std::minstd_rand(seed) exactly as the reference draws them
+    (uniform_dist_transform_ :16-44, Box-Muller :51-59, sphere points :61-84;
+    Python's math functions are the platform's libm, like the reference's).
+    Returns [(kx, ky, kz, phi)]."""
+    state = seed % 2147483647 or 1
+
+    def rand():
+        nonlocal state
+        state = (state * 48271) % 2147483647
+        return float(state)
+
+    MAX = 2147483646.0
+
+    def uniform(include_zero, include_one):
+        raw = rand()
+        if include_zero and include_one:
+            rng, raw = MAX - 1.0, raw - 1.0
+        elif include_zero:
+            rng, raw = MAX, raw - 1.0
+        elif include_one:
+            rng = MAX
+        else:
+            rng = MAX + 1.0
+        return raw / rng
+
+    def normal_pair():
+        x1 = uniform(False, False)
+        x2 = uniform(False, False)
+        coef = math.sqrt(-2.0 * math.log(x1))
+        return coef * math.cos(2.0 * _CELLO_PI * x2), coef * math.sin(2.0 * _CELLO_PI * x2)
+
+    waves = []
+    for _ in range(nwaves):
+        lam = min_lambda + (max_lambda - min_lambda) * uniform(True, True)
+        while True:
+            x, y = normal_pair()
+            z, _unused = normal_pair()
+            if x != 0.0 or y != 0.0 or z != 0.0:
+                break
+        mag = math.sqrt(x * x + y * y + z * z)
+        kx = (x / mag) * 2 * _CELLO_PI / lam
+        ky = (y / mag) * 2 * _CELLO_PI / lam
+        kz = (z / mag) * 2 * _CELLO_PI / lam
+        waves.append((kx, ky, kz, _CELLO_PI * uniform(True, False)))
+    return waves
+
+
+def _cloud_wave_average(waves, amplitude, xc, yc, zc, h):
+    """WavePerturbation::operator() (cpp:135-160): the perturbation averaged
+    over cells of widths h centred at (xc, yc, zc) (broadcastable tensors)"""
+    total = torch.zeros(torch.broadcast_shapes(xc.shape, yc.shape, zc.shape),
+                        dtype=torch.float64, device=xc.device)
+    alpha = 8.0 * amplitude / (h[0] * h[1] * h[2])
+    for kx, ky, kz, phi in waves:
+        ci = (math.sin(kx * h[0] * 0.5) * math.sin(ky * h[1] * 0.5)
+              * math.sin(kz * h[2] * 0.5)) / (kx * ky * kz)
+        total = total + ci * torch.cos(kx * xc + ky * yc + kz * zc + phi)
+    return alpha * total
+
+
 def cloud(n_local, g, lower, width, subsample_n, cloud_radius, center,
           cloud_density, wind_density, wind_velocity, wind_total_energy,
           wind_internal_energy=0.0, device="cuda", mhd=False, dual_energy=True,
-          bfield=(0.0, 0.0, 0.0)):
-    """EnzoInitialCloud (src/Enzo/initial/EnzoInitialCloud.cpp:606-748) without
-    a density perturbation (perturb_Nwaves = 0, the default): a sphere of
-    cloud_density at rest in a wind along +x, in pressure equilibrium. Cells cut
-    by the sphere's surface get the volume-weighted density of their 2^n per
+          bfield=(0.0, 0.0, 0.0), perturb=None):
+    """EnzoInitialCloud (src/Enzo/initial/EnzoInitialCloud.cpp:606-748): a sphere
+    of cloud_density at rest in a wind along +x, in pressure equilibrium. Cells
+    cut by the sphere's surface get the volume-weighted density of their 2^n per
     axis sub-cells and a mass-weighted velocity (cpp:320-386). `bfield`: the
-    uniform field the reference expects to find pre-initialised (cpp:452-523)."""
+    uniform field the reference expects to find pre-initialised (cpp:452-523).
+    `perturb` = (Nwaves, seed, amplitude, min_lambda, max_lambda): the optional
+    density perturbation of the cloud (Initial:cloud:perturb_*, cpp:86-163,
+    327-390): the wave parameters are drawn on the host exactly like the
+    reference's, the cell / sub-cell averages are evaluated on the device (so
+    they agree with the reference to the last bits of cos, not bit for bit)."""
     f64 = dict(dtype=torch.float64, device=device)
     m = [n_local[a] + 2 * g[a] for a in range(3)]
     sqr_radius = cloud_radius * cloud_radius
@@ -490,7 +557,47 @@ def cloud(n_local, g, lower, width, subsample_n, cloud_radius, center,
     frac = torch.where(enclosed, torch.ones_like(frac),
                        torch.where(overlap, frac, torch.zeros_like(frac)))
 
-    avg_density = frac * cloud_density * 1.0 + (1.0 - frac) * wind_density
+    perturbation = torch.zeros_like(frac)
+    if perturb is not None and perturb[0] > 0 and perturb[2] > 0.0:
+        nw, seed, amplitude, lmin, lmax = perturb
+        waves = cloud_perturbation_waves(int(nw), int(seed), lmin, lmax)
+        # enclosed cells: the average over the whole cell, at its centre
+        cen = []
+        for a in range(3):
+            idx = torch.arange(m[a] + 1, **f64) - g[a]
+            face = lower[a] + idx * width[a]
+            cen.append(along(a, 0.5 * (face[:-1] + face[1:])))
+        whole = _cloud_wave_average(waves, amplitude, cen[0], cen[1], cen[2], width)
+        perturbation = torch.where(enclosed, whole, perturbation)
+        # cut cells: the mean over the enclosed sub-cells (z, y, x order)
+        partial = overlap & ~enclosed
+        pidx = torch.nonzero(partial, as_tuple=True)
+        if pidx[0].numel() > 0:
+            left = []
+            for a in range(3):
+                idx = torch.arange(m[a] + 1, **f64) - g[a]
+                face = lower[a] + idx * width[a]
+                left.append(face[:-1][pidx[2 - a]])
+            sub_h = [width[a] / float(nsub) for a in range(3)]
+            psum = torch.zeros_like(left[0])
+            for oz in offs[2]:
+                sub_zc = left[2] + oz
+                for oy in offs[1]:
+                    sub_yc = left[1] + oy
+                    for ox in offs[0]:
+                        sub_xc = left[0] + ox
+                        dx, dy, dz = sub_xc - center[0], sub_yc - center[1], sub_zc - center[2]
+                        inside = ((dx * dx + dy * dy) + dz * dz) <= sqr_radius
+                        val = _cloud_wave_average(waves, amplitude, sub_xc, sub_yc, sub_zc,
+                                                  sub_h)
+                        psum = psum + torch.where(inside, val, torch.zeros_like(val))
+            cnt = count[pidx].to(torch.float64)
+            mean = torch.where(cnt > 0, psum / torch.clamp(cnt, min=1.0),
+                               torch.zeros_like(psum))
+            perturbation = perturbation.clone()
+            perturbation[pidx] = mean
+    perturbation = perturbation + 1.0
+    avg_density = frac * cloud_density * perturbation + (1.0 - frac) * wind_density
     ratio = torch.full_like(avg_density, wind_density) / avg_density   # true division
     wind_mass_weight = (1.0 - frac) * ratio
     f = {"density": avg_density,

@@ -369,8 +369,10 @@ def boundary_inflow(blk, axis, side, values, passive=(), n_passive=0):
 
 def ic_cloud(blk, lower, subsample_n, cloud_radius, center, cloud_density,
              wind_density, wind_velocity, wind_total_energy,
-             wind_internal_energy, ref_method=None):
-    """EnzoInitialCloud (no perturbation) on a host block, ghost zones too;
+             wind_internal_energy, ref_method=None, perturb=None):
+    """EnzoInitialCloud on a host block, ghost zones too; perturb = None or
+    (Nwaves, seed, amplitude, min_lambda, max_lambda), the Initial:cloud:
+    perturb_* parameters of the optional density perturbation;
     magnetic fields (if any) must already be initialised. ref_method: a
     CpuMethod(kind="ref") whose field list the block matches -- then the
     reference's own compiled EnzoInitialCloud::enforce_block fills the block
@@ -378,14 +380,22 @@ def ic_cloud(blk, lower, subsample_n, cloud_radius, center, cloud_density,
     lo = (C.c_double * 3)(*lower)
     p = (C.c_double * 9)(cloud_radius, *center, cloud_density, wind_density,
                          wind_velocity, wind_total_energy, wind_internal_energy)
+    nw, seed, amp, lmin, lmax = perturb if perturb is not None else (0, 0, 0., 0., 0.)
+    tail = [C.c_int, C.c_uint, C.c_double, C.c_double, C.c_double]
     if ref_method is not None:
         assert ref_method.kind == "ref"
-        fn = ref_method._lib.vlct_ref_ic_cloud
+        fn = ref_method._lib.vlct_ref_ic_cloud_perturbed
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.POINTER(abi.VlctBlock),
-                       C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
-        rc = fn(ref_method._h, C.byref(blk), lo, subsample_n, p)
+                       C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)] + tail
+        rc = fn(ref_method._h, C.byref(blk), lo, subsample_n, p, int(nw), int(seed),
+                float(amp), float(lmin), float(lmax))
     else:
-        rc = _ic_lib().vlct_ic_cloud(C.byref(blk), lo, subsample_n, p)
+        fn = _ic_lib().vlct_ic_cloud_perturbed
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(abi.VlctBlock), C.POINTER(C.c_double), C.c_int,
+                       C.POINTER(C.c_double)] + tail
+        rc = fn(C.byref(blk), lo, subsample_n, p, int(nw), int(seed), float(amp),
+                float(lmin), float(lmax))
     if rc != 0:
         raise RuntimeError(f"vlct_ic_cloud failed ({rc})")

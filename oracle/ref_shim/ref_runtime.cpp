@@ -371,8 +371,21 @@ int SHIM_FN(timestep)(void* handle, const vlct_block* b, double* dt_out)
 /// p[] = { cloud_radius, center_x, center_y, center_z, cloud_density,
 ///         wind_density, wind_velocity, wind_total_energy, wind_internal_energy }
 /// (the Initial:cloud parameters of input/vlct/dual_energy_cloud).
+int vlct_ref_ic_cloud_perturbed(void* handle, const vlct_block* b, const double* lower,
+                                int subsample_n, const double* p, int nwaves,
+                                unsigned int seed, double amplitude, double min_lambda,
+                                double max_lambda);
+
 int vlct_ref_ic_cloud(void* handle, const vlct_block* b, const double* lower,
                       int subsample_n, const double* p)
+{ return vlct_ref_ic_cloud_perturbed(handle, b, lower, subsample_n, p, 0, 0u, 0., 0., 0.); }
+
+/// ... with Initial:cloud:perturb_Nwaves / perturb_seed / perturb_amplitude /
+/// perturb_min_lambda / perturb_max_lambda (EnzoInitialCloud.hpp:39-58)
+int vlct_ref_ic_cloud_perturbed(void* handle, const vlct_block* b, const double* lower,
+                                int subsample_n, const double* p, int nwaves,
+                                unsigned int seed, double amplitude, double min_lambda,
+                                double max_lambda)
 {
   RefHandle* h = static_cast<RefHandle*>(handle);
   activate(h);
@@ -386,6 +399,13 @@ int vlct_ref_ic_cloud(void* handle, const vlct_block* b, const double* lower,
                           "wind_velocity", "wind_total_energy",
                           "wind_internal_energy" };
   for (int k = 0; k < 9; k++) pg.set(keys[k], fmt_double(p[k]));
+  if (nwaves > 0) {
+    pg.set("perturb_Nwaves", std::to_string(nwaves));
+    pg.set("perturb_seed", std::to_string(seed));
+    pg.set("perturb_amplitude", fmt_double(amplitude));
+    pg.set("perturb_min_lambda", fmt_double(min_lambda));
+    pg.set("perturb_max_lambda", fmt_double(max_lambda));
+  }
   EnzoInitialCloud initial(0, 0.0, pg);
   initial.enforce_block(&blk, nullptr);
   return 0;

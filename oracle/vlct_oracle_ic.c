@@ -9,7 +9,7 @@
  *
  *   vlct_ic_inclined_wave   initial/EnzoInitialInclinedWave.cpp
  *   vlct_ic_shock_tube      initial/EnzoInitialShockTube.cpp
- *   vlct_ic_cloud           initial/EnzoInitialCloud.cpp (unperturbed cloud)
+ *   vlct_ic_cloud[_perturbed] initial/EnzoInitialCloud.cpp (cloud in a wind, optional density perturbation)
  *   (face-B from a vector potential, centred B)  initial/EnzoInitialBCenter.cpp
  *
  * plus the periodic ghost-zone refresh of a single block
@@ -671,12 +671,96 @@ static int cloud_check_point(const double *center, double sqr_radius, double x,
   return (dx * dx + dy * dy + dz * dz) <= sqr_radius;
 }
 
-/* CloudInitHelper::query_cell without a perturbation (cpp:320-386):
- * fraction of the cell [left, right] enclosed by the sphere */
+/* ---- the optional density perturbation (cpp:16-163) ------------------------- */
+/* std::minstd_rand: x <- 48271 x mod (2^31 - 1), a zero seed becomes 1 */
+typedef struct { unsigned long long x; } minstd;
+#define MINSTD_MAX 2147483646.0
+static void minstd_seed(minstd *g, unsigned int seed)
+{ g->x = seed % 2147483647ULL; if (g->x == 0) g->x = 1; }
+static double minstd_next(minstd *g)
+{ g->x = (g->x * 48271ULL) % 2147483647ULL; return (double) g->x; }
+
+/* uniform_dist_transform_ (cpp:16-44) */
+static double cloud_uniform(minstd *g, int include_zero, int include_one)
+{
+  double raw = minstd_next(g);
+  double range;
+  if (include_zero && include_one) { range = MINSTD_MAX - 1.; raw--; }
+  else if (include_zero)           { range = MINSTD_MAX;      raw--; }
+  else if (include_one)            { range = MINSTD_MAX; }
+  else                             { range = MINSTD_MAX + 1.; }
+  return raw / range;
+}
+
+/* normal_dist_transform_ (Box-Muller, cpp:51-59) */
+static void cloud_normal_pair(minstd *g, double *a, double *b)
+{
+  double x1 = cloud_uniform(g, 0, 0);
+  double x2 = cloud_uniform(g, 0, 0);
+  double coef = sqrt(-2. * log(x1));
+  *a = coef * cos(2. * cello_pi * x2);
+  *b = coef * sin(2. * cello_pi * x2);
+}
+
+#define CLOUD_MAX_WAVES 1024
+typedef struct {
+  int nwaves;
+  double amplitude;
+  double kx[CLOUD_MAX_WAVES], ky[CLOUD_MAX_WAVES], kz[CLOUD_MAX_WAVES],
+         phi[CLOUD_MAX_WAVES];
+} cloud_waves;
+
+/* WavePerturbation::WavePerturbation (cpp:91-119) */
+static void cloud_waves_init(cloud_waves *w, int nwaves, unsigned int seed,
+                             double amplitude, double min_lambda, double max_lambda)
+{
+  w->nwaves = nwaves;
+  w->amplitude = amplitude;
+  if (!(nwaves > 0 && amplitude > 0.)) { w->nwaves = (nwaves > 0) ? nwaves : 0; }
+  if (nwaves > 0 && amplitude > 0.) {
+    minstd g;
+    minstd_seed(&g, seed);
+    for (int i = 0; i < nwaves; i++) {
+      double lambda = min_lambda + (max_lambda - min_lambda) * cloud_uniform(&g, 1, 1);
+      /* sample_sphere_points_ (cpp:61-84) */
+      double x, y, z, unused;
+      for (;;) {
+        cloud_normal_pair(&g, &x, &y);
+        cloud_normal_pair(&g, &z, &unused);
+        if ((x != 0.) || (y != 0.) || (z != 0.)) break;
+      }
+      double magnitude = sqrt(x * x + y * y + z * z);
+      w->kx[i] = (x / magnitude) * 2 * cello_pi / lambda;
+      w->ky[i] = (y / magnitude) * 2 * cello_pi / lambda;
+      w->kz[i] = (z / magnitude) * 2 * cello_pi / lambda;
+      w->phi[i] = cello_pi * cloud_uniform(&g, 1, 0);
+    }
+  } else {
+    w->nwaves = 0;     /* operator() then sums nothing: exactly 0 */
+  }
+}
+
+/* WavePerturbation::operator() (cpp:135-160): volume average over a cell */
+static double cloud_waves_eval(const cloud_waves *w, double xc, double yc, double zc,
+                               double hx, double hy, double hz)
+{
+  double total = 0.;
+  double alpha = 8. * w->amplitude / (hx * hy * hz);
+  for (int i = 0; i < w->nwaves; i++) {
+    double ci = (sin(w->kx[i] * hx * 0.5) * sin(w->ky[i] * hy * 0.5) *
+                 sin(w->kz[i] * hz * 0.5)) / (w->kx[i] * w->ky[i] * w->kz[i]);
+    total += ci * cos(w->kx[i] * xc + w->ky[i] * yc + w->kz[i] * zc + w->phi[i]);
+  }
+  return alpha * total;
+}
+
+/* CloudInitHelper::query_cell (cpp:327-390): fraction of the cell [left, right]
+ * enclosed by the sphere and the average density perturbation of that part */
 static double cloud_frac_enclosed(const double *center, double sqr_radius,
                                   const double *left, const double *right,
                                   int nsub, double num_subsampled_cells,
-                                  const double *off[3])
+                                  const double *off[3], const cloud_waves *w,
+                                  const double *h, double *perturbation)
 {
   /* SphereRegion::check_intersect (cpp:204-237) */
   double nearest[3], furthest[3];
@@ -691,35 +775,59 @@ static double cloud_frac_enclosed(const double *center, double sqr_radius,
       else furthest[i] = right[i];
     }
   }
-  if (cloud_check_point(center, sqr_radius, furthest[0], furthest[1], furthest[2]))
+  if (cloud_check_point(center, sqr_radius, furthest[0], furthest[1], furthest[2])) {
+    *perturbation = cloud_waves_eval(w, 0.5 * (left[0] + right[0]),
+                                     0.5 * (left[1] + right[1]),
+                                     0.5 * (left[2] + right[2]), h[0], h[1], h[2]);
     return 1.0;                                   /* enclosed_cell */
+  }
+  *perturbation = 0.;
   if (!cloud_check_point(center, sqr_radius, nearest[0], nearest[1], nearest[2]))
     return 0.0;                                   /* no_overlap */
   int n_enclosed = 0;                             /* partial_overlap */
+  double perturb_sum = 0.;
+  const double n_axis = (double) nsub;
+  const double sub_h[3] = { h[0] / n_axis, h[1] / n_axis, h[2] / n_axis };   /* cpp:295-296 */
   for (int sz = 0; sz < nsub; sz++) {
     double sub_zc = left[2] + off[2][sz];
     for (int sy = 0; sy < nsub; sy++) {
       double sub_yc = left[1] + off[1][sy];
       for (int sx = 0; sx < nsub; sx++) {
         double sub_xc = left[0] + off[0][sx];
-        if (cloud_check_point(center, sqr_radius, sub_xc, sub_yc, sub_zc))
+        if (cloud_check_point(center, sqr_radius, sub_xc, sub_yc, sub_zc)) {
           n_enclosed++;
+          perturb_sum += cloud_waves_eval(w, sub_xc, sub_yc, sub_zc, sub_h[0],
+                                          sub_h[1], sub_h[2]);
+        }
       }
     }
   }
+  if (n_enclosed > 0) *perturbation = perturb_sum / (double) n_enclosed;
   return (double) n_enclosed / num_subsampled_cells;   /* cpp:377 */
 }
 
-/* EnzoInitialCloud::enforce_block (initial/EnzoInitialCloud.cpp:606-748) with
- * perturb_Nwaves = 0 (the default; the perturbation is then exactly 0), no
+/* EnzoInitialCloud::enforce_block (initial/EnzoInitialCloud.cpp:606-748), no
  * "color" fields (the input/vlct/dual_energy_cloud files define no Group:color, so
  * cloud_dye / metal_density are not touched), magnetic fields pre-initialised
  * by the caller and uniform (MHDHandler, cpp:452-523).
  * p[] = { cloud_radius, center_x, center_y, center_z, cloud_density,
  *         wind_density, wind_velocity, wind_total_energy, wind_internal_energy }
  * lower: domain coordinate of the block's first active cell. */
+int vlct_ic_cloud_perturbed(const vlct_block *b, const double *lower, int subsample_n,
+                            const double *p, int nwaves, unsigned int seed,
+                            double amplitude, double min_lambda, double max_lambda);
+
+/* perturb_Nwaves = 0 (the default; the perturbation is then exactly 0) */
 int vlct_ic_cloud(const vlct_block *b, const double *lower, int subsample_n,
                   const double *p)
+{ return vlct_ic_cloud_perturbed(b, lower, subsample_n, p, 0, 0u, 0., 0., 0.); }
+
+/* ... with the density perturbation of Initial:cloud:perturb_* (a sum of
+ * `nwaves` inclined plane waves with wavelengths in [min_lambda, max_lambda],
+ * drawn from std::minstd_rand(seed); cpp:86-163, hpp:39-58) */
+int vlct_ic_cloud_perturbed(const vlct_block *b, const double *lower, int subsample_n,
+                            const double *p, int nwaves, unsigned int seed,
+                            double amplitude, double min_lambda, double max_lambda)
 {
   const int mx = b->nx + 2 * b->gx, my = b->ny + 2 * b->gy, mz = b->nz + 2 * b->gz;
   const int m[3] = { mx, my, mz }, g[3] = { b->gx, b->gy, b->gz };
@@ -729,6 +837,11 @@ int vlct_ic_cloud(const vlct_block *b, const double *lower, int subsample_n,
   const double density_cloud = p[4], density_wind = p[5], velocity_wind = p[6],
                etot_wind = p[7], eint_wind = p[8];
   if (subsample_n < 0 || p[0] <= 0.) return 1;
+  if (nwaves > CLOUD_MAX_WAVES) return 3;
+  if (nwaves > 0 && !(amplitude > 0. && min_lambda > 0. && max_lambda >= min_lambda))
+    return 4;                                        /* hpp:95-106 */
+  cloud_waves *waves = (cloud_waves *) malloc(sizeof(cloud_waves));
+  cloud_waves_init(waves, nwaves, seed, amplitude, min_lambda, max_lambda);
 
   /* Data::field_cell_faces with cx = cy = cz = 1 (Cello/data_Data.cpp:91-121) */
   double *xf[3];
@@ -779,9 +892,10 @@ int vlct_ic_cloud(const vlct_block *b, const double *lower, int subsample_n,
         b->velocity_z[c] = 0.;
         const double left[3] = { xf[0][ix], xf[1][iy], xf[2][iz] };
         const double right[3] = { xf[0][ix + 1], xf[1][iy + 1], xf[2][iz + 1] };
-        double frac_enclosed = cloud_frac_enclosed(center, sqr_radius, left, right,
-                                                   nsub, num_subsampled_cells, coff);
         double perturbation = 0.;
+        double frac_enclosed = cloud_frac_enclosed(center, sqr_radius, left, right,
+                                                   nsub, num_subsampled_cells, coff,
+                                                   waves, h, &perturbation);
         perturbation += 1.;
         double avg_density = (frac_enclosed * density_cloud * perturbation +
                               (1. - frac_enclosed) * density_wind);
@@ -803,5 +917,6 @@ int vlct_ic_cloud(const vlct_block *b, const double *lower, int subsample_n,
         }
       }
   for (int a = 0; a < 3; a++) { free(xf[a]); free(off[a]); }
+  free(waves);
   return 0;
 }

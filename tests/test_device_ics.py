@@ -69,6 +69,36 @@ def test_cloud_off_centre_matches_oracle_ic():
     assert np.unique(f["density"]).size > 100
 
 
+def test_perturbed_cloud_matches_oracle_ic():
+    """the optional density perturbation of the cloud (Initial:cloud:perturb_*,
+    EnzoInitialCloud.cpp:86-163, 327-390): wave parameters drawn on the host
+    bit for bit like the reference's std::minstd_rand sequence, cell and
+    sub-cell averages evaluated by torch -- equal to the oracle (itself
+    bit-identical to the compiled reference) to the last bits of cos()"""
+    from enzo_e_b200 import problems as DP
+    cfg = P.make_config(riemann="hllc", recon="plm", mhd=False)
+    n, g, d = (20, 14, 18), (3, 3, 3), (0.11, 0.11, 0.11)
+    lower = (-1.0, -0.8, -0.9)
+    perturb = (5, 20231, 0.12, 0.2, 0.61)
+    kw = dict(P.CLOUD, center=(0.13, -0.07, 0.21), cloud_radius=0.61, subsample_n=3,
+              wind_internal_energy=0.0)
+    f = P.alloc_fields(cfg, n, g)
+    oracle.ic_cloud(oracle.numpy_block(f, n, g, d), lower, perturb=perturb, **kw)
+    got = DP.cloud(n, g, lower, d, device="cpu", mhd=False, dual_energy=False,
+                   perturb=perturb, **kw)
+    assert set(got) == set(f)
+    for k in f:
+        np.testing.assert_allclose(got[k].numpy(), f[k], rtol=2e-14, atol=1e-300,
+                                   err_msg=k)
+    # the host-side wave table IS bit-identical: same PRNG, same libm
+    waves = DP.cloud_perturbation_waves(perturb[0], perturb[1], perturb[3], perturb[4])
+    assert len(waves) == 5 and all(0.0 <= w[3] < np.pi for w in waves)
+    lam = [2 * np.pi / np.sqrt(w[0] ** 2 + w[1] ** 2 + w[2] ** 2) for w in waves]
+    assert all(perturb[3] - 1e-12 <= x <= perturb[4] + 1e-12 for x in lam)
+    unperturbed = DP.cloud(n, g, lower, d, device="cpu", mhd=False, dual_energy=False, **kw)
+    assert float((got["density"] - unperturbed["density"]).abs().max()) > 0.01
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,mhd", [("fast", True), ("alfven", True),
                                       ("sound", False)])

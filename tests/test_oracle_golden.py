@@ -227,15 +227,22 @@ def test_dual_energy_cloud_symmetry(solver):
         assert all(bit_equal(f, f2).values())
 
 
+# Initial:cloud:perturb_{Nwaves, seed, amplitude, min_lambda, max_lambda}
+CLOUD_PERTURB = (5, 20231, 0.12, 0.2, 0.61)
+
+
 @pytest.mark.parametrize("case", ["answer_test_hlld", "answer_test_hllc",
-                                  "off_centre"])
+                                  "off_centre", "off_centre_perturbed"])
 def test_cloud_ic_restatement_equals_compiled_reference(case):
     """oracle/vlct_oracle_ic.c:vlct_ic_cloud against the reference's own
     EnzoInitialCloud::enforce_block (compiled unmodified into oracle/_ref),
     bit for bit, ghost zones included"""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref/libvlct_ref.so not available")
-    if case == "off_centre":
+    perturb = None
+    if case.startswith("off_centre"):
+        if case.endswith("perturbed"):    # the optional density perturbation
+            perturb = CLOUD_PERTURB       # (EnzoInitialCloud.cpp:86-163, 327-390)
         cfg = make_config(riemann="hllc", recon="plm", mhd=False)
         n, g, d = (20, 14, 18), (3, 3, 3), (0.11, 0.11, 0.11)
         lower = (-1.0, -0.8, -0.9)
@@ -246,16 +253,26 @@ def test_cloud_ic_restatement_equals_compiled_reference(case):
         n, g, d = (32, 32, 32), (3, 3, 3), (0.125,) * 3
         lower, kw = P.CLOUD_LOWER, P.CLOUD
     f = P.alloc_fields(cfg, n, g)
-    oracle.ic_cloud(oracle.numpy_block(f, n, g, d), lower, **kw)
+    oracle.ic_cloud(oracle.numpy_block(f, n, g, d), lower, perturb=perturb, **kw)
     f_ref = P.alloc_fields(cfg, n, g)
     for k in f_ref:                 # everything the initialiser must overwrite
         if not k.startswith("bfield") and k != "pressure":
             f_ref[k][...] = np.nan
     ref = oracle.CpuMethod(cfg, g, kind="ref")
-    oracle.ic_cloud(oracle.numpy_block(f_ref, n, g, d), lower, ref_method=ref, **kw)
+    oracle.ic_cloud(oracle.numpy_block(f_ref, n, g, d), lower, ref_method=ref,
+                    perturb=perturb, **kw)
     ref.close()
     assert all(bit_equal(f, f_ref).values()), bit_equal(f, f_ref)
     assert np.unique(f["density"]).size > 10
+    if perturb is not None:         # the cloud's interior is no longer uniform
+        f0 = P.alloc_fields(cfg, n, g)
+        oracle.ic_cloud(oracle.numpy_block(f0, n, g, d), lower, **kw)
+        inside = f0["density"] == kw["cloud_density"]
+        assert inside.sum() > 100
+        rel = f["density"][inside] / kw["cloud_density"] - 1.0
+        assert 0.01 < np.abs(rel).max() < 5 * perturb[2]
+        assert np.array_equal(f["density"][f0["density"] == kw["wind_density"]],
+                              f0["density"][f0["density"] == kw["wind_density"]])
 
 
 @pytest.mark.parametrize("axis", [0, 1, 2])
