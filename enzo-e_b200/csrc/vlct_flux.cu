@@ -430,9 +430,12 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   constexpr int kSlot = RingVars<MHD>::n * kMarchThreads;      // doubles per slot
   __shared__ double ring[kRingDepth * kSlot];
   double* const ring0 = ring + threadIdx.x;
+  // cells this chunk really needs: up to f1 - 1 + kFirst (prefetching further,
+  // into the next chunk's cells, cost 3 rows of DRAM traffic per 64-face chunk)
+  const int cell_end = min(mdim, f1 + kFirst);
 #pragma unroll
   for (int a = 0; a < kRingAhead; a++) {
-    if (f0 + kFirst + a < mdim)
+    if (f0 + kFirst + a < cell_end)
       ring_issue<MHD, DE, kMarchThreads>(ring0 + a * kSlot, u, c + (kFirst + a) * sd, bi,
                                          fb + a * sd);
     cp_async_commit();
@@ -442,7 +445,7 @@ k_flux_march(const __grid_constant__ Params P, const __grid_constant__ Geom G,
   for (int f = f0; f < f1; f++, c += sd, fb += sd) {
     double Wn[NV], wr[NV], wl_next[NV];
     double blong = 0.;
-    if (f + kFirst + kRingAhead < mdim)
+    if (f + kFirst + kRingAhead < cell_end)
       ring_issue<MHD, DE, kMarchThreads>(
           ring0 + ((slot + kRingAhead) & (kRingDepth - 1)) * kSlot, u,
           c + (kFirst + kRingAhead) * sd, bi, fb + kRingAhead * sd);
