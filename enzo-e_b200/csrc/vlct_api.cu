@@ -37,6 +37,7 @@ struct vlct_handle {
   // measurement hook (scripts/gpu_power.py): bit k set = launch kernel family k
   // of a step (KernelId order). Anything but "all" leaves garbage in the fields.
   long long debug_kernel_mask = -1;
+  int pair_kernels = default_pair_kernels();   // option "pair_kernels"
   Geom G{0, 0, 0};
   Scratch S;
   std::vector<void*> allocations;
@@ -514,12 +515,12 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
   // dt may live on the device (vlct_compute_dev): the stage constants are
   // formed there, so a step never has to wait for the host
   if (set_step_params)
-    launch_step_params(LaunchCtx{ st, &h->launches, &h->prof }, dt_dev, dt, nstages,
+    launch_step_params(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, dt_dev, dt, nstages,
                        width, h->d_step);
   if (fold_cfl && G.nrep != 1)
     return fail(h, VLCT_ERR_INTERNAL, "the CFL fold handles single blocks only");
   if (fold_cfl && set_step_params)
-    launch_timestep_reset(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits);
+    launch_timestep_reset(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, h->d_dt_bits);
   CflFold cfl;
   cfl.pressure = b->pressure;
   cfl.dt_bits = h->d_dt_bits;
@@ -535,7 +536,7 @@ int compute_on_device(vlct_handle* h, const vlct_block* b, const Geom& G,
     const FaceB& bi_cur = (stage == 0) ? bi : h->S.tbi;
     const FaceB& bi_out = (stage == 1 || nstages == 1) ? bi : h->S.tbi;
 
-    const LaunchCtx ctx{ st, &h->launches, &h->prof };
+    const LaunchCtx ctx{ st, &h->launches, &h->prof, h->pair_kernels };
     const int row = final_stage ? 1 : 0;
     const long long mask = h->debug_kernel_mask;
     const ZClip nothing{ 0, 0 };
@@ -769,7 +770,7 @@ int compute_entry(vlct_handle* h, const vlct_block* b, double dt, const double* 
                              ZCut{ CUT_NONE, 0 }, true, fused);
     if (rc == VLCT_OK && dt_next_dev != nullptr) {
       // courant * minimum, left on the device: nothing waits for the host
-      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, h->d_dt_bits,
                        h->cfg.courant, dt_next_dev);
       CUDA_TRY(h, cudaGetLastError());
     } else if (rc == VLCT_OK && fused) {
@@ -823,7 +824,7 @@ int timestep_launch(vlct_handle* h, const vlct_block* db, const Geom& G,
 {
   const double width[3] = { db->dx, db->dy, db->dz };
   const State u = state_of(h, db);
-  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof, h->pair_kernels };
   if (reset) launch_timestep_reset(ctx, h->d_dt_bits);
   launch_timestep(ctx, h->P, G, u, db->pressure, width, h->d_dt_bits, zc);
   CUDA_TRY(h, cudaGetLastError());
@@ -915,7 +916,7 @@ int vlct_timestep_dev(vlct_handle* h, const vlct_block* b, double* dt_device)
   cudaStream_t st = b->stream ? (cudaStream_t) b->stream : h->own_stream;
   if ((rc = timestep_launch(h, b, G, st)) != VLCT_OK) return rc;
   // "Multiply resulting dt by CourantSafetyNumber" (cpp:585-587), on the device
-  launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+  launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, h->d_dt_bits,
                    h->cfg.courant, dt_device);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
@@ -1137,7 +1138,7 @@ int batch_copy(vlct_handle* h, int a, const vlct_block* blocks, int first, int n
   const vlct_block& arena = h->arena[a];
   const bool host = (blocks[0].mem_space == VLCT_MEM_HOST);
   const Geom one{ G.mx, G.my, G.mz, 1, 0 };
-  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof, h->pair_kernels };
   // DEVICE blocks: gather / scatter kernels. HOST blocks: see host_batch_copy_mode.
   const bool use_kernels = h->ptr_table_usable && (!host || h->host_batch_copy_mode == 1);
   const bool use_batch_memcpy = host && !use_kernels && h->host_batch_copy_mode != 2 &&
@@ -1245,7 +1246,7 @@ int vlct_save_face_fluxes(vlct_handle* h, const vlct_block* b,
   const bool host = (out->mem_space == VLCT_MEM_HOST);
   cudaStream_t st = (b->mem_space == VLCT_MEM_DEVICE && b->stream)
                         ? (cudaStream_t) b->stream : h->own_stream;
-  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof, h->pair_kernels };
   const int n[3] = { b->nx, b->ny, b->nz }, g[3] = { b->gx, b->gy, b->gz };
   const int m[3] = { G.mx, G.my, G.mz };
   const int nstages = (h->cfg.time_scheme == VLCT_TIME_EULER) ? 1 : 2;
@@ -1424,7 +1425,7 @@ int vlct_timestep_batch(vlct_handle* h, const vlct_block* blocks, int nblocks,
   cudaStream_t st = (!host && blocks[0].stream) ? (cudaStream_t) blocks[0].stream
                                                  : h->own_stream;
   const int chunk = batch_chunk(h, geom_of(&blocks[0]));
-  const LaunchCtx ctx{ st, &h->launches, &h->prof };
+  const LaunchCtx ctx{ st, &h->launches, &h->prof, h->pair_kernels };
   if ((rc = prepare_ptr_table(h, blocks, nblocks)) != VLCT_OK) return rc;
   for (int first = 0; first < nblocks; first += chunk) {
     const int nb = (nblocks - first < chunk) ? nblocks - first : chunk;
@@ -1543,6 +1544,9 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
         h->stepped = false;
       }
     }
+  } else if (strcmp(key, "pair_kernels") == 0) {
+    if (value < 0 || value > 7) return fail(h, VLCT_ERR_INVALID_CONFIG, "pair_kernels in 0..7");
+    h->pair_kernels = (int) value;
   } else if (strcmp(key, "debug_kernel_mask") == 0) {
     h->debug_kernel_mask = value;
   } else if (strcmp(key, "device_pipeline_levels") == 0) {
@@ -1617,7 +1621,7 @@ int compute_dev_part(vlct_handle* h, const vlct_block* b, const double* dt_devic
     if (rc == VLCT_OK && fold) {
       // the three parts are done (INTERIOR, LOWER, UPPER, in this order): the
       // minimum is complete
-      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof }, h->d_dt_bits,
+      launch_finish_dt(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, h->d_dt_bits,
                        h->cfg.courant, dt_next_device);
       CUDA_TRY(h, cudaGetLastError());
     }
@@ -1735,7 +1739,7 @@ int vlct_refresh_periodic(vlct_handle* h, const vlct_block* b, int axes)
     if (n[axis] < g[axis])
       return fail(h, VLCT_ERR_INVALID_BLOCK,
                   "periodic refresh needs n >= ghost depth along every axis");
-    launch_wrap_axis_all(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my,
+    launch_wrap_axis_all(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, table, G.mz, G.my,
                          G.mx, axis, n[axis], g[axis]);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -1775,7 +1779,7 @@ int vlct_boundary(vlct_handle* h, const vlct_block* b, int axis, int side, int t
     table.face[table.count] = f.face;
     table.sign[table.count++] = sign;
   }
-  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, table, G.mz, G.my, G.mx,
                        axis, n[axis], g[axis], side, type);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
@@ -1820,7 +1824,7 @@ int vlct_boundary_inflow(vlct_handle* h, const vlct_block* b, int axis, int side
     table.face[table.count] = -1;
     table.sign[table.count++] = value;
   }
-  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+  launch_boundary_axis(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, table, G.mz, G.my, G.mx,
                        axis, n[axis], g[axis], side, VLCT_BOUNDARY_INFLOW);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;
@@ -1885,7 +1889,7 @@ int halo_copy(vlct_handle* h, const vlct_block* b, int axis, int side,
     for (int a = 0; a < 3; a++) if (a != axis) cnt *= (size_t) ext[a];
     off += cnt;
   }
-  launch_slab_copy_all(LaunchCtx{ st, &h->launches, &h->prof }, table, G.mz, G.my, G.mx,
+  launch_slab_copy_all(LaunchCtx{ st, &h->launches, &h->prof, h->pair_kernels }, table, G.mz, G.my, G.mx,
                        axis, g[axis], buffer, pack);
   CUDA_TRY(h, cudaGetLastError());
   return VLCT_OK;

@@ -23,6 +23,8 @@
 #include "vlct_physics.cuh"
 
 #include <cfloat>
+#include <cstdint>
+#include <cstdlib>
 
 namespace vlct {
 
@@ -577,6 +579,384 @@ k_update(const Params P, const typename GeomFor<STACKED>::type G, const UpdateAr
 }
 
 // ---------------------------------------------------------------------------
+// Pair variants of the cell kernels: a thread owns the two cells (i, i+1), i
+// even, of a row. Rows of every cell-strided array start 16-byte aligned when
+// mx is even (and the arrays themselves are: launch_* checks both), so each
+// array is moved with one 128-bit load / store per pair (LDG.E.128 / STG.E.128)
+// and the index arithmetic is paid once per two cells: the cell kernels run at
+// the board's power cap with 60-75 % of their instructions being address
+// arithmetic and loads, so instructions are what they cost. Only the x-face
+// array (rows of mx + 1 entries) keeps 64-bit accesses. Values at odd x
+// offsets (i-1, i+2) are single loads. Every cell evaluates exactly the
+// expressions of the one-cell kernels above: bit-identical.
+// A pair may stick out of the box by one cell on either side (odd lower bound,
+// odd upper bound): that cell is computed from in-bounds memory and not stored.
+// ---------------------------------------------------------------------------
+constexpr int kPairBlock = 128;      // threads = 256 cells, like kBlock
+
+__device__ __forceinline__ double2 ld2(const double* p)
+{ return __ldg(reinterpret_cast<const double2*>(p)); }
+
+/// store of a pair of which only the valid cells are written
+__device__ __forceinline__ void st_pair(double* p, double a, double b, bool va, bool vb)
+{
+  if (va && vb) *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  else if (va) p[0] = a;
+  else if (vb) p[1] = b;
+}
+
+inline dim3 pair_grid_for(const Geom& G, const Box& b)
+{
+  const unsigned npx = (unsigned) (b.hi[0] - (b.lo[0] & ~1) + 1) >> 1;
+  const unsigned ny = b.hi[1] - b.lo[1];
+  return dim3((npx * ny + kPairBlock - 1) / kPairBlock, stacked_nz(G, b), 1);
+}
+
+// i: the pair's first cell (even); va / vb: cell i / i+1 lies inside the box
+#define VLCT_PAIR_IN_BOX(G, box, i, j, kl, k, va, vb)                          \
+  const int i0__ = (box).lo[0] & ~1;                                           \
+  const unsigned npx__ = (unsigned) ((box).hi[0] - i0__ + 1) >> 1;             \
+  const unsigned t__ = blockIdx.x * kPairBlock + threadIdx.x;                  \
+  if (t__ >= npx__ * (unsigned) ((box).hi[1] - (box).lo[1])) return;           \
+  const unsigned jj__ = t__ / npx__;                                           \
+  const int i = i0__ + 2 * (int) (t__ - jj__ * npx__);                         \
+  const int j = (box).lo[1] + (int) jj__;                                      \
+  const bool va = (i >= (box).lo[0]), vb = (i + 1 < (box).hi[0]);              \
+  int kl, k;                                                                   \
+  if constexpr (STACKED) unstack((G), (box), blockIdx.y, kl, k);               \
+  else kl = k = (box).lo[2] + (int) blockIdx.y;
+
+/// a row's values at x = i, i+1 (one 128-bit load) and i+2 (cell b's +x
+/// neighbour: loaded only when cell b is computed for real)
+struct Row3 { double x0, x1, x2; };
+__device__ __forceinline__ Row3 row3(const double* p, bool vb)
+{
+  const double2 v = ld2(p);
+  Row3 r;
+  r.x0 = v.x; r.x1 = v.y; r.x2 = vb ? __ldg(p + 2) : 0.;
+  return r;
+}
+
+#ifndef VLCT_EDGE2_MINBLOCKS
+#define VLCT_EDGE2_MINBLOCKS 4
+#endif
+template <bool STACKED>
+__global__ void __launch_bounds__(kPairBlock, VLCT_EDGE2_MINBLOCKS)
+k_edge_efield2(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const Box box)
+{
+  VLCT_PAIR_IN_BOX(G, box, i, j, kl, k, va, vb);
+  const ptrdiff_t Y = (ptrdiff_t) G.mx, Z = (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
+  const size_t c = cidx(G, k, j, i);
+  const double* const vx = A.v[0] + c; const double* const vy = A.v[1] + c;
+  const double* const vz = A.v[2] + c; const double* const bx = A.b[0] + c;
+  const double* const by = A.b[1] + c; const double* const bz = A.b[2] + c;
+  // cell-centred E_d = -v_j B_k + v_k B_j  (compute_center_efield, CT.cpp:267-292)
+#define VLCT_EC(vj, bk, vk, bj) (-(vj) * (bk) + (vk) * (bj))
+  // the x component needs E_x on the rows 0, +y, +z, +y+z at x = i, i+1;
+  // the y component E_y on the rows 0, +z at x = i .. i+2;
+  // the z component E_z on the rows 0, +y at x = i .. i+2
+  double ex[4][2], ey[2][3], ez[2][3];
+  {
+    const Row3 vy0 = row3(vy, vb), vz0 = row3(vz, vb), by0 = row3(by, vb), bz0 = row3(bz, vb);
+    const Row3 vx0 = row3(vx, vb), bx0 = row3(bx, vb);
+    ex[0][0] = VLCT_EC(vy0.x0, bz0.x0, vz0.x0, by0.x0);
+    ex[0][1] = VLCT_EC(vy0.x1, bz0.x1, vz0.x1, by0.x1);
+    ey[0][0] = VLCT_EC(vz0.x0, bx0.x0, vx0.x0, bz0.x0);
+    ey[0][1] = VLCT_EC(vz0.x1, bx0.x1, vx0.x1, bz0.x1);
+    ey[0][2] = VLCT_EC(vz0.x2, bx0.x2, vx0.x2, bz0.x2);
+    ez[0][0] = VLCT_EC(vx0.x0, by0.x0, vy0.x0, bx0.x0);
+    ez[0][1] = VLCT_EC(vx0.x1, by0.x1, vy0.x1, bx0.x1);
+    ez[0][2] = VLCT_EC(vx0.x2, by0.x2, vy0.x2, bx0.x2);
+  }
+  {
+    // row +y: E_x at x = i, i+1; E_z at x = i .. i+2
+    const Row3 vxY = row3(vx + Y, vb), vyY = row3(vy + Y, vb);
+    const Row3 bxY = row3(bx + Y, vb), byY = row3(by + Y, vb);
+    const double2 vzY = ld2(vz + Y), bzY = ld2(bz + Y);
+    ex[1][0] = VLCT_EC(vyY.x0, bzY.x, vzY.x, byY.x0);
+    ex[1][1] = VLCT_EC(vyY.x1, bzY.y, vzY.y, byY.x1);
+    ez[1][0] = VLCT_EC(vxY.x0, byY.x0, vyY.x0, bxY.x0);
+    ez[1][1] = VLCT_EC(vxY.x1, byY.x1, vyY.x1, bxY.x1);
+    ez[1][2] = VLCT_EC(vxY.x2, byY.x2, vyY.x2, bxY.x2);
+  }
+  {
+    // row +z: E_x at x = i, i+1; E_y at x = i .. i+2
+    const Row3 vxZ = row3(vx + Z, vb), vzZ = row3(vz + Z, vb);
+    const Row3 bxZ = row3(bx + Z, vb), bzZ = row3(bz + Z, vb);
+    const double2 vyZ = ld2(vy + Z), byZ = ld2(by + Z);
+    ex[2][0] = VLCT_EC(vyZ.x, bzZ.x0, vzZ.x0, byZ.x);
+    ex[2][1] = VLCT_EC(vyZ.y, bzZ.x1, vzZ.x1, byZ.y);
+    ey[1][0] = VLCT_EC(vzZ.x0, bxZ.x0, vxZ.x0, bzZ.x0);
+    ey[1][1] = VLCT_EC(vzZ.x1, bxZ.x1, vxZ.x1, bzZ.x1);
+    ey[1][2] = VLCT_EC(vzZ.x2, bxZ.x2, vxZ.x2, bzZ.x2);
+  }
+  {
+    // row +y+z: E_x only
+    const double2 vyW = ld2(vy + Y + Z), vzW = ld2(vz + Y + Z);
+    const double2 byW = ld2(by + Y + Z), bzW = ld2(bz + Y + Z);
+    ex[3][0] = VLCT_EC(vyW.x, bzW.x, vzW.x, byW.x);
+    ex[3][1] = VLCT_EC(vyW.y, bzW.y, vzW.y, byW.y);
+  }
+#undef VLCT_EC
+  // upwind weights from the density fluxes (identify_upwind, CT.cpp:170-216)
+  const double* const rx = A.frho[0] + c;
+  const double* const ry = A.frho[1] + c;
+  const double* const rz = A.frho[2] + c;
+  const double2 rx0 = ld2(rx), rxY = ld2(rx + Y), rxZ = ld2(rx + Z);
+  const Row3 ry0 = row3(ry, vb); const double2 ryZ = ld2(ry + Z);
+  const Row3 rz0 = row3(rz, vb); const double2 rzY = ld2(rz + Y);
+  const double wx0[2] = { upwind_weight(rx0.x), upwind_weight(rx0.y) };
+  const double wxY[2] = { upwind_weight(rxY.x), upwind_weight(rxY.y) };
+  const double wxZ[2] = { upwind_weight(rxZ.x), upwind_weight(rxZ.y) };
+  const double wy0[3] = { upwind_weight(ry0.x0), upwind_weight(ry0.x1), upwind_weight(ry0.x2) };
+  const double wyZ[2] = { upwind_weight(ryZ.x), upwind_weight(ryZ.y) };
+  const double wz0[3] = { upwind_weight(rz0.x0), upwind_weight(rz0.x1), upwind_weight(rz0.x2) };
+  const double wzY[2] = { upwind_weight(rzY.x), upwind_weight(rzY.y) };
+  {
+    // x component: (j, k) = (y, z); E_x on y-faces is -F_y(B_z), on z-faces +F_z(B_y)
+    const double* const Fj = A.fb[1][2] + c;
+    const double* const Fk = A.fb[2][1] + c;
+    const double2 fj0 = ld2(Fj), fjZ = ld2(Fj + Z), fk0 = ld2(Fk), fkY = ld2(Fk + Y);
+    const double ea = edge_value(ex[0][0], ex[1][0], ex[2][0], ex[3][0], fj0.x, fjZ.x, fk0.x,
+                                 fkY.x, wy0[0], wyZ[0], wz0[0], wzY[0]);
+    const double eb = edge_value(ex[0][1], ex[1][1], ex[2][1], ex[3][1], fj0.y, fjZ.y, fk0.y,
+                                 fkY.y, wy0[1], wyZ[1], wz0[1], wzY[1]);
+    const int lo = A.box[0].lo[0];
+    st_pair(A.edge[0] + c, ea, eb, va && i >= lo, vb && i + 1 >= lo);
+  }
+  {
+    // y component: (j, k) = (z, x)
+    const double* const Fj = A.fb[2][0] + c;
+    const double* const Fk = A.fb[0][2] + c;
+    const Row3 fj = row3(Fj, vb);
+    const double2 fk0 = ld2(Fk), fkZ = ld2(Fk + Z);
+    const double ea = edge_value(ey[0][0], ey[1][0], ey[0][1], ey[1][1], fj.x0, fj.x1, fk0.x,
+                                 fkZ.x, wz0[0], wz0[1], wx0[0], wxZ[0]);
+    const double eb = edge_value(ey[0][1], ey[1][1], ey[0][2], ey[1][2], fj.x1, fj.x2, fk0.y,
+                                 fkZ.y, wz0[1], wz0[2], wx0[1], wxZ[1]);
+    const bool row = (j >= A.box[1].lo[1]);
+    st_pair(A.edge[1] + c, ea, eb, va && row, vb && row);
+  }
+  {
+    // z component: (j, k) = (x, y)
+    const double* const Fj = A.fb[0][1] + c;
+    const double* const Fk = A.fb[1][0] + c;
+    const double2 fj0 = ld2(Fj), fjY = ld2(Fj + Y);
+    const Row3 fk = row3(Fk, vb);
+    const double ea = edge_value(ez[0][0], ez[0][1], ez[1][0], ez[1][1], fj0.x, fjY.x, fk.x0,
+                                 fk.x1, wx0[0], wxY[0], wy0[0], wy0[1]);
+    const double eb = edge_value(ez[0][1], ez[0][2], ez[1][1], ez[1][2], fj0.y, fjY.y, fk.x1,
+                                 fk.x2, wx0[1], wxY[1], wy0[1], wy0[2]);
+    const bool lev = (kl >= A.box[2].lo[2]);
+    st_pair(A.edge[2] + c, ea, eb, va && lev, vb && lev);
+  }
+}
+
+template <bool STACKED>
+__global__ void __launch_bounds__(kPairBlock)
+k_face_bfield2(const typename GeomFor<STACKED>::type G, const FaceArgs A, const Box box)
+{
+  VLCT_PAIR_IN_BOX(G, box, i, j, kl, k, va, vb);
+  const ptrdiff_t Y = (ptrdiff_t) G.mx, Z = (ptrdiff_t) G.mx * (ptrdiff_t) G.my;
+  // x faces: rows of mx + 1 entries, 64-bit accesses, one cell after the other
+  if (va) face_component<0>(G, A, kl, k, j, i);
+  if (vb) face_component<0>(G, A, kl, k, j, i + 1);
+  const size_t c = cidx(G, k, j, i);
+  {
+    // y faces (D = 1: JD = z, KD = x); face j is edge index j-1 along y
+    const Box& bx = A.box[1];
+    if (j >= bx.lo[1] && j < bx.hi[1] && kl >= bx.lo[2] && kl < bx.hi[2]) {
+      const size_t e = c - Y;
+      const double2 ekR = ld2(A.edge[0] + e), ekL = ld2(A.edge[0] + e - Z);
+      const double2 ejR = ld2(A.edge[2] + e);
+      const double ejm = __ldg(A.edge[2] + e - 1);
+      const double sj = __ldg(A.sp + 2), sk = __ldg(A.sp + 0);
+      const size_t f = fidx(G, 1, k, j, i);
+      const double2 b0 = ld2(A.bi0[1] + f);
+      const double oa = b0.x - sj * (ekR.x - ekL.x) + sk * (ejR.x - ejm);
+      const double ob = b0.y - sj * (ekR.y - ekL.y) + sk * (ejR.y - ejR.x);
+      st_pair(A.bi_out[1] + f, oa, ob, va && i >= bx.lo[0] && i < bx.hi[0],
+              vb && i + 1 >= bx.lo[0] && i + 1 < bx.hi[0]);
+    }
+  }
+  {
+    // z faces (D = 2: JD = x, KD = y); face k is edge index k-1 along z
+    const Box& bx = A.box[2];
+    if (j >= bx.lo[1] && j < bx.hi[1] && kl >= bx.lo[2] && kl < bx.hi[2]) {
+      const size_t e = c - Z;
+      const double2 ekR = ld2(A.edge[1] + e);
+      const double ekm = __ldg(A.edge[1] + e - 1);
+      const double2 ejR = ld2(A.edge[0] + e), ejL = ld2(A.edge[0] + e - Y);
+      const double sj = __ldg(A.sp + 0), sk = __ldg(A.sp + 1);
+      const size_t f = fidx(G, 2, k, j, i);
+      const double2 b0 = ld2(A.bi0[2] + f);
+      const double oa = b0.x - sj * (ekR.x - ekm) + sk * (ejR.x - ejL.x);
+      const double ob = b0.y - sj * (ekR.y - ekR.x) + sk * (ejR.y - ejL.y);
+      st_pair(A.bi_out[2] + f, oa, ob, va && i >= bx.lo[0] && i < bx.hi[0],
+              vb && i + 1 >= bx.lo[0] && i + 1 < bx.hi[0]);
+    }
+  }
+}
+
+/// minimum over the block of two bit patterns per thread (see block_min_to)
+__device__ __forceinline__ unsigned long long dt_bits_of(double v)
+{ return (unsigned long long) __double_as_longlong(v); }
+
+#ifndef VLCT_UPDATE2_MINBLOCKS
+#define VLCT_UPDATE2_MINBLOCKS 4
+#endif
+struct Pair { double a, b; };
+
+template <bool MHD, bool DE, bool STACKED, bool CFL>
+__global__ void __launch_bounds__(kPairBlock, VLCT_UPDATE2_MINBLOCKS)
+k_update2(const Params P, const typename GeomFor<STACKED>::type G, const UpdateArgs A,
+          const Box box)
+{
+  const int i0 = box.lo[0] & ~1;
+  const unsigned npx = (unsigned) (box.hi[0] - i0 + 1) >> 1;
+  const unsigned t = blockIdx.x * kPairBlock + threadIdx.x;
+  const bool active = t < npx * (unsigned) (box.hi[1] - box.lo[1]);
+  if (!CFL && !active) return;
+  const unsigned jj = active ? t / npx : 0u;
+  const int i = active ? i0 + 2 * (int) (t - jj * npx) : i0;
+  const int j = box.lo[1] + (int) jj;
+  const bool va = active && (i >= box.lo[0]), vb = active && (i + 1 < box.hi[0]);
+  int kl, k;
+  if constexpr (STACKED) unstack(G, box, blockIdx.y, kl, k);
+  else kl = k = box.lo[2] + (int) blockIdx.y;
+  const size_t c = cidx(G, k, j, i);
+  const ptrdiff_t st[3] = { 1, (ptrdiff_t) G.mx, (ptrdiff_t) G.mx * (ptrdiff_t) G.my };
+  double dt_a = DBL_MAX, dt_b = DBL_MAX;
+
+  Pair bx = { 0., 0. }, by = { 0., 0. }, bz = { 0., 0. };
+  if (MHD && active) {
+    // x faces i, i+1, i+2 of the row (always inside the row of mx + 1 entries)
+    const double* const fx = A.bi_out[0] + fidx(G, 0, k, j, i);
+    const double f0 = __ldg(fx), f1 = __ldg(fx + 1), f2 = __ldg(fx + 2);
+    bx.a = 0.5 * (f0 + f1);
+    bx.b = 0.5 * (f1 + f2);
+    const double2 y0 = ld2(A.bi_out[1] + fidx(G, 1, k, j, i));
+    const double2 y1 = ld2(A.bi_out[1] + fidx(G, 1, k, j + 1, i));
+    by.a = 0.5 * (y0.x + y1.x);
+    by.b = 0.5 * (y0.y + y1.y);
+    const double2 z0 = ld2(A.bi_out[2] + fidx(G, 2, k, j, i));
+    const double2 z1 = ld2(A.bi_out[2] + fidx(G, 2, k + 1, j, i));
+    bz.a = 0.5 * (z0.x + z1.x);
+    bz.b = 0.5 * (z0.y + z1.y);
+    st_pair(A.out.bx + c, bx.a, bx.b, va, vb);
+    st_pair(A.out.by + c, by.a, by.b, va, vb);
+    st_pair(A.out.bz + c, bz.a, bz.b, va, vb);
+  }
+
+  const Box& in = A.inner;
+  const bool row_in = (j >= in.lo[1] && j < in.hi[1] && kl >= in.lo[2] && kl < in.hi[2]);
+  const bool ia = va && row_in && i >= in.lo[0] && i < in.hi[0];
+  const bool ib = vb && row_in && i + 1 >= in.lo[0] && i + 1 < in.hi[0];
+  if (!CFL && !ia && !ib) return;
+
+  if (ia || ib) {
+  const double dtd[3] = { __ldg(A.sp), __ldg(A.sp + 1), __ldg(A.sp + 2) };
+  // F_{c+1/2} - F_{c-1/2} of both cells along direction d
+  auto diff = [&](const double* q, int d) {
+    const double2 fc = ld2(q + c);
+    Pair r;
+    if (d == 0) {
+      const double fl = ia ? __ldg(q + c - 1) : 0.;
+      r.a = fc.x - fl; r.b = fc.y - fc.x;
+    } else {
+      const double2 fl = ld2(q + c - st[d]);
+      r.a = fc.x - fl.x; r.b = fc.y - fl.y;
+    }
+    return r;
+  };
+  Pair d_rho = { 0., 0. }, d_mx = { 0., 0. }, d_my = { 0., 0. }, d_mz = { 0., 0. },
+       d_e = { 0., 0. }, d_eint = { 0., 0. };
+  Pair p_floored = { 0., 0. };
+  if (DE) {
+    const double2 r = ld2(A.cur_rho + c), e = ld2(A.cur_eint + c);
+    p_floored.a = apply_floor((P.gamma - 1.0) * r.x * e.x, P.pressure_floor);
+    p_floored.b = apply_floor((P.gamma - 1.0) * r.y * e.y, P.pressure_floor);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const FluxSet& F = A.flux[d];
+    const double dtdx = dtd[d];
+    Pair f;
+    f = diff(F.rho, d); d_rho.a -= dtdx * f.a; d_rho.b -= dtdx * f.b;
+    f = diff(F.mx_, d); d_mx.a -= dtdx * f.a;  d_mx.b -= dtdx * f.b;
+    f = diff(F.my_, d); d_my.a -= dtdx * f.a;  d_my.b -= dtdx * f.b;
+    f = diff(F.mz_, d); d_mz.a -= dtdx * f.a;  d_mz.b -= dtdx * f.b;
+    f = diff(F.e, d);   d_e.a -= dtdx * f.a;   d_e.b -= dtdx * f.b;
+    if (DE) {
+      f = diff(F.eint, d); d_eint.a -= dtdx * f.a; d_eint.b -= dtdx * f.b;
+      f = diff(F.vbar, d);
+      d_eint.a -= dtdx * p_floored.a * f.a;
+      d_eint.b -= dtdx * p_floored.b * f.b;
+    }
+  }
+
+  const double2 rho0 = ld2(A.u0.rho + c);
+  const double2 vx0 = ld2(A.u0.vx + c), vy0 = ld2(A.u0.vy + c), vz0 = ld2(A.u0.vz + c);
+  if (A.gravity) {
+    const double2 ax = ld2(A.accel[0] + c), ay = ld2(A.accel[1] + c),
+                  az = ld2(A.accel[2] + c);
+    const double dt = __ldg(A.sp + 3);
+    d_mx.a += dt * rho0.x * ax.x; d_mx.b += dt * rho0.y * ax.y;
+    d_my.a += dt * rho0.x * ay.x; d_my.b += dt * rho0.y * ay.y;
+    d_mz.a += dt * rho0.x * az.x; d_mz.b += dt * rho0.y * az.y;
+    d_e.a += dt * rho0.x * ((vx0.x * ax.x) + (vy0.x * ay.x) + (vz0.x * az.x));
+    d_e.b += dt * rho0.y * ((vx0.y * ax.y) + (vy0.y * ay.y) + (vz0.y * az.y));
+  }
+  const double2 et0 = ld2(A.u0.etot + c);
+  double2 ei0 = make_double2(0., 0.);
+  if (DE) ei0 = ld2(A.u0.eint + c);
+
+  // conserved update, floors, dual-energy sync of one cell (as in k_update)
+  auto finish = [&](double old_rho, double vx0_, double vy0_, double vz0_, double etot0,
+                    double eint0, double drho, double dmx, double dmy, double dmz, double de,
+                    double deint, double bx_, double by_, double bz_, double& new_rho,
+                    double& vx, double& vy, double& vz, double& etot, double& eint,
+                    double& p, double& local_dt) {
+    new_rho = old_rho + drho;
+    new_rho = apply_floor(new_rho, P.density_floor);
+    const double inv_new_rho = 1. / new_rho;
+    vx = (vx0_ * old_rho + dmx) * inv_new_rho;
+    vy = (vy0_ * old_rho + dmy) * inv_new_rho;
+    vz = (vz0_ * old_rho + dmz) * inv_new_rho;
+    etot = (etot0 * old_rho + de) * inv_new_rho;
+    eint = 0.;
+    if (DE) eint = (eint0 * old_rho + deint) * inv_new_rho;
+    floor_energy_and_sync<DE, MHD>(P, new_rho, vx, vy, vz, bx_, by_, bz_, etot, eint);
+    if (CFL)
+      local_dt = timestep_of_cell<MHD, DE>(P, new_rho, vx, vy, vz, bx_, by_, bz_, etot, eint,
+                                           A.dx, A.dy, A.dz, p);
+  };
+  double ra, ua, va_, wa, ea, ia_, pa = 0., rb, ub, vb_, wb, eb, ib_, pb = 0.;
+  double la = DBL_MAX, lb = DBL_MAX;
+  finish(rho0.x, vx0.x, vy0.x, vz0.x, et0.x, ei0.x, d_rho.a, d_mx.a, d_my.a, d_mz.a, d_e.a,
+         d_eint.a, bx.a, by.a, bz.a, ra, ua, va_, wa, ea, ia_, pa, la);
+  finish(rho0.y, vx0.y, vy0.y, vz0.y, et0.y, ei0.y, d_rho.b, d_mx.b, d_my.b, d_mz.b, d_e.b,
+         d_eint.b, bx.b, by.b, bz.b, rb, ub, vb_, wb, eb, ib_, pb, lb);
+  if (CFL) {
+    if (ia) dt_a = la;
+    if (ib) dt_b = lb;
+    st_pair(A.pressure + c, pa, pb, ia, ib);
+  }
+  st_pair(A.out.rho + c, ra, rb, ia, ib);
+  st_pair(A.out.vx + c, ua, ub, ia, ib);
+  st_pair(A.out.vy + c, va_, vb_, ia, ib);
+  st_pair(A.out.vz + c, wa, wb, ia, ib);
+  st_pair(A.out.etot + c, ea, eb, ia, ib);
+  if (DE) st_pair(A.out.eint + c, ia_, ib_, ia, ib);
+  }
+  if (CFL) {
+    // non-negative doubles order like their bit patterns, NaNs above +inf
+    const unsigned long long ba = dt_bits_of(dt_a), bb = dt_bits_of(dt_b);
+    block_min_to(A.dt_bits, __longlong_as_double((long long) (bb < ba ? bb : ba)));
+  }
+}
+
+// ---------------------------------------------------------------------------
 // passive scalars without flux arrays, single block: one thread = one scalar
 // of one (x, y) column, marching along z
 // ---------------------------------------------------------------------------
@@ -971,6 +1351,21 @@ void Profiler::reset()
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+namespace {
+
+struct Align16 {
+  bool ok = true;
+  void operator()(const void* p) { if (((uintptr_t) p & 15u) != 0) ok = false; }
+};
+
+}  // namespace
+
+int default_pair_kernels()
+{
+  const char* e = getenv("VLCT_PAIR_MASK");
+  return e ? (atoi(e) & 7) : 2;
+}
+
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
                        const State& cur, const Scratch& S, int stage, int stale, ZClip zc)
 {
@@ -1014,8 +1409,19 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     // clips all three)
     if (clip_z(box, z_edge)) {
       ScopedLaunch sl(ctx, "k_edge_efield");
-      if (G.nrep > 1) k_edge_efield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
-      else            k_edge_efield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
+      Align16 al;
+      for (int d = 0; d < 3; d++) {
+        al(A.v[d]); al(A.b[d]); al(A.frho[d]); al(A.edge[d]);
+        for (int q = 0; q < 3; q++) if (q != d) al(A.fb[d][q]);
+      }
+      if ((ctx.pair_mask & 1) && G.mx % 2 == 0 && al.ok) {
+        const dim3 grid = pair_grid_for(G, box);
+        if (G.nrep > 1) k_edge_efield2<true><<<grid, kPairBlock, 0, st>>>(G, A, box);
+        else            k_edge_efield2<false><<<grid, kPairBlock, 0, st>>>(lite(G), A, box);
+      } else {
+        if (G.nrep > 1) k_edge_efield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
+        else            k_edge_efield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
+      }
     }
   }
   {
@@ -1035,8 +1441,17 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     for (int a = 0; a < 3; a++) { box.lo[a] = s + 1; box.hi[a] = m[a] - s; }
     if (clip_z(box, z_face)) {
       ScopedLaunch sl(ctx, "k_face_bfield");
-      if (G.nrep > 1) k_face_bfield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
-      else            k_face_bfield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
+      Align16 al;
+      for (int d = 0; d < 3; d++) al(A.edge[d]);
+      for (int d = 1; d < 3; d++) { al(A.bi0[d]); al(A.bi_out[d]); }
+      if ((ctx.pair_mask & 2) && G.mx % 2 == 0 && al.ok) {
+        const dim3 grid = pair_grid_for(G, box);
+        if (G.nrep > 1) k_face_bfield2<true><<<grid, kPairBlock, 0, st>>>(G, A, box);
+        else            k_face_bfield2<false><<<grid, kPairBlock, 0, st>>>(lite(G), A, box);
+      } else {
+        if (G.nrep > 1) k_face_bfield<true><<<grid_for(G, box), block, 0, st>>>(G, A, box);
+        else            k_face_bfield<false><<<grid_for(G, box), block, 0, st>>>(lite(G), A, box);
+      }
     }
   }
 }
@@ -1106,13 +1521,40 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
     const int block = kBlock; const dim3 grid = grid_for(G, box);
     ScopedLaunch sl(ctx, cfl ? "k_update_cfl" : "k_update");
     const bool in_kernel_scalars = (P.nsc > 0 && !scalar_kernel);
+    // pair kernel (128-bit accesses): even rows, 16-byte aligned arrays, no
+    // scalar work inside the kernel
+    Align16 al;
+    {
+      const State* sts[2] = { &A.u0, &A.out };
+      for (const State* q : sts) {
+        al(q->rho); al(q->vx); al(q->vy); al(q->vz); al(q->etot);
+        if (P.de) al(q->eint);
+      }
+      if (P.mhd) { al(A.out.bx); al(A.out.by); al(A.out.bz); al(A.bi_out[1]); al(A.bi_out[2]); }
+      for (int d = 0; d < 3; d++) {
+        const FluxSet& F = A.flux[d];
+        al(F.rho); al(F.mx_); al(F.my_); al(F.mz_); al(F.e);
+        if (P.de) { al(F.eint); al(F.vbar); }
+        if (gravity) al(A.accel[d]);
+      }
+      if (P.de) { al(A.cur_rho); al(A.cur_eint); }
+      if (cfl) al(A.pressure);
+    }
+    const bool pair = (ctx.pair_mask & 4) && !in_kernel_scalars && G.mx % 2 == 0 && al.ok;
+    const dim3 pgrid = pair_grid_for(G, box);
 #define VLCT_UPDATE3(MHD_, DE_, CFL_, SCAL_)                                      \
   do {                                                                          \
     if (G.nrep > 1) k_update<MHD_, DE_, true, CFL_, SCAL_><<<grid, block, 0, st>>>(P, G, A, box);  \
     else            k_update<MHD_, DE_, false, CFL_, SCAL_><<<grid, block, 0, st>>>(P, lite(G), A, box); \
   } while (0)
+#define VLCT_UPDATE2P(MHD_, DE_, CFL_)                                            \
+  do {                                                                          \
+    if (G.nrep > 1) k_update2<MHD_, DE_, true, CFL_><<<pgrid, kPairBlock, 0, st>>>(P, G, A, box);  \
+    else            k_update2<MHD_, DE_, false, CFL_><<<pgrid, kPairBlock, 0, st>>>(P, lite(G), A, box); \
+  } while (0)
 #define VLCT_UPDATE2(MHD_, DE_, CFL_)                                             \
-  do { if (in_kernel_scalars) VLCT_UPDATE3(MHD_, DE_, CFL_, true);              \
+  do { if (pair) VLCT_UPDATE2P(MHD_, DE_, CFL_);                                 \
+       else if (in_kernel_scalars) VLCT_UPDATE3(MHD_, DE_, CFL_, true);         \
        else VLCT_UPDATE3(MHD_, DE_, CFL_, false); } while (0)
 #define VLCT_UPDATE(MHD_, DE_)                                                   \
   do { if (cfl) VLCT_UPDATE2(MHD_, DE_, true); else VLCT_UPDATE2(MHD_, DE_, false); } while (0)
@@ -1125,6 +1567,7 @@ void launch_update(const LaunchCtx& ctx, const Params& P, const Geom& G,
     }
 #undef VLCT_UPDATE
 #undef VLCT_UPDATE2
+#undef VLCT_UPDATE2P
 #undef VLCT_UPDATE3
   }
   if (cfl == nullptr) return;

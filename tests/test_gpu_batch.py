@@ -40,8 +40,10 @@ def check_all(want, got):
 
 
 @pytest.mark.parametrize("name", BATCH_CASES)
-@pytest.mark.parametrize("device_resident", [True, False], ids=["device", "host"])
-def test_batch_matches_blocks_alone(name, device_resident):
+@pytest.mark.parametrize("device_resident,pair", [(True, None), (False, None), (True, 7),
+                                                  (True, 0)],
+                         ids=["device", "host", "device_pair7", "device_pair0"])
+def test_batch_matches_blocks_alone(name, device_resident, pair):
     import torch
     from enzo_e_b200.method import EnzoMethodMHDVlct, Block
     cfg = make_config(**CASES[name])
@@ -54,6 +56,8 @@ def test_batch_matches_blocks_alone(name, device_resident):
     else:
         fs = [copy_state(h) for h in hosts]
     method = EnzoMethodMHDVlct(config=cfg)
+    if pair is not None:      # stacked pair kernels (option "pair_kernels")
+        method.set_option("pair_kernels", pair)
     blocks = [Block(f, N, G, D, passive=passive_names(cfg)) for f in fs]
     launches0 = method.kernel_launches()
     dts = []

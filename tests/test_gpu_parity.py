@@ -243,3 +243,43 @@ def test_scalar_flux_arrays_option_is_bit_neutral(name):
         method.close()
         assert dts == dts_want
         assert all(bit_equal(want, got).values()), option
+
+
+@pytest.mark.parametrize("name", ["mhd_hlld_plm", "mhd_hlld_athena_de",
+                                  "mhd_hlld_gravity_de_eta0", "hd_hllc_plm",
+                                  "hd_hllc_gravity", "mhd_hlld_plm_de_floors",
+                                  "hd_hllc_euler_floors", "mhd_hlld_plm_scalars"])
+@pytest.mark.parametrize("shape", [(20, 12, 10), (19, 12, 10), (8, 8, 8)],
+                         ids=["even", "odd_falls_back", "cube8"])
+def test_pair_kernels_option_is_bit_neutral(name, shape):
+    """The cell kernels as pair kernels (two x-cells per thread, 128-bit loads
+    and stores: option "pair_kernels", bit 0 edge E, 1 face B, 2 update) and as
+    one-cell kernels give the oracle's bits -- fields, ghost zones, every dt,
+    with the CFL fold (compute_and_timestep) and without. Odd row lengths fall
+    back to the one-cell kernels."""
+    import torch
+    from enzo_e_b200.method import EnzoMethodMHDVlct, Block
+    cfg = make_config(**{**CASES, **FLOOR_CASES}[name])
+    n, g, d = shape, (3, 3, 3), (0.1, 0.12, 0.09)
+    host = random_state(cfg, n, g, seed=11)
+    want, dts_want = run_cpu(cfg, host, n, g, d, 3)
+    for mask in (0, 7, 2, 5):
+        for fused in (False, True):
+            method = EnzoMethodMHDVlct(config=cfg)
+            method.set_option("pair_kernels", mask)
+            f = {k: torch.from_numpy(v.copy()).cuda() for k, v in host.items()}
+            block = Block(f, n, g, d, passive=passive_names(cfg))
+            dts = [method.timestep(block)]
+            for step in range(3):
+                if fused and step < 2:
+                    dts.append(method.compute_and_timestep(block, dts[-1]))
+                else:
+                    method.compute(block, dts[-1])
+                    if step < 2:
+                        dts.append(method.timestep(block))
+            method.synchronize()
+            got = {k: v.cpu().numpy() for k, v in f.items()}
+            method.close()
+            assert dts == dts_want, (mask, fused)
+            eq = bit_equal(want, got)
+            assert all(eq.values()), (mask, fused, eq)
