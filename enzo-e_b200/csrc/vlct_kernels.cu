@@ -802,8 +802,11 @@ k_face_bfield2(const typename GeomFor<STACKED>::type G, const FaceArgs A, const 
 __device__ __forceinline__ unsigned long long dt_bits_of(double v)
 { return (unsigned long long) __double_as_longlong(v); }
 
+// (6 blocks of 128 threads: 80 registers, no spills; measured at 512^3 against
+// the one-cell kernel's 11.58 ms per step: 4 blocks 11.98, 6 blocks 11.27,
+// 8 blocks (64 registers, spills) 12.17 -- profiles/r2l_update_pair_occupancy.json)
 #ifndef VLCT_UPDATE2_MINBLOCKS
-#define VLCT_UPDATE2_MINBLOCKS 4
+#define VLCT_UPDATE2_MINBLOCKS 6
 #endif
 struct Pair { double a, b; };
 
@@ -1363,7 +1366,7 @@ struct Align16 {
 int default_pair_kernels()
 {
   const char* e = getenv("VLCT_PAIR_MASK");
-  return e ? (atoi(e) & 7) : 2;
+  return e ? (atoi(e) & 7) : 6;
 }
 
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,

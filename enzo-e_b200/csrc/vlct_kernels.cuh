@@ -100,13 +100,13 @@ struct LaunchCtx {
   Profiler* prof;
   // which cell kernels run as pair kernels (two x-cells per thread, 128-bit
   // accesses): bit 0 edge E, bit 1 face B, bit 2 update (option "pair_kernels")
-  int pair_mask = 2;
+  int pair_mask = 6;
 };
 
-/// default of the option "pair_kernels": face B only (measured, DESIGN.md 4.3:
-/// the edge-E and update pair kernels execute 25-30 % fewer instructions but
-/// hold half as many warps and are 3-5 % slower); VLCT_PAIR_MASK in the
-/// environment overrides it for A/B runs
+/// default of the option "pair_kernels": face B and update (measured, DESIGN.md
+/// 4.3: -9 % and -3 %; the edge-E pair kernel executes 26 % fewer instructions
+/// but needs 128 registers, holds a third of the warps and is 3 % slower);
+/// VLCT_PAIR_MASK in the environment overrides it for A/B runs
 int default_pair_kernels();
 
 /// A half-open range [lo, hi) along z that a launch is clipped to, in the

@@ -346,9 +346,10 @@ int vlct_host_unregister(vlct_handle *h, void *ptr);
  *   "pair_kernels"  which cell kernels run as pair kernels (a thread owns two
  *        x-neighbours and moves them with 128-bit loads / stores; needs an
  *        even row length mx and 16-byte aligned arrays, else the one-cell
- *        kernels run): bit 0 edge E, bit 1 face B, bit 2 update. Default 2:
- *        measured at 512^3, the face-B pair kernel is 9 % faster, the other
- *        two execute 25-30 % fewer instructions but are 3-5 % slower.
+ *        kernels run): bit 0 edge E, bit 1 face B, bit 2 update. Default 6:
+ *        measured at 512^3, the face-B pair kernel is 9 % faster and the
+ *        update 3 %; the edge-E pair kernel executes 26 % fewer instructions
+ *        but holds a third of the warps and is 3 % slower.
  *   "device_pipeline_levels" run VLCT_MEM_DEVICE steps in passes of n levels
  *        too (0 = off, default; a test hook for the pass machinery). */
 int vlct_set_option(vlct_handle *h, const char *key, long long value);
