@@ -343,13 +343,16 @@ int vlct_host_unregister(vlct_handle *h, void *ptr);
  *        the current ones and the D2H copy of the finished ones overlap.
  *        -1 (default): ~mz/32 levels per pass for blocks of >= 32 MB per
  *        field, one shot below that; 0: always one shot; n > 0: n levels.
- *   "pair_kernels"  which cell kernels run as pair kernels (a thread owns two
- *        x-neighbours and moves them with 128-bit loads / stores; needs an
- *        even row length mx and 16-byte aligned arrays, else the one-cell
- *        kernels run): bit 0 edge E, bit 1 face B, bit 2 update. Default 6:
- *        measured at 512^3, the face-B pair kernel is 9 % faster and the
- *        update 3 %; the edge-E pair kernel executes 26 % fewer instructions
- *        but holds a third of the warps and is 3 % slower.
+ *   "pair_kernels"  variants of the cell kernels, a bit mask. Bits 0-2: edge E,
+ *        face B, update as pair kernels (a thread owns two x-neighbours and
+ *        moves them with 128-bit loads / stores). Bit 3: edge E of a single
+ *        block with its inputs staged by the TMA unit (cp.async.bulk.tensor
+ *        boxes, a producer warp and 16 consumer warps over mbarriers). All need
+ *        an even row length mx and 16-byte aligned arrays, else the one-cell
+ *        kernels run. Default 14. Measured at 512^3: TMA-staged edge E 4.45 ->
+ *        3.46 ms per launch (95 % of the HBM peak), face-B pair kernel -9 %,
+ *        update -3 %; the edge-E pair kernel (bit 0) is 3 % slower than the
+ *        one-cell kernel.
  *   "device_pipeline_levels" run VLCT_MEM_DEVICE steps in passes of n levels
  *        too (0 = off, default; a test hook for the pass machinery). */
 int vlct_set_option(vlct_handle *h, const char *key, long long value);

@@ -249,12 +249,13 @@ def test_scalar_flux_arrays_option_is_bit_neutral(name):
                                   "mhd_hlld_gravity_de_eta0", "hd_hllc_plm",
                                   "hd_hllc_gravity", "mhd_hlld_plm_de_floors",
                                   "hd_hllc_euler_floors", "mhd_hlld_plm_scalars"])
-@pytest.mark.parametrize("shape", [(20, 12, 10), (19, 12, 10), (8, 8, 8)],
-                         ids=["even", "odd_falls_back", "cube8"])
+@pytest.mark.parametrize("shape", [(20, 12, 10), (19, 12, 10), (8, 8, 8), (70, 20, 6)],
+                         ids=["even", "odd_falls_back", "cube8", "several_tiles"])
 def test_pair_kernels_option_is_bit_neutral(name, shape):
     """The cell kernels as pair kernels (two x-cells per thread, 128-bit loads
-    and stores: option "pair_kernels", bit 0 edge E, 1 face B, 2 update) and as
-    one-cell kernels give the oracle's bits -- fields, ghost zones, every dt,
+    and stores: option "pair_kernels", bit 0 edge E, 1 face B, 2 update), the
+    edge E with TMA-staged inputs (bit 3: tiles of 64 x 8 cells marching along
+    z) and the one-cell kernels give the oracle's bits -- fields, ghost zones, every dt,
     with the CFL fold (compute_and_timestep) and without. Odd row lengths fall
     back to the one-cell kernels."""
     import torch
@@ -263,7 +264,7 @@ def test_pair_kernels_option_is_bit_neutral(name, shape):
     n, g, d = shape, (3, 3, 3), (0.1, 0.12, 0.09)
     host = random_state(cfg, n, g, seed=11)
     want, dts_want = run_cpu(cfg, host, n, g, d, 3)
-    for mask in (0, 7, 2, 5):
+    for mask in (0, 7, 14, 9):
         for fused in (False, True):
             method = EnzoMethodMHDVlct(config=cfg)
             method.set_option("pair_kernels", mask)
