@@ -413,6 +413,9 @@ FAMILIES = {
     "k_edge_efield": {"doubles": 18, "units": lambda m, name: (m - 2) ** 3},
     # per cell: 3 edge E + 3 face B in, 3 face B out
     "k_face_bfield": {"doubles": 9, "units": lambda m, name: (m - 2) ** 3},
+    # edge E + face B in one TMA-staged kernel (the edge E never reach HBM):
+    # v, B (6) + 6 B-fluxes + 3 density fluxes + 3 face B in, 3 face B out
+    "k_ct_tma": {"doubles": 21, "units": lambda m, name: (m - 2) ** 3},
     # per cell: 8 fields in, pressure out (k_timestep_shell: the ghost shell only)
     "k_timestep": {"doubles": 9, "units": lambda m, name: (
         m ** 3 - (m - 6) ** 3 if name.endswith("shell") else m ** 3)},

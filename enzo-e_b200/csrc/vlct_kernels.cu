@@ -804,17 +804,23 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+/// wait for the phase with the given parity. try_wait suspends the thread in
+/// hardware for a bounded time; a phase that never completes (a faulting copy)
+/// traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "VLCT_MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra VLCT_MBAR_DONE;\n"
-      "bra VLCT_MBAR_WAIT;\n"
-      "VLCT_MBAR_DONE:\n"
-      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+  const unsigned addr = smem_u32(bar);
+  for (unsigned it = 0; it < (1u << 24); it++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
 }
 /// one box of a 3-D tensor map, global -> shared; completes on the mbarrier
 __device__ __forceinline__ void tma_box_g2s(void* dst, const CUtensorMap* map, int x, int y,
@@ -928,6 +934,170 @@ k_edge_efield_tma(const GeomLite G, const __grid_constant__ EdgeTmaArgs A, const
     // this warp is done with the stage of level k
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(empty + st0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Constrained transport in one TMA-staged kernel: k_edge_efield_tma whose
+// consumers also update the faces, so that the edge E never reach HBM (-3
+// stores and -6 loads of 18 + 9 doubles per cell and stage). A thread evaluates
+// the three edge E of its cell at level k, publishes them in shared memory,
+// and updates the x face on its +x side, the y face on its +y side (they need
+// E_y / E_x of level k-1: kept in registers) and the z face above it; the
+// edges of the -x / -y neighbours come from shared memory. A block is 64 x 8
+// columns of which 62 x 7 update faces (column 0 and row 0 only provide the
+// neighbours' edges). Same expressions in the same order as k_edge_efield +
+// k_face_bfield: bit-identical.
+// ---------------------------------------------------------------------------
+struct CtTmaArgs {
+  alignas(64) CUtensorMap map[kTmaArrays];
+  const double* bi0[3];
+  double* bi_out[3];
+  const double* sp;           // dt/dx, dt/dy, dt/dz of the stage
+  int s;                      // stale depth: the edge and face boxes follow from it
+  int zlo;                    // first face level (cells for x / y faces, face index for z)
+  int zhi;                    // z faces: index < zhi
+  int kend;                   // the march ends below this cell level
+};
+constexpr size_t kCtExchBytes = (size_t) 3 * kTmaTY * kTmaTX * sizeof(double);
+constexpr size_t kCtSmemBytes = (size_t) kTmaStages * kTmaLevelD * sizeof(double) +
+                                kCtExchBytes + 64;
+
+__device__ __forceinline__ void consumer_barrier()
+{ asm volatile("bar.sync 1, %0;" :: "n"(kTmaConsumers) : "memory"); }
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_ct_tma(const GeomLite G, const __grid_constant__ CtTmaArgs A, const int chunk)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* const buf = reinterpret_cast<double*>(smem_raw);
+  double (*const X)[kTmaTY][kTmaTX] = reinterpret_cast<double (*)[kTmaTY][kTmaTX]>(
+      smem_raw + (size_t) kTmaStages * kTmaLevelD * sizeof(double));
+  unsigned long long* const full = reinterpret_cast<unsigned long long*>(
+      smem_raw + (size_t) kTmaStages * kTmaLevelD * sizeof(double) + kCtExchBytes);
+  unsigned long long* const empty = full + kTmaStages;
+  const int tid = threadIdx.x;
+  const int s = A.s;
+  // column (0, 0) of the block is cell (xb, j0 - 1). The x coordinate of a TMA
+  // box must be even (16-byte granularity along the contiguous axis), so a
+  // block advances by 62 columns: columns 1..62 update faces, column 0 and
+  // row 0 only provide the neighbours' edges.
+  const int xb = ((s - 1) & ~1) + (kTmaTX - 2) * (int) blockIdx.x;
+  const int j0 = s + (kTmaTY - 1) * (int) blockIdx.y;
+  // levels of this chunk; one warm-up level below it provides E_x, E_y of k-1
+  const int K0 = A.zlo - 1;
+  const int kc0 = K0 + (int) blockIdx.z * chunk;
+  const int kc1 = min(kc0 + chunk, A.kend);
+  const int kstart = (kc0 > K0) ? kc0 - 1 : kc0;
+  if (tid == 0) {
+    for (int b = 0; b < kTmaStages; b++) {
+      mbar_init(full + b, 1);
+      mbar_init(empty + b, kTmaConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kTmaConsumers) {
+    // ---- producer warp: levels kstart .. kc1, one TMA box per array ----
+    const int lane = tid - kTmaConsumers;
+#pragma unroll 1
+    for (int n = 0; n <= kc1 - kstart; n++) {
+      const int st = n % kTmaStages, use = n / kTmaStages;
+      if (use > 0) mbar_wait(empty + st, (unsigned) (use - 1) & 1u);
+      if (lane == 0) mbar_expect_tx(full + st, kTmaLevelTx);
+      __syncwarp();
+      if (lane < kTmaArrays)
+        tma_box_g2s(buf + (size_t) st * kTmaLevelD + lane * kTmaArrayD, &A.map[lane], xb,
+                    j0 - 1, kstart + n, full + st);
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int lx = tid & (kTmaTX - 1), ly = tid / kTmaTX;
+  const int i = xb + lx, j = j0 - 1 + ly;
+  // edges live inside the union of the three edge boxes (CT.cpp:548-556)
+  const bool ein = (i >= s && i < G.mx - s - 1 && j >= s && j < G.my - s - 1);
+  const bool own = ein && lx > 0 && lx < kTmaTX - 1 && ly > 0;
+  // faces this column updates (CT.cpp:646-667)
+  const bool fx_col = own && j >= s + 1;
+  const bool fy_col = own && i >= s + 1;
+  const bool fz_col = own && i >= s + 1 && j >= s + 1;
+  const double sdx = __ldg(A.sp), sdy = __ldg(A.sp + 1), sdz = __ldg(A.sp + 2);
+  const int o = ly * kTmaRowD + lx;
+  constexpr int AR = kTmaArrayD;
+  constexpr int Yo = kTmaRowD;
+  double ex_prev = 0., ey_prev = 0.;
+#pragma unroll 1
+  for (int k = kstart; k < kc1; k++) {
+    const int n = k - kstart;
+    const int st0 = n % kTmaStages, st1 = (n + 1) % kTmaStages;
+    const bool faces = (k >= kc0);              // not the warm-up level (block-uniform)
+    const bool xy_level = faces && (k > K0);    // k >= zlo; k < kend holds in the loop
+    const bool z_level = faces && (k + 1 < A.zhi);
+    // the faces' old values: issued before the edges are evaluated
+    double b0x = 0., b0y = 0., b0z = 0.;
+    size_t fxi = 0, fyi = 0, fzi = 0;
+    if (fx_col && xy_level) { fxi = fidx(G, 0, k, j, i + 1); b0x = __ldg(A.bi0[0] + fxi); }
+    if (fy_col && xy_level) { fyi = fidx(G, 1, k, j + 1, i); b0y = __ldg(A.bi0[1] + fyi); }
+    if (fz_col && z_level)  { fzi = fidx(G, 2, k + 1, j, i); b0z = __ldg(A.bi0[2] + fzi); }
+    mbar_wait(full + st0, (unsigned) (n / kTmaStages) & 1u);
+    mbar_wait(full + st1, (unsigned) ((n + 1) / kTmaStages) & 1u);
+    double ex = 0., ey = 0., ez = 0.;
+    if (ein) {
+      const double* const c0 = buf + (size_t) st0 * kTmaLevelD + o;   // level k
+      const double* const c1 = buf + (size_t) st1 * kTmaLevelD + o;   // level k+1
+#define VLCT_EX(p, d) ecen_((p)[TA_VY * AR + (d)], (p)[TA_BZ * AR + (d)], (p)[TA_VZ * AR + (d)], (p)[TA_BY * AR + (d)])
+#define VLCT_EY(p, d) ecen_((p)[TA_VZ * AR + (d)], (p)[TA_BX * AR + (d)], (p)[TA_VX * AR + (d)], (p)[TA_BZ * AR + (d)])
+#define VLCT_EZ(p, d) ecen_((p)[TA_VX * AR + (d)], (p)[TA_BY * AR + (d)], (p)[TA_VY * AR + (d)], (p)[TA_BX * AR + (d)])
+      const double wx0 = upwind_weight(c0[TA_RX * AR]), wxY = upwind_weight(c0[TA_RX * AR + Yo]),
+                   wxZ = upwind_weight(c1[TA_RX * AR]);
+      const double wy0 = upwind_weight(c0[TA_RY * AR]), wyZ = upwind_weight(c1[TA_RY * AR]),
+                   wyX = upwind_weight(c0[TA_RY * AR + 1]);
+      const double wz0 = upwind_weight(c0[TA_RZ * AR]), wzX = upwind_weight(c0[TA_RZ * AR + 1]),
+                   wzY = upwind_weight(c0[TA_RZ * AR + Yo]);
+      ex = edge_value(VLCT_EX(c0, 0), VLCT_EX(c0, Yo), VLCT_EX(c1, 0), VLCT_EX(c1, Yo),
+                      c0[TA_F12 * AR], c1[TA_F12 * AR], c0[TA_F21 * AR], c0[TA_F21 * AR + Yo],
+                      wy0, wyZ, wz0, wzY);
+      ey = edge_value(VLCT_EY(c0, 0), VLCT_EY(c1, 0), VLCT_EY(c0, 1), VLCT_EY(c1, 1),
+                      c0[TA_F20 * AR], c0[TA_F20 * AR + 1], c0[TA_F02 * AR], c1[TA_F02 * AR],
+                      wz0, wzX, wx0, wxZ);
+      ez = edge_value(VLCT_EZ(c0, 0), VLCT_EZ(c0, 1), VLCT_EZ(c0, Yo), VLCT_EZ(c0, Yo + 1),
+                      c0[TA_F01 * AR], c0[TA_F01 * AR + Yo], c0[TA_F10 * AR],
+                      c0[TA_F10 * AR + 1], wx0, wxY, wy0, wyX);
+#undef VLCT_EX
+#undef VLCT_EY
+#undef VLCT_EZ
+    }
+    // this warp is done with the stage of level k
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty + st0);
+    if (faces) {
+      X[0][ly][lx] = ex;
+      X[1][ly][lx] = ey;
+      X[2][ly][lx] = ez;
+      consumer_barrier();
+      if (fx_col && xy_level) {
+        // x face i+1: B -= dt/dy (E_z(j) - E_z(j-1)) - dt/dz (E_y(k) - E_y(k-1))
+        const double ez_jm = X[2][ly - 1][lx];
+        A.bi_out[0][fxi] = b0x - sdy * (ez - ez_jm) + sdz * (ey - ey_prev);
+      }
+      if (fy_col && xy_level) {
+        // y face j+1: B -= dt/dz (E_x(k) - E_x(k-1)) - dt/dx (E_z(i) - E_z(i-1))
+        const double ez_im = X[2][ly][lx - 1];
+        A.bi_out[1][fyi] = b0y - sdz * (ex - ex_prev) + sdx * (ez - ez_im);
+      }
+      if (fz_col && z_level) {
+        // z face k+1: B -= dt/dx (E_y(i) - E_y(i-1)) - dt/dy (E_x(j) - E_x(j-1))
+        const double ey_im = X[1][ly][lx - 1];
+        const double ex_jm = X[0][ly - 1][lx];
+        A.bi_out[2][fzi] = b0z - sdx * (ey - ey_im) + sdy * (ex - ex_jm);
+      }
+      consumer_barrier();    // the exchange buffer may be rewritten
+    }
+    ex_prev = ex;
+    ey_prev = ey;
   }
 }
 
@@ -1590,7 +1760,7 @@ struct Align16 {
 int default_pair_kernels()
 {
   const char* e = getenv("VLCT_PAIR_MASK");
-  return e ? (atoi(e) & 15) : 14;
+  return e ? (atoi(e) & 31) : 30;
 }
 
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
@@ -1616,6 +1786,54 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
   cudaStream_t st = ctx.st;
   const int m[3] = { G.mx, G.my, G.mz };
   const int block = kBlock;
+  if ((ctx.pair_mask & 16) && G.nrep == 1 && G.mx % 2 == 0 && z_face.hi > z_face.lo &&
+      z_edge.hi > z_edge.lo) {
+    // edge E + face B in one TMA-staged kernel (k_ct_tma). The faces of the
+    // face clip, the edges they need evaluated on the way: the pass tables of
+    // vlct_api.cu keep the inputs of those edges intact.
+    const double* in[kTmaArrays];
+    in[TA_VX] = cur.vx; in[TA_VY] = cur.vy; in[TA_VZ] = cur.vz;
+    in[TA_BX] = cur.bx; in[TA_BY] = cur.by; in[TA_BZ] = cur.bz;
+    in[TA_RX] = S.flux[0].rho; in[TA_RY] = S.flux[1].rho; in[TA_RZ] = S.flux[2].rho;
+    in[TA_F12] = S.flux[1].bz; in[TA_F21] = S.flux[2].by; in[TA_F20] = S.flux[2].bx;
+    in[TA_F02] = S.flux[0].bz; in[TA_F01] = S.flux[0].by; in[TA_F10] = S.flux[1].bx;
+    Align16 al;
+    for (int a = 0; a < kTmaArrays; a++) al(in[a]);
+    CtTmaArgs T;
+    bool ok = al.ok;
+    for (int a = 0; a < kTmaArrays && ok; a++)
+      ok = tensor_map_for(in[a], G.mx, G.my, G.mz, &T.map[a]);
+    if (ok) {
+      const int zlo = (s + 1 > z_face.lo) ? s + 1 : z_face.lo;
+      const int zhi = (G.mz - s < z_face.hi) ? G.mz - s : z_face.hi;
+      const int kend = (G.mz - s - 1 < z_face.hi) ? G.mz - s - 1 : z_face.hi;
+      const int K0 = zlo - 1;
+      const int ncx = G.mx - 2 * s - 1, ncy = G.my - 2 * s - 1;
+      if (kend <= K0 || ncx <= 0 || ncy <= 0) return;
+      for (int d = 0; d < 3; d++) { T.bi0[d] = bi0.bi[d]; T.bi_out[d] = bi_out.bi[d]; }
+      T.sp = step_params;
+      T.s = s; T.zlo = zlo; T.zhi = zhi; T.kend = kend;
+      const int nk = kend - K0;
+      int chunk = 64;
+      if (nk < 2 * chunk) chunk = nk;
+      // (columns from ((s - 1) & ~1) + 1 on, 62 per block: see the kernel)
+      const int xfirst = ((s - 1) & ~1) + 1;
+      const dim3 grid((unsigned) ((G.mx - s - 1 - xfirst + kTmaTX - 3) / (kTmaTX - 2)),
+                      (unsigned) ((ncy + kTmaTY - 2) / (kTmaTY - 1)),
+                      (unsigned) ((nk + chunk - 1) / chunk));
+      static bool smem_set[64] = {};
+      int device = 0;
+      cudaGetDevice(&device);
+      if (device < 0 || device >= 64 || !smem_set[device]) {
+        cudaFuncSetAttribute(k_ct_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) kCtSmemBytes);
+        if (device >= 0 && device < 64) smem_set[device] = true;
+      }
+      ScopedLaunch sl(ctx, "k_ct_tma");
+      k_ct_tma<<<grid, kTmaThreads, kCtSmemBytes, st>>>(lite(G), T, chunk);
+      return;
+    }
+  }
   {
     EdgeArgs A;
     A.v[0] = cur.vx; A.v[1] = cur.vy; A.v[2] = cur.vz;

@@ -100,14 +100,17 @@ struct LaunchCtx {
   Profiler* prof;
   // which cell kernels run as pair kernels (two x-cells per thread, 128-bit
   // accesses): bit 0 edge E, bit 1 face B, bit 2 update; bit 3: edge E of a
-  // single block with TMA-staged inputs (option "pair_kernels")
-  int pair_mask = 14;
+  // single block with TMA-staged inputs; bit 4: edge E + face B of a single
+  // block in one TMA-staged kernel, which then replaces both (option
+  // "pair_kernels")
+  int pair_mask = 30;
 };
 
-/// default of the option "pair_kernels": TMA-staged edge E, face B and update
-/// as pair kernels (measured, DESIGN.md 4.3: -22 %, -9 % and -3 %; the edge-E
-/// pair kernel executes 26 % fewer instructions but needs 128 registers, holds
-/// a third of the warps and is 3 % slower);
+/// default of the option "pair_kernels": the fused TMA-staged CT kernel, and
+/// where it does not apply the TMA-staged edge E, face B and update as pair
+/// kernels (measured; the edge-E pair kernel executes 26 % fewer
+/// instructions but needs 128 registers, holds a third of the warps and is
+/// 3 % slower);
 /// VLCT_PAIR_MASK in the environment overrides it for A/B runs
 int default_pair_kernels();
 

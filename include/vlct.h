@@ -347,12 +347,14 @@ int vlct_host_unregister(vlct_handle *h, void *ptr);
  *        face B, update as pair kernels (a thread owns two x-neighbours and
  *        moves them with 128-bit loads / stores). Bit 3: edge E of a single
  *        block with its inputs staged by the TMA unit (cp.async.bulk.tensor
- *        boxes, a producer warp and 16 consumer warps over mbarriers). All need
- *        an even row length mx and 16-byte aligned arrays, else the one-cell
- *        kernels run. Default 14. Measured at 512^3: TMA-staged edge E 4.45 ->
- *        3.46 ms per launch (95 % of the HBM peak), face-B pair kernel -9 %,
- *        update -3 %; the edge-E pair kernel (bit 0) is 3 % slower than the
- *        one-cell kernel.
+ *        boxes, a producer warp and 16 consumer warps over mbarriers). Bit 4:
+ *        edge E and face B of a single block in one such kernel (the edge E
+ *        stay on chip); it replaces both. All need an even row length mx and
+ *        16-byte aligned arrays, else the one-cell kernels run. Default 30.
+ *        Measured at 512^3 per stage: edge E 4.45 -> 3.46 ms TMA-staged (86 %
+ *        of the HBM peak on algorithmic bytes), edge E + face B 6.0 -> 4.8 ms
+ *        fused, face-B pair kernel -9 %, update -3 %; the edge-E pair kernel
+ *        (bit 0) is 3 % slower than the one-cell kernel.
  *   "device_pipeline_levels" run VLCT_MEM_DEVICE steps in passes of n levels
  *        too (0 = off, default; a test hook for the pass machinery). */
 int vlct_set_option(vlct_handle *h, const char *key, long long value);
