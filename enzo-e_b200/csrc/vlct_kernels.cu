@@ -1814,7 +1814,11 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
       T.sp = step_params;
       T.s = s; T.zlo = zlo; T.zhi = zhi; T.kend = kend;
       const int nk = kend - K0;
-      int chunk = 64;
+      static const int chunk_default = [] {
+        const char* e = getenv("VLCT_CT_CHUNK");      // A/B runs
+        return (e && atoi(e) > 0) ? atoi(e) : 64;
+      }();
+      int chunk = chunk_default;
       if (nk < 2 * chunk) chunk = nk;
       // (columns from ((s - 1) & ~1) + 1 on, 62 per block: see the kernel)
       const int xfirst = ((s - 1) & ~1) + 1;

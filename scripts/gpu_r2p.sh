@@ -16,8 +16,8 @@ if [ "${NCU_LIST:-1}" = 1 ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 300 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
 fi
 if [ "${NCU_FULL:-1}" = 1 ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_edge_efield_tma -s 2 -c 2 -o gpurun_out/prof_edge_tma_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-ncu -i gpurun_out/prof_edge_tma_$TAG.ncu-rep --page details --csv > gpurun_out/ncu_full_edge_tma_$TAG.csv 2>/dev/null
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_ct_tma} -s 2 -c 2 -o gpurun_out/prof_${NCU_KERNEL:-k_ct_tma}_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+ncu -i gpurun_out/prof_${NCU_KERNEL:-k_ct_tma}_$TAG.ncu-rep --page details --csv > gpurun_out/ncu_full_${NCU_KERNEL:-k_ct_tma}_$TAG.csv 2>/dev/null
 fi
 python - <<PY
 import json
