@@ -1545,7 +1545,7 @@ int vlct_set_option(vlct_handle* h, const char* key, long long value)
       }
     }
   } else if (strcmp(key, "pair_kernels") == 0) {
-    if (value < 0 || value > 31) return fail(h, VLCT_ERR_INVALID_CONFIG, "pair_kernels in 0..31");
+    if (value < 0 || value > 63) return fail(h, VLCT_ERR_INVALID_CONFIG, "pair_kernels in 0..63");
     h->pair_kernels = (int) value;
   } else if (strcmp(key, "debug_kernel_mask") == 0) {
     h->debug_kernel_mask = value;

@@ -1750,6 +1750,33 @@ bool tensor_map_for(const double* p, int mx, int my, int mz, CUtensorMap* out)
   return true;
 }
 
+/// The TMA-staged kernels keep one block per SM busy for a whole z chunk:
+/// blocks of a launch = tiles x chunks. Small blocks of cells do not fill the
+/// chip with them and keep the one-cell / pair kernels. The criterion uses the
+/// block's full depth, never the clipped range of a launch: all z passes of a
+/// step must take the same path (the fused kernel writes no edge arrays).
+bool tma_tiles_fill_chip(long long tiles, int mz, bool force)
+{
+  if (force) return true;       // option "pair_kernels" bit 5 (tests)
+  static const long long min_blocks = [] {
+    const char* e = getenv("VLCT_TMA_MIN_BLOCKS");    // A/B runs
+    return (e && atoll(e) >= 0) ? atoll(e) : 148LL;
+  }();
+  return tiles * ((mz + 15) / 16) >= min_blocks;
+}
+
+/// z chunk of a TMA-staged launch over nk levels: about two waves of blocks,
+/// 16..64 levels per chunk (a chunk costs one or two extra levels)
+int tma_chunk(long long tiles, int nk)
+{
+  const long long want = (296 + tiles - 1) / tiles;       // chunks for two waves
+  long long chunk = nk / (want > 0 ? want : 1);
+  if (chunk > 64) chunk = 64;
+  if (chunk < 16) chunk = 16;
+  if (nk < 2 * chunk) chunk = nk;
+  return (int) chunk;
+}
+
 struct Align16 {
   bool ok = true;
   void operator()(const void* p) { if (((uintptr_t) p & 15u) != 0) ok = false; }
@@ -1760,7 +1787,7 @@ struct Align16 {
 int default_pair_kernels()
 {
   const char* e = getenv("VLCT_PAIR_MASK");
-  return e ? (atoi(e) & 31) : 30;
+  return e ? (atoi(e) & 63) : 30;
 }
 
 void launch_primitives(const LaunchCtx& ctx, const Params& P, const Geom& G,
@@ -1800,7 +1827,10 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
     Align16 al;
     for (int a = 0; a < kTmaArrays; a++) al(in[a]);
     CtTmaArgs T;
-    bool ok = al.ok;
+    bool ok = al.ok &&
+              tma_tiles_fill_chip((long long) ((G.mx - 2 * s + kTmaTX - 3) / (kTmaTX - 2)) *
+                                  ((G.my - 2 * s - 1 + kTmaTY - 2) / (kTmaTY - 1)), G.mz,
+                                  (ctx.pair_mask & 32) != 0);
     for (int a = 0; a < kTmaArrays && ok; a++)
       ok = tensor_map_for(in[a], G.mx, G.my, G.mz, &T.map[a]);
     if (ok) {
@@ -1814,17 +1844,12 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
       T.sp = step_params;
       T.s = s; T.zlo = zlo; T.zhi = zhi; T.kend = kend;
       const int nk = kend - K0;
-      static const int chunk_default = [] {
-        const char* e = getenv("VLCT_CT_CHUNK");      // A/B runs
-        return (e && atoi(e) > 0) ? atoi(e) : 64;
-      }();
-      int chunk = chunk_default;
-      if (nk < 2 * chunk) chunk = nk;
       // (columns from ((s - 1) & ~1) + 1 on, 62 per block: see the kernel)
       const int xfirst = ((s - 1) & ~1) + 1;
-      const dim3 grid((unsigned) ((G.mx - s - 1 - xfirst + kTmaTX - 3) / (kTmaTX - 2)),
-                      (unsigned) ((ncy + kTmaTY - 2) / (kTmaTY - 1)),
-                      (unsigned) ((nk + chunk - 1) / chunk));
+      const unsigned gx = (unsigned) ((G.mx - s - 1 - xfirst + kTmaTX - 3) / (kTmaTX - 2));
+      const unsigned gy = (unsigned) ((ncy + kTmaTY - 2) / (kTmaTY - 1));
+      const int chunk = tma_chunk((long long) gx * gy, nk);
+      const dim3 grid(gx, gy, (unsigned) ((nk + chunk - 1) / chunk));
       static bool smem_set[64] = {};
       int device = 0;
       cudaGetDevice(&device);
@@ -1863,7 +1888,10 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
         al(A.v[d]); al(A.b[d]); al(A.frho[d]); al(A.edge[d]);
         for (int q = 0; q < 3; q++) if (q != d) al(A.fb[d][q]);
       }
-      bool use_tma = (ctx.pair_mask & 8) && G.nrep == 1 && G.mx % 2 == 0 && al.ok;
+      bool use_tma = (ctx.pair_mask & 8) && G.nrep == 1 && G.mx % 2 == 0 && al.ok &&
+                     tma_tiles_fill_chip((long long) ((G.mx - 2 * s + kTmaTX - 1) / kTmaTX) *
+                                         ((G.my - 2 * s - 1 + kTmaTY - 1) / kTmaTY), G.mz,
+                                         (ctx.pair_mask & 32) != 0);
       EdgeTmaArgs T;
       if (use_tma) {
         // inputs staged by TMA boxes (k_edge_efield_tma); without the driver's
@@ -1881,12 +1909,11 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
         for (int d = 0; d < 3; d++) T.edge[d] = A.edge[d];
         T.s = s; T.k0 = box.lo[2]; T.kend = box.hi[2];
         const int nk = box.hi[2] - box.lo[2];
-        int chunk = 64;
-        if (nk < 2 * chunk) chunk = nk;
         const int x0 = s & ~1;
-        const dim3 grid((unsigned) ((G.mx - s - 1 - x0 + kTmaTX - 1) / kTmaTX),
-                        (unsigned) ((G.my - 2 * s - 1 + kTmaTY - 1) / kTmaTY),
-                        (unsigned) ((nk + chunk - 1) / chunk));
+        const unsigned gx = (unsigned) ((G.mx - s - 1 - x0 + kTmaTX - 1) / kTmaTX);
+        const unsigned gy = (unsigned) ((G.my - 2 * s - 1 + kTmaTY - 1) / kTmaTY);
+        const int chunk = tma_chunk((long long) gx * gy, nk);
+        const dim3 grid(gx, gy, (unsigned) ((nk + chunk - 1) / chunk));
         static bool smem_set[64] = {};
         int device = 0;
         cudaGetDevice(&device);

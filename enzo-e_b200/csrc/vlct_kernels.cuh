@@ -101,8 +101,9 @@ struct LaunchCtx {
   // which cell kernels run as pair kernels (two x-cells per thread, 128-bit
   // accesses): bit 0 edge E, bit 1 face B, bit 2 update; bit 3: edge E of a
   // single block with TMA-staged inputs; bit 4: edge E + face B of a single
-  // block in one TMA-staged kernel, which then replaces both (option
-  // "pair_kernels")
+  // block in one TMA-staged kernel, which then replaces both; bit 5: the
+  // TMA-staged kernels also for blocks too small to fill the chip with their
+  // tiles (tests) (option "pair_kernels")
   int pair_mask = 30;
 };
 

@@ -255,8 +255,9 @@ def test_pair_kernels_option_is_bit_neutral(name, shape):
     """The cell kernels as pair kernels (two x-cells per thread, 128-bit loads
     and stores: option "pair_kernels", bit 0 edge E, 1 face B, 2 update), the
     edge E with TMA-staged inputs (bit 3: tiles of 64 x 8 cells marching along
-    z), edge E + face B in one TMA-staged kernel (bit 4) and the one-cell
-    kernels give the oracle's bits -- fields, ghost zones, every dt,
+    z), edge E + face B in one TMA-staged kernel (bit 4; bit 5 makes small
+    blocks take the TMA-staged kernels too) and the one-cell kernels give the
+    oracle's bits -- fields, ghost zones, every dt,
     with the CFL fold (compute_and_timestep) and without. Odd row lengths fall
     back to the one-cell kernels."""
     import torch
@@ -265,7 +266,7 @@ def test_pair_kernels_option_is_bit_neutral(name, shape):
     n, g, d = shape, (3, 3, 3), (0.1, 0.12, 0.09)
     host = random_state(cfg, n, g, seed=11)
     want, dts_want = run_cpu(cfg, host, n, g, d, 3)
-    for mask in (0, 7, 14, 9, 30):
+    for mask in (0, 7, 14 + 32, 9 + 32, 30 + 32, 30):
         for fused in (False, True):
             method = EnzoMethodMHDVlct(config=cfg)
             method.set_option("pair_kernels", mask)
