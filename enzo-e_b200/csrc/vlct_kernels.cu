@@ -758,9 +758,9 @@ k_edge_efield2(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const 
 
 // ---------------------------------------------------------------------------
 // Edge E with its inputs staged by the TMA unit (cp.async.bulk.tensor, SASS
-// UTMALDG): a block owns a tile of 64 x 8 cells and marches along z. A
+// UTMALDG): a block owns a tile of 32 x 16 cells and marches along z. A
 // producer warp asks the TMA unit for what the next level needs -- one box of
-// 9 rows x 66 doubles from each of the 15 input arrays, completion counted on
+// 17 rows x 34 doubles from each of the 15 input arrays, completion counted on
 // an mbarrier -- up to three levels ahead; the 16 consumer warps read
 // everything from shared memory at immediate offsets and hand a level's stage
 // back through a second mbarrier (no block-wide barrier). The loads in flight are no longer
@@ -773,21 +773,30 @@ k_edge_efield2(const typename GeomFor<STACKED>::type G, const EdgeArgs A, const 
 __device__ __forceinline__ double ecen_(double vj, double bk, double vk, double bj)
 { return (-vj * bk + vk * bj); }
 
-constexpr int kTmaTX = 64, kTmaTY = 8;
+#ifndef VLCT_TMA_TX
+#define VLCT_TMA_TX 32
+#endif
+#ifndef VLCT_TMA_TY
+#define VLCT_TMA_TY 16
+#endif
+#ifndef VLCT_TMA_STAGES
+#define VLCT_TMA_STAGES 3
+#endif
+constexpr int kTmaTX = VLCT_TMA_TX, kTmaTY = VLCT_TMA_TY;
 constexpr int kTmaRows = kTmaTY + 1;        // rows a level needs: +1 for the +y neighbours
 constexpr int kTmaRowD = kTmaTX + 2;        // doubles per row: +1 for +x, +1 keeps 16 bytes
 constexpr int kTmaArrays = 15;
-// one staged array = one TMA box of 9 rows x 66 doubles, padded to a multiple
+// one staged array = one TMA box of (TY + 1) rows x (TX + 2) doubles, padded to a multiple
 // of 128 bytes (destination alignment of cp.async.bulk.tensor)
 constexpr int kTmaArrayD = ((kTmaRows * kTmaRowD * 8 + 127) / 128) * 128 / 8;
 constexpr int kTmaLevelD = kTmaArrays * kTmaArrayD;            // doubles per level buffer
 constexpr unsigned kTmaLevelTx = kTmaArrays * kTmaRows * kTmaRowD * 8;   // bytes that land
-constexpr int kTmaStages = 3;
-constexpr size_t kTmaSmemBytes = (size_t) kTmaStages * kTmaLevelD * sizeof(double) + 64;
+constexpr int kTmaStages = VLCT_TMA_STAGES;
+constexpr size_t kTmaSmemBytes = (size_t) kTmaStages * kTmaLevelD * sizeof(double) + 128;
 enum { TA_VX = 0, TA_VY, TA_VZ, TA_BX, TA_BY, TA_BZ, TA_RX, TA_RY, TA_RZ,
        TA_F12, TA_F21, TA_F20, TA_F02, TA_F01, TA_F10 };
 struct EdgeTmaArgs {
-  // (x, y, z) tensor maps of the 15 input arrays, box 66 x 9 x 1, zero fill
+  // (x, y, z) tensor maps of the 15 input arrays, box (TX + 2) x (TY + 1) x 1, zero fill
   // outside the array
   alignas(64) CUtensorMap map[kTmaArrays];
   double* edge[3];
@@ -944,9 +953,9 @@ k_edge_efield_tma(const GeomLite G, const __grid_constant__ EdgeTmaArgs A, const
 // the three edge E of its cell at level k, publishes them in shared memory,
 // and updates the x face on its +x side, the y face on its +y side (they need
 // E_y / E_x of level k-1: kept in registers) and the z face above it; the
-// edges of the -x / -y neighbours come from shared memory. A block is 64 x 8
-// columns of which 62 x 7 update faces (column 0 and row 0 only provide the
-// neighbours' edges). Same expressions in the same order as k_edge_efield +
+// edges of the -x / -y neighbours come from shared memory. A block is 32 x 16
+// columns of which 30 x 15 update faces (column 0 and row 0 only provide the
+// neighbours' edges; measured against 64 x 8: 8.95 vs 9.23 ms per step). Same expressions in the same order as k_edge_efield +
 // k_face_bfield: bit-identical.
 // ---------------------------------------------------------------------------
 struct CtTmaArgs {
@@ -961,7 +970,7 @@ struct CtTmaArgs {
 };
 constexpr size_t kCtExchBytes = (size_t) 3 * kTmaTY * kTmaTX * sizeof(double);
 constexpr size_t kCtSmemBytes = (size_t) kTmaStages * kTmaLevelD * sizeof(double) +
-                                kCtExchBytes + 64;
+                                kCtExchBytes + 128;
 
 __device__ __forceinline__ void consumer_barrier()
 { asm volatile("bar.sync 1, %0;" :: "n"(kTmaConsumers) : "memory"); }
@@ -980,8 +989,8 @@ k_ct_tma(const GeomLite G, const __grid_constant__ CtTmaArgs A, const int chunk)
   const int s = A.s;
   // column (0, 0) of the block is cell (xb, j0 - 1). The x coordinate of a TMA
   // box must be even (16-byte granularity along the contiguous axis), so a
-  // block advances by 62 columns: columns 1..62 update faces, column 0 and
-  // row 0 only provide the neighbours' edges.
+  // block advances by TX - 2 columns: columns 1..TX-2 update faces, column 0
+  // and row 0 only provide the neighbours' edges.
   const int xb = ((s - 1) & ~1) + (kTmaTX - 2) * (int) blockIdx.x;
   const int j0 = s + (kTmaTY - 1) * (int) blockIdx.y;
   // levels of this chunk; one warm-up level below it provides E_x, E_y of k-1
@@ -1029,6 +1038,25 @@ k_ct_tma(const GeomLite G, const __grid_constant__ CtTmaArgs A, const int chunk)
   constexpr int AR = kTmaArrayD;
   constexpr int Yo = kTmaRowD;
   double ex_prev = 0., ey_prev = 0.;
+#define VLCT_EX(p, d) ecen_((p)[TA_VY * AR + (d)], (p)[TA_BZ * AR + (d)], (p)[TA_VZ * AR + (d)], (p)[TA_BY * AR + (d)])
+#define VLCT_EY(p, d) ecen_((p)[TA_VZ * AR + (d)], (p)[TA_BX * AR + (d)], (p)[TA_VX * AR + (d)], (p)[TA_BZ * AR + (d)])
+#define VLCT_EZ(p, d) ecen_((p)[TA_VX * AR + (d)], (p)[TA_BY * AR + (d)], (p)[TA_VY * AR + (d)], (p)[TA_BX * AR + (d)])
+  // What level k shares with the "+z" rows of level k-1 is carried from one
+  // iteration to the next (47 shared-memory reads per cell and level instead
+  // of 69: the consumers are bound by shared-memory bandwidth)
+  double EX0 = 0., EXY = 0., EY0 = 0., EY1 = 0., f12_0 = 0., f02_0 = 0., wx0 = 0., wy0 = 0.;
+  mbar_wait(full + 0, 0u);
+  if (ein) {
+    const double* const c0 = buf + o;           // level kstart sits in stage 0
+    EX0 = VLCT_EX(c0, 0);
+    EXY = VLCT_EX(c0, Yo);
+    EY0 = VLCT_EY(c0, 0);
+    EY1 = VLCT_EY(c0, 1);
+    f12_0 = c0[TA_F12 * AR];
+    f02_0 = c0[TA_F02 * AR];
+    wx0 = upwind_weight(c0[TA_RX * AR]);
+    wy0 = upwind_weight(c0[TA_RY * AR]);
+  }
 #pragma unroll 1
   for (int k = kstart; k < kc1; k++) {
     const int n = k - kstart;
@@ -1048,27 +1076,29 @@ k_ct_tma(const GeomLite G, const __grid_constant__ CtTmaArgs A, const int chunk)
     if (ein) {
       const double* const c0 = buf + (size_t) st0 * kTmaLevelD + o;   // level k
       const double* const c1 = buf + (size_t) st1 * kTmaLevelD + o;   // level k+1
-#define VLCT_EX(p, d) ecen_((p)[TA_VY * AR + (d)], (p)[TA_BZ * AR + (d)], (p)[TA_VZ * AR + (d)], (p)[TA_BY * AR + (d)])
-#define VLCT_EY(p, d) ecen_((p)[TA_VZ * AR + (d)], (p)[TA_BX * AR + (d)], (p)[TA_VX * AR + (d)], (p)[TA_BZ * AR + (d)])
-#define VLCT_EZ(p, d) ecen_((p)[TA_VX * AR + (d)], (p)[TA_BY * AR + (d)], (p)[TA_VY * AR + (d)], (p)[TA_BX * AR + (d)])
-      const double wx0 = upwind_weight(c0[TA_RX * AR]), wxY = upwind_weight(c0[TA_RX * AR + Yo]),
-                   wxZ = upwind_weight(c1[TA_RX * AR]);
-      const double wy0 = upwind_weight(c0[TA_RY * AR]), wyZ = upwind_weight(c1[TA_RY * AR]),
-                   wyX = upwind_weight(c0[TA_RY * AR + 1]);
+      // level k+1: E_x on the rows 0, +y; E_y at x, x+1; two fluxes, two weights
+      const double vzZ = c1[TA_VZ * AR], bzZ = c1[TA_BZ * AR];
+      const double EXZ = ecen_(c1[TA_VY * AR], bzZ, vzZ, c1[TA_BY * AR]);
+      const double EXW = VLCT_EX(c1, Yo);
+      const double EYZ = ecen_(vzZ, c1[TA_BX * AR], c1[TA_VX * AR], bzZ);
+      const double EYZ1 = VLCT_EY(c1, 1);
+      const double f12_Z = c1[TA_F12 * AR], f02_Z = c1[TA_F02 * AR];
+      const double wxZ = upwind_weight(c1[TA_RX * AR]);
+      const double wyZ = upwind_weight(c1[TA_RY * AR]);
+      // level k only: E_z at (x, x+1) x (y, y+1), the other fluxes and weights
+      const double wxY = upwind_weight(c0[TA_RX * AR + Yo]);
+      const double wyX = upwind_weight(c0[TA_RY * AR + 1]);
       const double wz0 = upwind_weight(c0[TA_RZ * AR]), wzX = upwind_weight(c0[TA_RZ * AR + 1]),
                    wzY = upwind_weight(c0[TA_RZ * AR + Yo]);
-      ex = edge_value(VLCT_EX(c0, 0), VLCT_EX(c0, Yo), VLCT_EX(c1, 0), VLCT_EX(c1, Yo),
-                      c0[TA_F12 * AR], c1[TA_F12 * AR], c0[TA_F21 * AR], c0[TA_F21 * AR + Yo],
+      ex = edge_value(EX0, EXY, EXZ, EXW, f12_0, f12_Z, c0[TA_F21 * AR], c0[TA_F21 * AR + Yo],
                       wy0, wyZ, wz0, wzY);
-      ey = edge_value(VLCT_EY(c0, 0), VLCT_EY(c1, 0), VLCT_EY(c0, 1), VLCT_EY(c1, 1),
-                      c0[TA_F20 * AR], c0[TA_F20 * AR + 1], c0[TA_F02 * AR], c1[TA_F02 * AR],
+      ey = edge_value(EY0, EYZ, EY1, EYZ1, c0[TA_F20 * AR], c0[TA_F20 * AR + 1], f02_0, f02_Z,
                       wz0, wzX, wx0, wxZ);
       ez = edge_value(VLCT_EZ(c0, 0), VLCT_EZ(c0, 1), VLCT_EZ(c0, Yo), VLCT_EZ(c0, Yo + 1),
                       c0[TA_F01 * AR], c0[TA_F01 * AR + Yo], c0[TA_F10 * AR],
                       c0[TA_F10 * AR + 1], wx0, wxY, wy0, wyX);
-#undef VLCT_EX
-#undef VLCT_EY
-#undef VLCT_EZ
+      EX0 = EXZ; EXY = EXW; EY0 = EYZ; EY1 = EYZ1;
+      f12_0 = f12_Z; f02_0 = f02_Z; wx0 = wxZ; wy0 = wyZ;
     }
     // this warp is done with the stage of level k
     __syncwarp();
@@ -1099,6 +1129,9 @@ k_ct_tma(const GeomLite G, const __grid_constant__ CtTmaArgs A, const int chunk)
     ex_prev = ex;
     ey_prev = ey;
   }
+#undef VLCT_EX
+#undef VLCT_EY
+#undef VLCT_EZ
 }
 
 template <bool STACKED>
@@ -1706,7 +1739,7 @@ void Profiler::reset()
 namespace {
 
 /// 3-D tensor map (x fastest) of a cell-strided fp64 array for boxes of
-/// 66 x 9 x 1 elements; cached per (pointer, shape). False if the driver entry
+/// (TX + 2) x (TY + 1) x 1 elements; cached per (pointer, shape). False if the driver entry
 /// point is missing or the encode fails.
 bool tensor_map_for(const double* p, int mx, int my, int mz, CUtensorMap* out)
 {
@@ -1844,7 +1877,7 @@ void launch_ct(const LaunchCtx& ctx, const Params& P, const Geom& G,
       T.sp = step_params;
       T.s = s; T.zlo = zlo; T.zhi = zhi; T.kend = kend;
       const int nk = kend - K0;
-      // (columns from ((s - 1) & ~1) + 1 on, 62 per block: see the kernel)
+      // (columns from ((s - 1) & ~1) + 1 on, TX - 2 per block: see the kernel)
       const int xfirst = ((s - 1) & ~1) + 1;
       const unsigned gx = (unsigned) ((G.mx - s - 1 - xfirst + kTmaTX - 3) / (kTmaTX - 2));
       const unsigned gy = (unsigned) ((ncy + kTmaTY - 2) / (kTmaTY - 1));
