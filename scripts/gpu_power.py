@@ -55,7 +55,8 @@ def main():
     n, width = (size,) * 3, (1.0 / size,) * 3
     stream = torch.cuda.Stream(device=dev)
     K = {"scal": 1, "flux_xy": 2, "flux_z": 4, "edge": 8, "face": 16, "update": 32}
-    families = {"all": 63, "flux": 6, "cell": 56, "edge": 8, "face": 16, "update": 32,
+    # ("ct": edge + face together take the fused TMA-staged kernel, k_ct_tma)
+    families = {"all": 63, "flux": 6, "cell": 56, "ct": 24, "edge": 8, "face": 16, "update": 32,
                 "flux_xy": 2, "flux_z": 4}
     with torch.cuda.stream(stream):
         fields = problems.orszag_tang(n, GHOST, (0, 0, 0), width, device=dev)

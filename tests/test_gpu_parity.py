@@ -249,8 +249,10 @@ def test_scalar_flux_arrays_option_is_bit_neutral(name):
                                   "mhd_hlld_gravity_de_eta0", "hd_hllc_plm",
                                   "hd_hllc_gravity", "mhd_hlld_plm_de_floors",
                                   "hd_hllc_euler_floors", "mhd_hlld_plm_scalars"])
-@pytest.mark.parametrize("shape", [(20, 12, 10), (19, 12, 10), (8, 8, 8), (70, 20, 6)],
-                         ids=["even", "odd_falls_back", "cube8", "several_tiles"])
+@pytest.mark.parametrize("shape", [(20, 12, 10), (19, 12, 10), (8, 8, 8), (70, 20, 6),
+                                   (60, 26, 48)],
+                         ids=["even", "odd_falls_back", "cube8", "several_tiles",
+                              "tiles_and_chunks"])
 def test_pair_kernels_option_is_bit_neutral(name, shape):
     """The cell kernels as pair kernels (two x-cells per thread, 128-bit loads
     and stores: option "pair_kernels", bit 0 edge E, 1 face B, 2 update), the
@@ -259,7 +261,8 @@ def test_pair_kernels_option_is_bit_neutral(name, shape):
     blocks take the TMA-staged kernels too) and the one-cell kernels give the
     oracle's bits -- fields, ghost zones, every dt,
     with the CFL fold (compute_and_timestep) and without. Odd row lengths fall
-    back to the one-cell kernels."""
+    back to the one-cell kernels; the last shape gives the TMA-staged kernels
+    3 x 3 tiles and four z chunks (warm-up levels, tile and chunk boundaries)."""
     import torch
     from enzo_e_b200.method import EnzoMethodMHDVlct, Block
     cfg = make_config(**{**CASES, **FLOOR_CASES}[name])
