@@ -351,8 +351,8 @@ int vlct_host_unregister(vlct_handle *h, void *ptr);
  *        edge E and face B of a single block in one such kernel (the edge E
  *        stay on chip); it replaces both. All need an even row length mx and
  *        16-byte aligned arrays, else the one-cell kernels run; the TMA-staged
- *        kernels also need a block whose 30 x 15 tiles fill the chip (about
- *        128^3 cells; bit 5 lifts that, for tests). Default 30.
+ *        kernels also need a block whose 30 x 15 tiles fill the chip (from about
+ *        96^3 cells; bit 5 lifts that, for tests). Default 30.
  *        Measured at 512^3 per stage: edge E 4.45 -> 3.46 ms TMA-staged (86 %
  *        of the HBM peak on algorithmic bytes), edge E + face B 6.0 -> 4.8 ms
  *        fused, face-B pair kernel -9 %, update -3 %; the edge-E pair kernel
